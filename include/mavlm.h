@@ -1,0 +1,104 @@
+/* mavlm.h -- C ABI of the B200 (sm_100a) visual-memory path.
+ *
+ * Drop-in boundary for the hot path of 1023604540/Memory-Augmented-VLM:
+ *   mm_projector -> get_2dPool (bilinear 27x27->14x14) -> temporal PE -> chunked recurrent
+ *   memory (formation + evolution) -> memory fuser -> token assembly.
+ * The reference has no FFI of its own: its boundary is a set of Python nn.Module call sites
+ * (llava/model/llava_arch.py:302, 495, 511, 530-537, 546, 550-551).  Each entry point below
+ * names the reference call site it replaces; the Python host in
+ * `memory-augmented-vlm_b200/` keeps the reference module signatures / state_dict keys and
+ * binds these symbols with ctypes.
+ *
+ * Conventions
+ *   - plain C: pointers are CUDA device pointers unless named host_*; sizes are element counts.
+ *   - `stream` is a cudaStream_t passed as void* (the caller's current stream); nothing in this
+ *     library synchronises, allocates persistent device memory, throws, or calls exit().
+ *   - return value: 0 on success, negative MAVLM_E_* otherwise; mavlm_last_error_string() gives
+ *     the message for the calling thread.
+ *   - dtype: MAVLM_F32 runs the exact fp32 SIMT tier (parity <= 1e-5 vs the fp64 oracle),
+ *     MAVLM_BF16 runs the TMA + tcgen05/TMEM tier (bf16 operands, fp32 accumulate/softmax/LN).
+ *   - there is no CPU fallback and no other-architecture path: a non-sm_100 device is an error.
+ */
+#ifndef MAVLM_H_
+#define MAVLM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAVLM_VERSION 100 /* 0.1.0 */
+#define MAVLM_API __attribute__((visibility("default")))
+
+enum { MAVLM_F32 = 0, MAVLM_BF16 = 1 };
+enum { MAVLM_ACT_NONE = 0, MAVLM_ACT_GELU_ERF = 1, MAVLM_ACT_RELU = 2 };
+enum { MAVLM_POOL_BILINEAR = 0, MAVLM_POOL_AVERAGE = 1, MAVLM_POOL_MAX = 2 };
+enum {
+  MAVLM_OK = 0,
+  MAVLM_E_INVALID = -1,  /* bad argument (shape / alignment / dtype)            */
+  MAVLM_E_CUDA = -2,     /* CUDA runtime / driver error (launch failure, ...)    */
+  MAVLM_E_ARCH = -3,     /* device is not sm_100 (B200)                          */
+  MAVLM_E_INDEX = -4,    /* index out of range (PE frame index), host-validated  */
+  MAVLM_E_WORKSPACE = -5 /* workspace too small                                   */
+};
+
+MAVLM_API int mavlm_version(void);
+MAVLM_API const char* mavlm_last_error_string(void);
+/* Verifies that `device` is compute capability 10.x; MAVLM_E_ARCH otherwise. */
+MAVLM_API int mavlm_check_device(int device);
+
+/* ---- a2 + a3: get_2dPool (llava_arch.py:277-297) fused with TemporalPositionalEncoding
+ * (position_encoding.py:57-64).  x [F, side*side, D] -> y [F, out_side*out_side, D];
+ * bilinear, align_corners=False.  pe_table (fp32 [max_frames, D]) and frame_idx (int64 [F], device)
+ * may both be NULL for pooling alone.  Indices are validated by the caller on the host
+ * (position_encoding.py:73-76 raises ValueError there).  mode average/max are the reference's two
+ * other (shape-incompatible downstream) modes with kernel = stride. */
+MAVLM_API int mavlm_pool_pe_fwd(const void* x, void* y, const float* pe_table, const int64_t* frame_idx, int frames, int side,
+                      int out_side, int stride, int dim, int mode, int dtype, void* stream);
+
+/* ---- a3 alone: x [T, N, C] + pe_table[frame_idx[t]] cast to dtype (position_encoding.py:57-64). */
+MAVLM_API int mavlm_add_pe_fwd(const void* x, void* y, const float* pe_table, const int64_t* frame_idx, int frames, int tokens,
+                     int dim, int dtype, void* stream);
+
+/* ---- nn.Linear (+activation / +residual) used by mm_projector (builder.py:41-48), q/k/v/dense
+ * projections (MemoryController.py:23,37-39), the RMT MLP (:63-67) and the fuser (llava_arch.py:132-136):
+ *   C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]) (+ resid[M,N]) (+ addvec[N])
+ * A, W, resid in `dtype`; bias/addvec in `dtype`; C in out_dtype (MAVLM_F32 allowed with bf16 inputs:
+ * used for the pre-LayerNorm sum).  ld* are row strides in elements.  bias/resid/addvec may be NULL. */
+MAVLM_API int mavlm_gemm_bias_act_fwd(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* resid,
+                            int64_t ldr, const void* addvec, void* C, int64_t ldc, int M, int N, int K, int act,
+                            int dtype, int out_dtype, void* stream);
+
+/* ---- nn.LayerNorm over the last dim (MemoryController.py:24,28): y = (x-mean)/sqrt(var+eps)*g+b.
+ * x in x_dtype (MAVLM_F32 pre-LN sums or `dtype`), gamma/beta and y in dtype. */
+MAVLM_API int mavlm_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, int rows, int dim, float eps,
+                        int x_dtype, int dtype, void* stream);
+
+/* ---- multi-head softmax(q k^T * scale) v of Attention.forward (MemoryController.py:42-54), flash-style,
+ * probs never materialised in the bf16 tier.  Q [B, Lq, H*dh] (row stride ldq), K/V [B, Lk, H*dh]
+ * (row strides ldk/ldv, batch strides in elements), O [B, Lq, H*dh].  lse (fp32 [B,H,Lq], natural log) may be
+ * NULL.  col_scores (fp32 [B, Lk]) if non-NULL receives sum over heads and queries of the normalised
+ * probabilities (MemoryController.py:135; fp32 tier only). workspace: see mavlm_xattn_workspace_bytes. */
+MAVLM_API size_t mavlm_xattn_workspace_bytes(int batch, int heads, int lq, int lk, int head_dim, int dtype);
+MAVLM_API int mavlm_xattn_fwd(const void* Q, int64_t ldq, int64_t q_batch_stride, const void* K, int64_t ldk,
+                    int64_t k_batch_stride, const void* V, int64_t ldv, int64_t v_batch_stride, void* O, int64_t ldo,
+                    int64_t o_batch_stride, float* lse, float* col_scores, int batch, int heads, int lq, int lk,
+                    int head_dim, float scale, int dtype, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a14 + a15: type embeddings + token assembly (llava_arch.py:548-554, 620-629, 708-731).
+ * Writes seq [10 + n_mem_rows + 1 + 9 + n_fine*tokens + 1, D]:
+ *   rows of embed_table at prompt_mem_ids | mem (+type_emb[0]) | newline | prompt_frm rows |
+ *   frames[fine_idx] (+type_emb[1]) | newline.
+ * mem may be NULL when the fuser GEMM already wrote that segment in place (addvec = type_emb[0]).
+ * prompt ids / fine_idx are device int64.  drop_frames != 0 stops after the memory newline. */
+MAVLM_API int mavlm_assemble_fwd(void* seq, const void* mem, int64_t n_mem_rows, const void* frames, const int64_t* fine_idx,
+                       int n_fine, int tokens, const void* type_emb, const void* newline, const void* embed_table,
+                       const int64_t* prompt_mem_ids, int n_prompt_mem, const int64_t* prompt_frm_ids,
+                       int n_prompt_frm, int dim, int drop_frames, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAVLM_H_ */

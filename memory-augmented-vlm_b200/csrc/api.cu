@@ -1,0 +1,79 @@
+// extern "C" dispatch for the dense ops: picks the tcgen05 tier (bf16) or the exact SIMT tier (fp32).
+#include "common.cuh"
+
+namespace mavlm {
+int gemm_fp32(const float* A, long long lda, const float* W, long long ldw, const float* bias, const float* resid,
+              long long ldr, const float* addvec, float* C, long long ldc, int M, int N, int K, int act,
+              cudaStream_t st);
+int gemm_bf16_tc(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw,
+                 const __nv_bfloat16* bias, const __nv_bfloat16* resid, long long ldr, const __nv_bfloat16* addvec,
+                 void* C, long long ldc, int M, int N, int K, int act, int out_f32, cudaStream_t st);
+void gemm_tc_force_bn(int bn);
+int xattn_fp32(const float* Q, long long ldq, long long qb, const float* K, long long ldk, long long kb, const float* V,
+               long long ldv, long long vb, float* O, long long ldo, long long ob, float* lse, float* col_scores,
+               int batch, int heads, int lq, int lk, int dh, float scale, void* ws, size_t ws_bytes, cudaStream_t st);
+int xattn_bf16_tc(const __nv_bfloat16* Q, long long ldq, long long qb, const __nv_bfloat16* K, long long ldk,
+                  long long kb, const __nv_bfloat16* V, long long ldv, long long vb, __nv_bfloat16* O, long long ldo,
+                  long long ob, float* lse, int batch, int heads, int lq, int lk, int dh, float scale,
+                  cudaStream_t st);
+}  // namespace mavlm
+
+using namespace mavlm;
+
+extern "C" {
+
+int mavlm_gemm_bias_act_fwd(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* resid,
+                            int64_t ldr, const void* addvec, void* C, int64_t ldc, int M, int N, int K, int act,
+                            int dtype, int out_dtype, void* stream) {
+  MAVLM_REQUIRE(M >= 0 && N >= 0 && K > 0, MAVLM_E_INVALID, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
+  MAVLM_REQUIRE(act >= MAVLM_ACT_NONE && act <= MAVLM_ACT_RELU, MAVLM_E_INVALID, "gemm: bad activation %d", act);
+  MAVLM_REQUIRE(A != nullptr && W != nullptr && C != nullptr, MAVLM_E_INVALID, "gemm: NULL operand");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == MAVLM_F32) {
+    MAVLM_REQUIRE(out_dtype == MAVLM_F32, MAVLM_E_INVALID, "gemm: fp32 inputs require fp32 output");
+    return gemm_fp32(static_cast<const float*>(A), lda, static_cast<const float*>(W), ldw,
+                     static_cast<const float*>(bias), static_cast<const float*>(resid), ldr,
+                     static_cast<const float*>(addvec), static_cast<float*>(C), ldc, M, N, K, act, st);
+  }
+  MAVLM_REQUIRE(dtype == MAVLM_BF16, MAVLM_E_INVALID, "gemm: bad dtype %d", dtype);
+  MAVLM_REQUIRE(out_dtype == MAVLM_BF16 || out_dtype == MAVLM_F32, MAVLM_E_INVALID, "gemm: bad out_dtype %d",
+                out_dtype);
+  return gemm_bf16_tc(static_cast<const __nv_bfloat16*>(A), lda, static_cast<const __nv_bfloat16*>(W), ldw,
+                      static_cast<const __nv_bfloat16*>(bias), static_cast<const __nv_bfloat16*>(resid), ldr,
+                      static_cast<const __nv_bfloat16*>(addvec), C, ldc, M, N, K, act, out_dtype == MAVLM_F32, st);
+}
+
+size_t mavlm_xattn_workspace_bytes(int batch, int heads, int lq, int lk, int head_dim, int dtype) {
+  (void)head_dim;
+  if (dtype == MAVLM_F32) return static_cast<size_t>(batch) * heads * lq * static_cast<size_t>(lk) * sizeof(float);
+  return 0;
+}
+
+int mavlm_xattn_fwd(const void* Q, int64_t ldq, int64_t q_batch_stride, const void* K, int64_t ldk,
+                    int64_t k_batch_stride, const void* V, int64_t ldv, int64_t v_batch_stride, void* O, int64_t ldo,
+                    int64_t o_batch_stride, float* lse, float* col_scores, int batch, int heads, int lq, int lk,
+                    int head_dim, float scale, int dtype, void* workspace, size_t workspace_bytes, void* stream) {
+  MAVLM_REQUIRE(batch >= 0 && heads > 0 && lq >= 0 && lk >= 0 && head_dim > 0, MAVLM_E_INVALID, "xattn: bad shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == MAVLM_F32)
+    return xattn_fp32(static_cast<const float*>(Q), ldq, q_batch_stride, static_cast<const float*>(K), ldk,
+                      k_batch_stride, static_cast<const float*>(V), ldv, v_batch_stride, static_cast<float*>(O), ldo,
+                      o_batch_stride, lse, col_scores, batch, heads, lq, lk, head_dim, scale, workspace,
+                      workspace_bytes, st);
+  MAVLM_REQUIRE(dtype == MAVLM_BF16, MAVLM_E_INVALID, "xattn: bad dtype %d", dtype);
+  MAVLM_REQUIRE(col_scores == nullptr, MAVLM_E_INVALID,
+                "xattn: col_scores (frame scores, MemoryController.py:135) is produced by the fp32 tier only");
+  return xattn_bf16_tc(static_cast<const __nv_bfloat16*>(Q), ldq, q_batch_stride,
+                       static_cast<const __nv_bfloat16*>(K), ldk, k_batch_stride,
+                       static_cast<const __nv_bfloat16*>(V), ldv, v_batch_stride, static_cast<__nv_bfloat16*>(O), ldo,
+                       o_batch_stride, lse, batch, heads, lq, lk, head_dim, scale, st);
+}
+
+/* development knob (not part of the reference-facing surface): force the GEMM N tile (0 = heuristic) */
+MAVLM_API int mavlm_debug_force_gemm_bn(int bn) {
+  MAVLM_REQUIRE(bn == 0 || bn == 64 || bn == 128 || bn == 192 || bn == 256, MAVLM_E_INVALID, "bad BN %d", bn);
+  gemm_tc_force_bn(bn);
+  return MAVLM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,388 @@
+// Bandwidth-bound kernels of the visual-memory path (sm_100a): fused spatial pool + temporal PE,
+// standalone PE add, LayerNorm, token assembly.  All are 16-byte vectorised along the hidden
+// dimension, coalesced, fp32 internal math with a single rounding to the storage dtype.
+#include "common.cuh"
+
+namespace mavlm {
+
+template <typename T>
+struct Vec;  // 16-byte vector of T <-> floats
+template <>
+struct Vec<float> {
+  static constexpr int N = 4;
+  __device__ static void load(const float* p, float (&v)[4]) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  __device__ static void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <>
+struct Vec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __device__ static void load(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+  __device__ static void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 t;
+    t.x = pack_bf16x2(v[0], v[1]); t.y = pack_bf16x2(v[2], v[3]);
+    t.z = pack_bf16x2(v[4], v[5]); t.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// K2 + K3: channels-last spatial pool (+ PE).  One thread per (frame, out token, 16-byte
+// channel group); the 4 bilinear taps are 4 independent 16-byte loads.
+// Tap arithmetic follows ATen upsample_bilinear2d (align_corners=False): scale = in/out (fp32),
+// src = max(scale*(o+0.5)-0.5, 0), i0 = (int)src, i1 = i0 + (i0 < in-1), l1 = src - i0.
+// ---------------------------------------------------------------------------------------
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) pool_pe_kernel(const T* __restrict__ x, T* __restrict__ y,
+                                                      const float* __restrict__ pe, const int64_t* __restrict__ fidx,
+                                                      int frames, int side, int out_side, int stride, int dim) {
+  constexpr int V = Vec<T>::N;
+  const int groups = dim / V;
+  const long long total = static_cast<long long>(frames) * out_side * out_side * groups;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % groups);
+    long long t = i / groups;
+    const int ox = static_cast<int>(t % out_side);
+    t /= out_side;
+    const int oy = static_cast<int>(t % out_side);
+    const int f = static_cast<int>(t / out_side);
+    const T* xf = x + (static_cast<long long>(f) * side * side) * dim + g * V;
+    float acc[V];
+    if (MODE == MAVLM_POOL_BILINEAR) {
+      const float scale = static_cast<float>(side) / static_cast<float>(out_side);
+      float sy = fmaxf(scale * (oy + 0.5f) - 0.5f, 0.f);
+      float sx = fmaxf(scale * (ox + 0.5f) - 0.5f, 0.f);
+      int y0 = min(static_cast<int>(sy), side - 1), x0 = min(static_cast<int>(sx), side - 1);
+      int y1 = y0 + (y0 < side - 1), x1 = x0 + (x0 < side - 1);
+      float ly1 = sy - y0, lx1 = sx - x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+      float v00[V], v01[V], v10[V], v11[V];
+      Vec<T>::load(xf + (static_cast<long long>(y0) * side + x0) * dim, v00);
+      Vec<T>::load(xf + (static_cast<long long>(y0) * side + x1) * dim, v01);
+      Vec<T>::load(xf + (static_cast<long long>(y1) * side + x0) * dim, v10);
+      Vec<T>::load(xf + (static_cast<long long>(y1) * side + x1) * dim, v11);
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[k] = ly0 * (lx0 * v00[k] + lx1 * v01[k]) + ly1 * (lx0 * v10[k] + lx1 * v11[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[k] = (MODE == MAVLM_POOL_MAX) ? -INFINITY : 0.f;
+      for (int dy = 0; dy < stride; ++dy)
+        for (int dx = 0; dx < stride; ++dx) {
+          float v[V];
+          Vec<T>::load(xf + (static_cast<long long>(oy * stride + dy) * side + (ox * stride + dx)) * dim, v);
+#pragma unroll
+          for (int k = 0; k < V; ++k) acc[k] = (MODE == MAVLM_POOL_MAX) ? fmaxf(acc[k], v[k]) : acc[k] + v[k];
+        }
+      if (MODE == MAVLM_POOL_AVERAGE) {
+        const float inv = 1.f / static_cast<float>(stride * stride);
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] *= inv;
+      }
+    }
+    if (pe != nullptr) {
+      const float* p = pe + fidx[f] * dim + g * V;
+#pragma unroll
+      for (int k = 0; k < V; k += 4) {
+        float4 q = __ldg(reinterpret_cast<const float4*>(p + k));
+        acc[k] += q.x; acc[k + 1] += q.y; acc[k + 2] += q.z; acc[k + 3] += q.w;
+      }
+    }
+    Vec<T>::store(y + ((static_cast<long long>(f) * out_side + oy) * out_side + ox) * dim + g * V, acc);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) add_pe_kernel(const T* __restrict__ x, T* __restrict__ y,
+                                                     const float* __restrict__ pe, const int64_t* __restrict__ fidx,
+                                                     int frames, int tokens, int dim) {
+  constexpr int V = Vec<T>::N;
+  const int groups = dim / V;
+  const long long total = static_cast<long long>(frames) * tokens * groups;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % groups);
+    const long long row = i / groups;
+    const int f = static_cast<int>(row / tokens);
+    float v[V];
+    Vec<T>::load(x + row * dim + g * V, v);
+    const float* p = pe + fidx[f] * dim + g * V;
+#pragma unroll
+    for (int k = 0; k < V; ++k) v[k] += __ldg(p + k);
+    Vec<T>::store(y + row * dim + g * V, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// LayerNorm: one CTA per row, row cached in registers, exact two-pass statistics in fp32
+// (eps = 1e-12 in the RMT makes the one-pass E[x^2]-E[x]^2 form unsafe).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = (l < nw) ? red[l] : 0.f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  return t;
+}
+
+template <typename TI, typename TO, int THREADS, int CACHE>
+__global__ void __launch_bounds__(THREADS) layernorm_kernel(const TI* __restrict__ x, const TO* __restrict__ gamma,
+                                                            const TO* __restrict__ beta, TO* __restrict__ y, int dim,
+                                                            float eps) {
+  __shared__ float red[32];
+  const long long row = blockIdx.x;
+  const TI* xr = x + row * dim;
+  TO* yr = y + row * dim;
+  float v[CACHE][4];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < CACHE; ++c) {
+    const int i = (c * THREADS + threadIdx.x) * 4;
+    if (i < dim) {
+      if (sizeof(TI) == 4) {
+        float4 t = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(xr) + i);
+        v[c][0] = t.x; v[c][1] = t.y; v[c][2] = t.z; v[c][3] = t.w;
+      } else {
+        uint2 t = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(xr) + i);
+        float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&t.x));
+        float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&t.y));
+        v[c][0] = a.x; v[c][1] = a.y; v[c][2] = b.x; v[c][3] = b.y;
+      }
+      s += (v[c][0] + v[c][1]) + (v[c][2] + v[c][3]);
+    } else {
+      v[c][0] = v[c][1] = v[c][2] = v[c][3] = 0.f;
+    }
+  }
+  const float mean = block_sum(s, red) / static_cast<float>(dim);
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < CACHE; ++c) {
+    const int i = (c * THREADS + threadIdx.x) * 4;
+    if (i < dim) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float d = v[c][k] - mean;
+        q += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(block_sum(q, red) / static_cast<float>(dim) + eps);
+#pragma unroll
+  for (int c = 0; c < CACHE; ++c) {
+    const int i = (c * THREADS + threadIdx.x) * 4;
+    if (i < dim) {
+      float o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float g, b;
+        if (sizeof(TO) == 4) {
+          g = reinterpret_cast<const float*>(gamma)[i + k];
+          b = reinterpret_cast<const float*>(beta)[i + k];
+        } else {
+          g = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(gamma)[i + k]);
+          b = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(beta)[i + k]);
+        }
+        o[k] = (v[c][k] - mean) * rstd * g + b;
+      }
+      if (sizeof(TO) == 4) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(yr) + i) = make_float4(o[0], o[1], o[2], o[3]);
+      } else {
+        uint2 t;
+        t.x = pack_bf16x2(o[0], o[1]);
+        t.y = pack_bf16x2(o[2], o[3]);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(yr) + i) = t;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K12 + K13: token assembly.  One CTA per output row; the row kind is decoded from its index.
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) assemble_kernel(T* __restrict__ seq, const T* __restrict__ mem, long long n_mem,
+                                                       const T* __restrict__ frames,
+                                                       const int64_t* __restrict__ fine_idx, int n_fine, int tokens,
+                                                       const T* __restrict__ type_emb, const T* __restrict__ newline,
+                                                       const T* __restrict__ table,
+                                                       const int64_t* __restrict__ pm_ids, int n_pm,
+                                                       const int64_t* __restrict__ pf_ids, int n_pf, int dim) {
+  constexpr int V = Vec<T>::N;
+  long long r = blockIdx.x;
+  const T* src = nullptr;
+  const T* add = nullptr;
+  const long long n_fine_rows = static_cast<long long>(n_fine) * tokens;
+  if (r < n_pm) {
+    src = table + pm_ids[r] * dim;
+  } else if ((r -= n_pm) < n_mem) {
+    if (mem == nullptr) return;  // written in place by the fuser GEMM epilogue
+    src = mem + r * dim;
+    add = type_emb;
+  } else if ((r -= n_mem) < 1) {
+    src = newline;
+  } else if ((r -= 1) < n_pf) {
+    src = table + pf_ids[r] * dim;
+  } else if ((r -= n_pf) < n_fine_rows) {
+    const long long f = r / tokens, t = r % tokens;
+    src = frames + (fine_idx[f] * tokens + t) * dim;
+    add = type_emb + dim;
+  } else {
+    src = newline;
+  }
+  T* dst = seq + static_cast<long long>(blockIdx.x) * dim;
+  for (int i = threadIdx.x * V; i < dim; i += blockDim.x * V) {
+    float v[V];
+    Vec<T>::load(src + i, v);
+    if (add != nullptr) {
+      float a[V];
+      Vec<T>::load(add + i, a);
+#pragma unroll
+      for (int k = 0; k < V; ++k) v[k] += a[k];
+    }
+    Vec<T>::store(dst + i, v);
+  }
+}
+
+static int grid_for(long long total_threads, int block) {
+  long long b = (total_threads + block - 1) / block;
+  const long long cap = static_cast<long long>(sm_count()) * 32;  // grid-stride beyond 32 CTAs/SM
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+template <typename T>
+static int launch_pool(const void* x, void* y, const float* pe, const int64_t* fidx, int frames, int side,
+                       int out_side, int stride, int dim, int mode, cudaStream_t st) {
+  const long long total = static_cast<long long>(frames) * out_side * out_side * (dim / Vec<T>::N);
+  const int grid = grid_for(total, 256);
+  const T* xp = static_cast<const T*>(x);
+  T* yp = static_cast<T*>(y);
+  if (mode == MAVLM_POOL_BILINEAR)
+    pool_pe_kernel<T, MAVLM_POOL_BILINEAR><<<grid, 256, 0, st>>>(xp, yp, pe, fidx, frames, side, out_side, stride, dim);
+  else if (mode == MAVLM_POOL_AVERAGE)
+    pool_pe_kernel<T, MAVLM_POOL_AVERAGE><<<grid, 256, 0, st>>>(xp, yp, pe, fidx, frames, side, out_side, stride, dim);
+  else
+    pool_pe_kernel<T, MAVLM_POOL_MAX><<<grid, 256, 0, st>>>(xp, yp, pe, fidx, frames, side, out_side, stride, dim);
+  MAVLM_LAUNCH_OK();
+  return MAVLM_OK;
+}
+
+int layernorm_launch(const void* x, const void* gamma, const void* beta, void* y, int rows, int dim, float eps,
+                     int x_dtype, int dtype, cudaStream_t st) {
+  MAVLM_REQUIRE(dim % 4 == 0 && dim > 0 && dim <= 256 * 4 * 4, MAVLM_E_INVALID,
+                "layernorm: dim %d must be a multiple of 4 and <= 4096", dim);
+  MAVLM_REQUIRE(x_dtype == MAVLM_F32 || x_dtype == dtype, MAVLM_E_INVALID, "layernorm: x_dtype must be f32 or dtype");
+  if (rows == 0) return MAVLM_OK;
+#define MAVLM_LN(TI, TO, TH, CA)                                                                                   \
+  layernorm_kernel<TI, TO, TH, CA><<<rows, TH, 0, st>>>(static_cast<const TI*>(x), static_cast<const TO*>(gamma), \
+                                                         static_cast<const TO*>(beta), static_cast<TO*>(y), dim, eps)
+  if (dim <= 512) {
+    if (dtype == MAVLM_F32) MAVLM_LN(float, float, 128, 1);
+    else if (x_dtype == MAVLM_F32) MAVLM_LN(float, __nv_bfloat16, 128, 1);
+    else MAVLM_LN(__nv_bfloat16, __nv_bfloat16, 128, 1);
+  } else {
+    if (dtype == MAVLM_F32) MAVLM_LN(float, float, 256, 4);
+    else if (x_dtype == MAVLM_F32) MAVLM_LN(float, __nv_bfloat16, 256, 4);
+    else MAVLM_LN(__nv_bfloat16, __nv_bfloat16, 256, 4);
+  }
+#undef MAVLM_LN
+  MAVLM_LAUNCH_OK();
+  return MAVLM_OK;
+}
+
+}  // namespace mavlm
+
+using namespace mavlm;
+
+extern "C" {
+
+int mavlm_pool_pe_fwd(const void* x, void* y, const float* pe_table, const int64_t* frame_idx, int frames, int side,
+                      int out_side, int stride, int dim, int mode, int dtype, void* stream) {
+  MAVLM_REQUIRE(dtype == MAVLM_F32 || dtype == MAVLM_BF16, MAVLM_E_INVALID, "pool_pe: bad dtype %d", dtype);
+  MAVLM_REQUIRE(mode >= MAVLM_POOL_BILINEAR && mode <= MAVLM_POOL_MAX, MAVLM_E_INVALID,
+                "Unexpected mm_spatial_pool_mode: %d", mode);
+  const int vec = dtype == MAVLM_F32 ? 4 : 8;
+  MAVLM_REQUIRE(dim > 0 && dim % vec == 0, MAVLM_E_INVALID, "pool_pe: dim %d must be a multiple of %d", dim, vec);
+  MAVLM_REQUIRE(side > 0 && out_side > 0 && stride > 0, MAVLM_E_INVALID, "pool_pe: bad geometry");
+  MAVLM_REQUIRE((pe_table == nullptr) == (frame_idx == nullptr), MAVLM_E_INVALID,
+                "pool_pe: pe_table and frame_idx must both be given or both be NULL");
+  if (mode != MAVLM_POOL_BILINEAR)
+    MAVLM_REQUIRE(out_side * stride <= side, MAVLM_E_INVALID, "pool_pe: window exceeds the input");
+  if (frames == 0) return MAVLM_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return dtype == MAVLM_F32
+             ? launch_pool<float>(x, y, pe_table, frame_idx, frames, side, out_side, stride, dim, mode, st)
+             : launch_pool<__nv_bfloat16>(x, y, pe_table, frame_idx, frames, side, out_side, stride, dim, mode, st);
+}
+
+int mavlm_add_pe_fwd(const void* x, void* y, const float* pe_table, const int64_t* frame_idx, int frames, int tokens,
+                     int dim, int dtype, void* stream) {
+  MAVLM_REQUIRE(dtype == MAVLM_F32 || dtype == MAVLM_BF16, MAVLM_E_INVALID, "add_pe: bad dtype %d", dtype);
+  const int vec = dtype == MAVLM_F32 ? 4 : 8;
+  MAVLM_REQUIRE(dim > 0 && dim % vec == 0, MAVLM_E_INVALID, "add_pe: dim %d must be a multiple of %d", dim, vec);
+  MAVLM_REQUIRE(pe_table != nullptr && frame_idx != nullptr, MAVLM_E_INVALID, "add_pe: NULL table / indices");
+  if (frames == 0 || tokens == 0) return MAVLM_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long total = static_cast<long long>(frames) * tokens * (dim / vec);
+  const int grid = grid_for(total, 256);
+  if (dtype == MAVLM_F32)
+    add_pe_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), static_cast<float*>(y), pe_table,
+                                               frame_idx, frames, tokens, dim);
+  else
+    add_pe_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x),
+                                                       static_cast<__nv_bfloat16*>(y), pe_table, frame_idx, frames,
+                                                       tokens, dim);
+  MAVLM_LAUNCH_OK();
+  return MAVLM_OK;
+}
+
+int mavlm_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, int rows, int dim, float eps,
+                        int x_dtype, int dtype, void* stream) {
+  MAVLM_REQUIRE(dtype == MAVLM_F32 || dtype == MAVLM_BF16, MAVLM_E_INVALID, "layernorm: bad dtype %d", dtype);
+  return layernorm_launch(x, gamma, beta, y, rows, dim, eps, x_dtype, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int mavlm_assemble_fwd(void* seq, const void* mem, int64_t n_mem_rows, const void* frames, const int64_t* fine_idx,
+                       int n_fine, int tokens, const void* type_emb, const void* newline, const void* embed_table,
+                       const int64_t* prompt_mem_ids, int n_prompt_mem, const int64_t* prompt_frm_ids,
+                       int n_prompt_frm, int dim, int drop_frames, int dtype, void* stream) {
+  MAVLM_REQUIRE(dtype == MAVLM_F32 || dtype == MAVLM_BF16, MAVLM_E_INVALID, "assemble: bad dtype %d", dtype);
+  const int vec = dtype == MAVLM_F32 ? 4 : 8;
+  MAVLM_REQUIRE(dim > 0 && dim % vec == 0, MAVLM_E_INVALID, "assemble: dim %d must be a multiple of %d", dim, vec);
+  long long rows = n_prompt_mem + n_mem_rows + 1;
+  if (!drop_frames) rows += n_prompt_frm + static_cast<long long>(n_fine) * tokens + 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == MAVLM_F32)
+    assemble_kernel<float><<<static_cast<unsigned>(rows), 128, 0, st>>>(
+        static_cast<float*>(seq), static_cast<const float*>(mem), n_mem_rows, static_cast<const float*>(frames),
+        fine_idx, n_fine, tokens, static_cast<const float*>(type_emb), static_cast<const float*>(newline),
+        static_cast<const float*>(embed_table), prompt_mem_ids, n_prompt_mem, prompt_frm_ids, n_prompt_frm, dim);
+  else
+    assemble_kernel<__nv_bfloat16><<<static_cast<unsigned>(rows), 128, 0, st>>>(
+        static_cast<__nv_bfloat16*>(seq), static_cast<const __nv_bfloat16*>(mem), n_mem_rows,
+        static_cast<const __nv_bfloat16*>(frames), fine_idx, n_fine, tokens,
+        static_cast<const __nv_bfloat16*>(type_emb), static_cast<const __nv_bfloat16*>(newline),
+        static_cast<const __nv_bfloat16*>(embed_table), prompt_mem_ids, n_prompt_mem, prompt_frm_ids, n_prompt_frm,
+        dim);
+  MAVLM_LAUNCH_OK();
+  return MAVLM_OK;
+}
+
+}  // extern "C"

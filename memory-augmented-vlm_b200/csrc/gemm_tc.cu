@@ -1,0 +1,313 @@
+// bf16 GEMM on the 5th-gen tensor cores (sm_100a):  C = act(A * W^T + bias) (+ resid) (+ addvec)
+//   A [M,K] row-major (K-major operand), W [N,K] row-major (nn.Linear weight, K-major operand).
+// Persistent, warp-specialised CTA (192 threads, one per SM):
+//   warp 0  : TMA producer  (cp.async.bulk.tensor, 128B swizzle, STAGES-deep smem ring, mbarrier tx)
+//   warp 1  : MMA issuer    (one elected lane issues tcgen05.mma cta_group::1, M=128 x N=BN x K=16;
+//                            accumulators double-buffered in TMEM so the epilogue of tile i overlaps
+//                            the main loop of tile i+1; tcgen05.commit releases smem stages)
+//   warps 2-5: epilogue     (tcgen05.ld 32x32b -> registers -> bias / GELU(erf) / ReLU / residual ->
+//                            bf16 or fp32 rows, 16-byte vector stores)
+// Tiles are walked m-fastest so that the CTAs running concurrently share one W slab (read once from
+// HBM, re-used out of L2) while A (a few MB) stays L2 resident.
+#include "common.cuh"
+
+namespace mavlm {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+struct GemmTcParams {
+  int M, N, K;
+  const __nv_bfloat16* bias;
+  const __nv_bfloat16* resid;
+  long long ldr;
+  const __nv_bfloat16* addvec;
+  void* C;
+  long long ldc;
+  int act;
+  int out_f32;
+  int m_tiles, n_tiles;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 192 ? 5 : (BN >= 128 ? 6 : 8));
+  static constexpr int ACC_STRIDE = (BN <= 64) ? 64 : (BN <= 128 ? 128 : 256);
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  // ring | bias[2][BN] | addv[2][BN] | barriers | tmem ptr ; +1024 for manual alignment
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * BN * 4 + (2 * STAGES + 4) * 8 + 16 + 1024;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmTcParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  float* bias_s = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+  float* addv_s = bias_s + 2 * BN;
+  uint64_t* full = reinterpret_cast<uint64_t*>(addv_s + 2 * BN);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int kblocks = (p.K + GEMM_BK - 1) / GEMM_BK;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % p.m_tiles) * GEMM_BM, n0 = (tile / p.m_tiles) * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+          tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], kb * GEMM_BK, m0);
+          tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * GEMM_BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc = umma_desc_kmajor(smem_u32(sA + stage * Cfg::A_BYTES));
+          const uint64_t b_desc = umma_desc_kmajor(smem_u32(sB + stage * Cfg::B_BYTES));
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k)  // +32 B per K=16 step inside the 128 B swizzle row
+            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);
+        if ((acc ^= 1) == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int q = warp & 3;                     // TMEM lane quadrant this warp may access
+    const int et = (warp - 2) * 32 + lane;      // 0..127 within the epilogue group
+    const int row_in_tile = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile % p.m_tiles) * GEMM_BM, n0 = (tile / p.m_tiles) * BN;
+      float* bs = bias_s + acc * BN;
+      float* as = addv_s + acc * BN;
+      for (int j = et; j < BN; j += 128) {
+        const int n = n0 + j;
+        bs[j] = (p.bias != nullptr && n < p.N) ? __bfloat162float(p.bias[n]) : 0.f;
+        as[j] = (p.addvec != nullptr && n < p.N) ? __bfloat162float(p.addvec[n]) : 0.f;
+      }
+      named_bar_sync(1, 128);
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + row_in_tile;
+      const bool row_ok = row < p.M;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::ACC_STRIDE + c * 32, r);
+        tmem_ld_wait();
+        const int nc = n0 + c * 32;
+        if (row_ok && nc < p.N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bs[c * 32 + j];
+          if (p.act == MAVLM_ACT_GELU_ERF) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
+          } else if (p.act == MAVLM_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          const bool full_chunk = nc + 32 <= p.N;
+          if (p.resid != nullptr) {
+            const __nv_bfloat16* rp = p.resid + row * p.ldr + nc;
+            if (full_chunk) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint4 t = __ldg(reinterpret_cast<const uint4*>(rp) + g);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __bfloat1622float2(h[e]);
+                  v[g * 8 + 2 * e] += f.x;
+                  v[g * 8 + 2 * e + 1] += f.y;
+                }
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (nc + j < p.N) v[j] += __bfloat162float(rp[j]);
+            }
+          }
+          if (p.addvec != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += as[c * 32 + j];
+          }
+          if (p.out_f32) {
+            float* cp = static_cast<float*>(p.C) + row * p.ldc + nc;
+            if (full_chunk) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                reinterpret_cast<float4*>(cp)[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (nc + j < p.N) cp[j] = v[j];
+            }
+          } else {
+            __nv_bfloat16* cp = static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + nc;
+            if (full_chunk) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                uint4 t;
+                t.x = pack_bf16x2(v[8 * g], v[8 * g + 1]);
+                t.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
+                t.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
+                t.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
+                reinterpret_cast<uint4*>(cp)[g] = t;
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (nc + j < p.N) cp[j] = __float2bfloat16(v[j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if ((acc ^= 1) == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN>
+static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmTcParams p, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    MAVLM_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  p.m_tiles = ceil_div(p.M, GEMM_BM);
+  p.n_tiles = ceil_div(p.N, BN);
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+  MAVLM_LAUNCH_OK();
+  return MAVLM_OK;
+}
+
+// Pick the N tile: minimise (waves x tile width / tile efficiency); wide tiles re-use A better
+// (smem read B/clk per MMA cycle drops), narrow tiles quantise better on 148 SMs.
+static int g_force_bn = 0;
+int gemm_tc_pick_bn(int M, int N) {
+  if (g_force_bn) return g_force_bn;
+  const int sms = sm_count();
+  const int cand[4] = {256, 192, 128, 64};
+  const float eff[4] = {1.00f, 0.97f, 0.90f, 0.62f};
+  int best = 128;
+  float best_cost = 1e30f;
+  const int mt = ceil_div(M, GEMM_BM);
+  for (int i = 0; i < 4; ++i) {
+    const int tiles = mt * ceil_div(N, cand[i]);
+    const int waves = ceil_div(tiles, sms);
+    const float cost = static_cast<float>(waves) * cand[i] / eff[i];
+    if (cost < best_cost - 1e-3f) {
+      best_cost = cost;
+      best = cand[i];
+    }
+  }
+  return best;
+}
+
+int gemm_bf16_tc(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw,
+                 const __nv_bfloat16* bias, const __nv_bfloat16* resid, long long ldr, const __nv_bfloat16* addvec,
+                 void* C, long long ldc, int M, int N, int K, int act, int out_f32, cudaStream_t st) {
+  if (M == 0 || N == 0) return MAVLM_OK;
+  MAVLM_REQUIRE(K > 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, MAVLM_E_INVALID,
+                "bf16 gemm: K (%d), lda (%lld), ldw (%lld) must be multiples of 8", K, lda, ldw);
+  const int cvec = out_f32 ? 4 : 8;
+  MAVLM_REQUIRE(ldc % cvec == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0, MAVLM_E_INVALID,
+                "bf16 gemm: C must be 16-byte aligned with ldc %% %d == 0", cvec);
+  if (resid != nullptr)
+    MAVLM_REQUIRE(ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(resid) & 15) == 0, MAVLM_E_INVALID,
+                  "bf16 gemm: resid must be 16-byte aligned with ldr %% 8 == 0");
+  const int bn = gemm_tc_pick_bn(M, N);
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+    const uint64_t str[1] = {static_cast<uint64_t>(lda) * 2};
+    const uint32_t box[2] = {GEMM_BK, GEMM_BM};
+    int rc = make_tmap_bf16(&tmA, A, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    const uint64_t str[1] = {static_cast<uint64_t>(ldw) * 2};
+    const uint32_t box[2] = {GEMM_BK, static_cast<uint32_t>(bn)};
+    int rc = make_tmap_bf16(&tmB, W, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  GemmTcParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.bias = bias; p.resid = resid; p.ldr = ldr; p.addvec = addvec;
+  p.C = C; p.ldc = ldc; p.act = act; p.out_f32 = out_f32;
+  switch (bn) {
+    case 256: return launch_gemm_tc<256>(tmA, tmB, p, st);
+    case 192: return launch_gemm_tc<192>(tmA, tmB, p, st);
+    case 128: return launch_gemm_tc<128>(tmA, tmB, p, st);
+    default:  return launch_gemm_tc<64>(tmA, tmB, p, st);
+  }
+}
+
+void gemm_tc_force_bn(int bn) { g_force_bn = bn; }
+
+}  // namespace mavlm

@@ -1,0 +1,189 @@
+"""Tensor-level wrappers over the C ABI: validate, allocate outputs with torch (PyTorch owns all
+storage), pass raw pointers + the current CUDA stream.  PyTorch is plumbing here (device memory,
+streams); every computation below runs in libmavlm.so.  No fallback: CPU tensors are an error.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU_ERF, ACT_NONE, ACT_RELU, BF16, F32
+
+_DTYPES = {torch.float32: F32, torch.bfloat16: BF16}
+_device_checked = set()
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise TypeError(f"mavlm supports float32 and bfloat16 tensors, got {t.dtype}") from None
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("mavlm: tensor is not on a CUDA device; this path has no CPU fallback")
+        dev = t.device.index
+        if dev not in _device_checked:
+            _lib.check(_lib.load().mavlm_check_device(dev), "check_device")
+            _device_checked.add(dev)
+
+
+def _rowmajor2d(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise RuntimeError(f"mavlm: {name} must be 2-D with unit inner stride, got shape {tuple(t.shape)} "
+                           f"strides {t.stride()}")
+    return t
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: int = ACT_NONE,
+           resid: Optional[torch.Tensor] = None, addvec: Optional[torch.Tensor] = None,
+           out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """y = act(x @ weight.T + bias) (+ resid) (+ addvec);  x [..., K], weight [N, K] (nn.Linear layout)."""
+    _need_cuda(x, weight, bias, resid, addvec, out)
+    lead = x.shape[:-1]
+    k = x.shape[-1]
+    x2 = x.reshape(-1, k)
+    if x2.stride(1) != 1:
+        x2 = x2.contiguous()
+    n = weight.shape[0]
+    if weight.shape[1] != k:
+        raise RuntimeError(f"mavlm.linear: weight {tuple(weight.shape)} does not match input features {k}")
+    _rowmajor2d(weight, "weight")
+    m = x2.shape[0]
+    odt = out_dtype or x.dtype
+    r2 = None
+    if resid is not None:
+        r2 = resid.reshape(-1, n)
+        if r2.shape[0] != m or r2.stride(1) != 1:
+            raise RuntimeError("mavlm.linear: resid shape mismatch")
+    if out is None:
+        out2 = torch.empty((m, n), dtype=odt, device=x.device)
+    else:
+        out2 = out.reshape(-1, n) if out.dim() != 2 else out
+        if out2.shape[0] != m or out2.stride(1) != 1 or out2.data_ptr() != out.data_ptr():
+            raise RuntimeError("mavlm.linear: out must be a row-major [M, N] view")
+        odt = out2.dtype
+    for t in (weight, bias, resid, addvec):
+        if t is not None and t.dtype != x.dtype:
+            raise TypeError(f"mavlm.linear: operand dtype {t.dtype} != input dtype {x.dtype}")
+    lib = _lib.load()
+    st = lib.mavlm_gemm_bias_act_fwd(_ptr(x2), x2.stride(0), _ptr(weight), weight.stride(0), _ptr(bias), _ptr(r2),
+                                     0 if r2 is None else r2.stride(0), _ptr(addvec), _ptr(out2), out2.stride(0), m, n,
+                                     k, act, dtype_code(x), _DTYPES[odt], _stream())
+    _lib.check(st, "gemm_bias_act_fwd")
+    if out is not None:
+        return out
+    return out2.reshape(*lead, n)
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
+              out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    _need_cuda(x, gamma, beta)
+    d = x.shape[-1]
+    x2 = x.reshape(-1, d)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    odt = out_dtype or gamma.dtype
+    y = torch.empty(x2.shape, dtype=odt, device=x.device)
+    st = _lib.load().mavlm_layernorm_fwd(_ptr(x2), _ptr(gamma), _ptr(beta), _ptr(y), x2.shape[0], d, float(eps),
+                                         dtype_code(x2), _DTYPES[odt], _stream())
+    _lib.check(st, "layernorm_fwd")
+    return y.reshape(x.shape)
+
+
+def xattn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *, head_dim: Optional[int] = None,
+          scale: Optional[float] = None, want_lse: bool = False,
+          want_col_scores: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """softmax(q k^T * scale) v per head.  q [B, Lq, H*dh], k/v [B, Lk, H*dh] (last dim contiguous; row /
+    batch strides free, so k and v may be column slices of one fused projection buffer)."""
+    _need_cuda(q, k, v)
+    if q.dim() != 3 or k.dim() != 3 or v.dim() != 3:
+        raise RuntimeError("mavlm.xattn: q, k, v must be [B, L, H*dh]")
+    for t in (q, k, v):
+        if t.stride(2) != 1:
+            raise RuntimeError("mavlm.xattn: last dim must be contiguous")
+    b, lq, hd = q.shape
+    lk = k.shape[1]
+    dh = head_dim or hd // heads
+    if scale is None:
+        scale = 1.0 / math.sqrt(dh)
+    o = torch.empty((b, lq, hd), dtype=q.dtype, device=q.device)
+    lse = torch.empty((b, heads, lq), dtype=torch.float32, device=q.device) if want_lse else None
+    cs = torch.empty((b, lk), dtype=torch.float32, device=q.device) if want_col_scores else None
+    lib = _lib.load()
+    code = dtype_code(q)
+    ws_bytes = lib.mavlm_xattn_workspace_bytes(b, heads, lq, lk, dh, code)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device) if ws_bytes else None
+    st = lib.mavlm_xattn_fwd(_ptr(q), q.stride(1), q.stride(0), _ptr(k), k.stride(1), k.stride(0), _ptr(v),
+                             v.stride(1), v.stride(0), _ptr(o), o.stride(1), o.stride(0), _ptr(lse), _ptr(cs), b,
+                             heads, lq, lk, dh, float(scale), code, _ptr(ws), ws_bytes, _stream())
+    _lib.check(st, "xattn_fwd")
+    return o, lse, cs
+
+
+def pool_pe(x: torch.Tensor, *, side: int, stride: int = 2, mode: str = "bilinear",
+            pe_table: Optional[torch.Tensor] = None, frame_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[F, side*side, D] -> [F, out*out, D] (+ pe_table[frame_idx] when given)."""
+    _need_cuda(x, pe_table, frame_idx)
+    modes = {"bilinear": _lib.POOL_BILINEAR, "average": _lib.POOL_AVERAGE, "max": _lib.POOL_MAX}
+    if mode not in modes:
+        raise ValueError(f"Unexpected mm_spatial_pool_mode: {mode}")          # llava_arch.py:294
+    f, n, d = x.shape
+    if n != side * side:
+        raise RuntimeError(f"mavlm.pool_pe: {n} tokens is not {side}x{side}")
+    out_side = math.ceil(side / stride) if mode == "bilinear" else side // stride
+    x = x.contiguous()
+    y = torch.empty((f, out_side * out_side, d), dtype=x.dtype, device=x.device)
+    if pe_table is not None:
+        if pe_table.dtype != torch.float32 or not pe_table.is_contiguous() or pe_table.shape[1] != d:
+            raise RuntimeError("mavlm.pool_pe: pe_table must be contiguous fp32 [max_frames, D]")
+        frame_idx = frame_idx.to(device=x.device, dtype=torch.int64).contiguous()
+    st = _lib.load().mavlm_pool_pe_fwd(_ptr(x), _ptr(y), _ptr(pe_table), _ptr(frame_idx), f, side, out_side, stride, d,
+                                       modes[mode], dtype_code(x), _stream())
+    _lib.check(st, "pool_pe_fwd")
+    return y
+
+
+def add_pe(x: torch.Tensor, pe_table: torch.Tensor, frame_idx: torch.Tensor) -> torch.Tensor:
+    """x [T, N, C] + pe_table[frame_idx][:, None, :]."""
+    _need_cuda(x, pe_table, frame_idx)
+    t, n, c = x.shape
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    frame_idx = frame_idx.to(device=x.device, dtype=torch.int64).contiguous()
+    st = _lib.load().mavlm_add_pe_fwd(_ptr(x), _ptr(y), _ptr(pe_table), _ptr(frame_idx), t, n, c, dtype_code(x),
+                                      _stream())
+    _lib.check(st, "add_pe_fwd")
+    return y
+
+
+def assemble(seq: torch.Tensor, mem: Optional[torch.Tensor], n_mem_rows: int, frames: torch.Tensor,
+             fine_idx: torch.Tensor, tokens: int, type_emb: torch.Tensor, newline: torch.Tensor,
+             embed_table: torch.Tensor, prompt_mem_ids: torch.Tensor, prompt_frm_ids: torch.Tensor,
+             drop_frames: bool = False) -> torch.Tensor:
+    _need_cuda(seq, mem, frames, fine_idx, type_emb, newline, embed_table, prompt_mem_ids, prompt_frm_ids)
+    d = seq.shape[-1]
+    for t in (mem, frames, type_emb, newline, embed_table):
+        if t is not None and (t.dtype != seq.dtype or not t.is_contiguous()):
+            raise RuntimeError("mavlm.assemble: operands must be contiguous and of the sequence dtype")
+    st = _lib.load().mavlm_assemble_fwd(_ptr(seq), _ptr(mem), n_mem_rows, _ptr(frames), _ptr(fine_idx),
+                                        fine_idx.numel(), tokens, _ptr(type_emb), _ptr(newline), _ptr(embed_table),
+                                        _ptr(prompt_mem_ids), prompt_mem_ids.numel(), _ptr(prompt_frm_ids),
+                                        prompt_frm_ids.numel(), d, int(drop_frames), dtype_code(seq), _stream())
+    _lib.check(st, "assemble_fwd")
+    return seq

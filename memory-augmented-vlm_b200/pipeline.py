@@ -1,0 +1,192 @@
+"""Chunk scheduler + fused visual-memory pipeline (the hot path of
+llava_arch.py:481-557, 613-629, 705-731 for a batch of equal-length videos).
+
+    tower tokens [B, F, 729, Dv]
+      -> mm_projector (2 GEMMs, GELU fused)                                  K1
+      -> bilinear 27x27 -> 14x14 pool + temporal PE (one kernel)             K2+K3
+      -> frame-side K/V of BOTH formation layers for ALL chunks in one GEMM  K5   (memory independent)
+      -> for each chunk, sequentially:  evolution attention over the ring of cached states (their K/V
+         projections cached, newest state projected once) -> 2 x [Q proj, fused attention, O proj +
+         residual -> LN, MLP up (ReLU fused), MLP down + residual -> LN]    K5-K8, K10
+      -> memory fuser (GEMM + GELU, GEMM + bias + type_emb[0]) written straight into the final
+         sequence buffer; prompts / newline / fine frames + type_emb[1] by the assembly kernel  K11-K13
+
+Differences from the reference that do not change the result: `image.mean(dim=1)` (K4) is never
+computed (only its length is used, segment.py:180); cached states live in a ring buffer whose slot
+order differs from `torch.cat(cache)` -- attention is invariant to key order, and the fuser output is
+written to the reference's row positions; probs are never materialised.  Per-video results equal
+B independent reference calls (the reference supports one video per rank, llava_arch.py:436).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import ACT_GELU_ERF, ACT_NONE, ACT_RELU
+from .modules import (Attention, MemoryFuserMLP, TemporalPositionalEncoding, TransformerProjector, VisionProjector,
+                      fine_frame_indices, uniform_segment_variant)
+
+MEMORY_PROMPT_IDS = (1986, 374, 264, 1550, 11591, 12126, 315, 279, 2766, 25)      # llava_arch.py:708
+FRAME_PROMPT_IDS = (9485, 525, 48876, 9124, 14087, 504, 279, 2766, 25)            # llava_arch.py:714
+
+
+class VisualMemoryPipeline(nn.Module):
+    """Holds (references to) the drop-in modules and runs the whole path for B videos."""
+
+    def __init__(self, *, mm_projector: Optional[VisionProjector], recurrent_memory_transformer: TransformerProjector,
+                 memory_fuser: MemoryFuserMLP, positional_encoding: TemporalPositionalEncoding,
+                 token_type_embedding: nn.Embedding, image_newline: torch.Tensor, embed_tokens: nn.Embedding,
+                 chunk_size: int = 32, max_fine_frames: int = 32, num_patches_per_side: int = 27,
+                 pool_stride: int = 2, projector_frames_per_pass: int = 64):
+        super().__init__()
+        self.mm_projector = mm_projector
+        self.recurrent_memory_transformer = recurrent_memory_transformer
+        self.memory_fuser = memory_fuser
+        self.positional_encoding = positional_encoding
+        self.token_type_embedding = token_type_embedding
+        self.image_newline = image_newline
+        self.embed_tokens = embed_tokens
+        self.chunk_size = chunk_size
+        self.max_fine_frames = max_fine_frames
+        self.side = num_patches_per_side
+        self.pool_stride = pool_stride
+        self.projector_frames_per_pass = projector_frames_per_pass
+        self._consts: Dict = {}
+
+    # ------------------------------------------------------------------------------------------
+    def _const_ids(self, device):
+        key = str(device)
+        if key not in self._consts:
+            self._consts[key] = (torch.tensor(MEMORY_PROMPT_IDS, dtype=torch.int64, device=device),
+                                 torch.tensor(FRAME_PROMPT_IDS, dtype=torch.int64, device=device))
+        return self._consts[key]
+
+    def sequence_length(self, n_states: int, n_fine: int, drop_frames: bool = False) -> int:
+        rmt = self.recurrent_memory_transformer
+        lq = rmt.num_memory_tokens * rmt.patch_size
+        n = len(MEMORY_PROMPT_IDS) + n_states * lq + 1
+        if not drop_frames:
+            n += len(FRAME_PROMPT_IDS) + n_fine * rmt.patch_size + 1
+        return n
+
+    def _formation_kv_weights(self):
+        """[Wk0;Wv0;Wk1;Wv1;...] so the frame-side K/V of every layer come out of one GEMM."""
+        rmt = self.recurrent_memory_transformer
+        packs = [l.memory_segment_fusion_attention.packed() for l in rmt.layers]
+        key = tuple(id(p["wkv"]) for p in packs)
+        c = self._consts.get("fkv")
+        if c is None or c[0] != key:
+            w = torch.cat([p["wkv"] for p in packs], dim=0).contiguous()
+            b = torch.cat([p["bkv"] for p in packs], dim=0).contiguous()
+            self._consts["fkv"] = (key, w, b)
+        return self._consts["fkv"][1], self._consts["fkv"][2]
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def encode_frames(self, tower_tokens: torch.Tensor, frame_idx: torch.Tensor) -> torch.Tensor:
+        """[N, side*side, Dv] tower tokens (+ original frame indices [N]) -> pooled + PE'd [N, P, D]
+        (encode_images -> get_2dPool -> positional_encoding, llava_arch.py:481-511)."""
+        pe = self.positional_encoding
+        pe.validate(frame_idx)
+        frame_idx = frame_idx.to(tower_tokens.device)
+        n = tower_tokens.shape[0]
+        outs = []
+        step = max(1, self.projector_frames_per_pass)
+        table = pe.table()
+        for i in range(0, n, step):
+            y = self.mm_projector(tower_tokens[i:i + step])
+            outs.append(ops.pool_pe(y, side=self.side, stride=self.pool_stride, mode="bilinear", pe_table=table,
+                                    frame_idx=frame_idx[i:i + step]))
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+
+    @torch.no_grad()
+    def memory_forward(self, z: torch.Tensor, *, seq_out: Optional[torch.Tensor] = None, drop_frames: bool = False,
+                       return_states: bool = True) -> Dict[str, torch.Tensor]:
+        """z: pooled + PE'd frames [B, F, P, D].  Runs the recurrence, the fuser and the assembly."""
+        rmt = self.recurrent_memory_transformer
+        b, f, p, d = z.shape
+        dtype, dev = z.dtype, z.device
+        m_slots, lq = rmt.num_memory_tokens, rmt.num_memory_tokens * p
+        heads = rmt.layers[0].memory_segment_fusion_attention.num_attention_heads
+        dh = d // heads
+        scale = 1.0 / math.sqrt(dh)
+        cap = rmt.cache_size
+        z2 = z.reshape(b, f * p, d)
+
+        # frame-side K/V for all chunks and layers (memory independent): one GEMM
+        packs = [l.memory_segment_fusion_attention.packed() for l in rmt.layers]
+        dhp = packs[0]["dhp"]
+        hd = heads * dhp
+        wf, bf = self._formation_kv_weights()
+        kvf = ops.linear(z2, wf, bf)                                    # [B, F*P, depth*2*hd]
+
+        bounds = uniform_segment_variant(f, self.chunk_size)
+        n_chunks = len(bounds) - 1
+        n_keep = min(n_chunks, cap)
+        evo = rmt.memory_update_attention
+        evo_p = evo.packed()
+        ring_states = torch.empty((b, cap, lq, d), dtype=dtype, device=dev)
+        ring_kv = torch.empty((b, cap * lq, 2 * hd), dtype=dtype, device=dev) if n_chunks > 1 else None
+
+        mem = rmt.initial_state(dtype).reshape(1, lq, d).expand(b, lq, d).contiguous()
+        for t in range(n_chunks):
+            if t > 0:
+                # memory evolution: Q = newest state, K/V = every state still cached (incl. itself)
+                n = min(t, cap)
+                q = ops.linear(mem, evo_p["wq"], evo_p["bq"])
+                kv = ring_kv[:, : n * lq]
+                ctx, _, _ = ops.xattn(q, kv[..., :hd], kv[..., hd:], heads, head_dim=dhp, scale=scale)
+                mem = evo.residual(ctx, mem, weight=evo_p["wo"])
+            r0, r1 = bounds[t] * p, bounds[t + 1] * p
+            for li, layer in enumerate(rmt.layers):
+                pk = packs[li]
+                att = layer.memory_segment_fusion_attention
+                q = ops.linear(mem, pk["wq"], pk["bq"])
+                kcol = li * 2 * hd
+                ctx, _, _ = ops.xattn(q, kvf[:, r0:r1, kcol:kcol + hd], kvf[:, r0:r1, kcol + hd:kcol + 2 * hd], heads,
+                                      head_dim=dhp, scale=scale)
+                a = att.residual(ctx, mem, weight=pk["wo"])
+                up = ops.linear(a, layer.mlp[0].weight, layer.mlp[0].bias, act=layer._act)
+                mem = layer.residual(up, a)
+            slot = t % cap
+            ring_states[:, slot].copy_(mem)
+            if t + 1 < n_chunks:                                        # project the new state once for later chunks
+                for bi in range(b):
+                    ops.linear(mem[bi], evo_p["wkv"], evo_p["bkv"], out=ring_kv[bi, slot * lq:(slot + 1) * lq])
+
+        # fuser + assembly: state written at chunk t sits in slot t % cap; reference order is oldest first
+        first = n_chunks - n_keep
+        n_fine = min(self.max_fine_frames, f)
+        fine_idx = fine_frame_indices(f, self.max_fine_frames).to(dev)
+        seq_len = self.sequence_length(n_keep, n_fine, drop_frames)
+        if seq_out is None:
+            seq_out = torch.empty((b, seq_len, d), dtype=dtype, device=dev)
+        pm_ids, pf_ids = self._const_ids(dev)
+        emb = self.token_type_embedding.weight.detach()
+        npm = len(MEMORY_PROMPT_IDS)
+        fz = self.memory_fuser
+        hidden = ops.linear(ring_states[:, :n_keep].reshape(b * n_keep * lq, d), fz[0].weight, fz[0].bias,
+                            act=ACT_GELU_ERF).reshape(b, n_keep, lq, 4 * d)
+        for bi in range(b):
+            for i in range(n_keep):
+                slot = (first + i) % cap
+                dst = seq_out[bi, npm + i * lq: npm + (i + 1) * lq]
+                ops.linear(hidden[bi, slot], fz[2].weight, fz[2].bias, addvec=emb[0], out=dst)
+            ops.assemble(seq_out[bi], None, n_keep * lq, z[bi], fine_idx, p, emb, self.image_newline.detach(),
+                         self.embed_tokens.weight.detach(), pm_ids, pf_ids, drop_frames)
+        out = {"sequence": seq_out}
+        if return_states:
+            order = [(first + i) % cap for i in range(n_keep)]
+            out["states"] = ring_states[:, order]                       # [B, n_keep, Lq, D], oldest first
+        return out
+
+    @torch.no_grad()
+    def forward(self, tower_tokens: torch.Tensor, frame_idx: torch.Tensor, **kw) -> Dict[str, torch.Tensor]:
+        """tower_tokens [B, F, side*side, Dv], frame_idx [B, F] (original-video indices for the PE)."""
+        b, f = tower_tokens.shape[:2]
+        z = self.encode_frames(tower_tokens.reshape(b * f, *tower_tokens.shape[2:]), frame_idx.reshape(-1))
+        return self.memory_forward(z.reshape(b, f, *z.shape[1:]), **kw)
