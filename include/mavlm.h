@@ -46,6 +46,8 @@ enum {
 
 MAVLM_API int mavlm_version(void);
 MAVLM_API const char* mavlm_last_error_string(void);
+/* Number of CUDA kernels this library has launched in this process (monotonic; for accounting). */
+MAVLM_API unsigned long long mavlm_launch_count(void);
 /* Verifies that `device` is compute capability 10.x; MAVLM_E_ARCH otherwise. */
 MAVLM_API int mavlm_check_device(int device);
 

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_ulonglong, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmavlm.so")
@@ -27,6 +27,7 @@ class MavlmError(RuntimeError):
 PROTOTYPES = {
     "mavlm_version": (c_int, []),
     "mavlm_last_error_string": (c_char_p, []),
+    "mavlm_launch_count": (c_ulonglong, []),
     "mavlm_check_device": (c_int, [c_int]),
     "mavlm_pool_pe_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                   c_int, c_void_p]),

@@ -41,7 +41,7 @@ struct AttnCfg {
   static constexpr int RING = (DH == 448) ? 9 : 12;
   static constexpr int TMEM_COLS = (DH + 64 <= 256) ? 256 : 512;
   static constexpr int S_COL = DH;
-  static constexpr int NBARS = 2 * RING + 6;
+  static constexpr int NBARS = 2 * RING + 7;
   static constexpr int SMEM_BYTES = Q_BYTES + 2 * ATT_P_BYTES + RING * ATT_SLICE_BYTES + NBARS * 8 + 16 + 1024;
 };
 
@@ -63,8 +63,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint64_t* s_full = q_full + 1;
   uint64_t* s_free = s_full + 1;
   uint64_t* p_full = s_free + 1;  // [2]
-  uint64_t* o_done = p_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+  uint64_t* o_done = p_full + 2;  // [2]: PV(j) commits to o_done[j & 1] so that a parity wait is never ambiguous
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * ATT_BQ, h = blockIdx.y, b = blockIdx.z;
@@ -83,7 +83,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     mbar_init(s_free, 4);
     mbar_init(&p_full[0], 4);
     mbar_init(&p_full[1], 4);
-    mbar_init(o_done, 1);
+    mbar_init(&o_done[0], 1);
+    mbar_init(&o_done[1], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -134,7 +135,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           umma_commit(&kv_empty[stage]);
           if (++stage == RING) { stage = 0; phase ^= 1; }
         }
-        umma_commit(o_done);
+        umma_commit(&o_done[jj & 1]);
       };
       mbar_wait(q_full, 0);
       tc_fence_after();
@@ -193,7 +194,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       } else {
         const bool need = mx > m_used + 8.f;
         if (__any_sync(0xffffffffu, need)) {
-          mbar_wait(o_done, (j - 1) & 1);  // PV(j-1) finished: O is quiescent until P(j) is published
+          // PV(j-1) finished => O is quiescent until P(j) is published.  s_full(j) implies PV(j-2) and
+          // older are complete, so o_done[(j-1)&1] is at most one completion behind: parity is exact.
+          mbar_wait(&o_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
           tc_fence_after();
           const float alpha = need ? exp2f(m_used - mx) : 1.f;
 #pragma unroll 1
@@ -234,7 +237,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[j & 1]);
     }
-    mbar_wait(o_done, (J - 1) & 1);
+    mbar_wait(&o_done[(J - 1) & 1], ((J - 1) >> 1) & 1);  // PV(J-3) known complete (s_full(J-1)): exact as above
     tc_fence_after();
     const float inv = 1.f / l;
     const int q = q0 + row;

@@ -32,7 +32,12 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     }                                       \
   } while (0)
 
-#define MAVLM_LAUNCH_OK() MAVLM_CUDA_OK(cudaGetLastError())
+extern unsigned long long g_launches;  // kernels launched by this library (bench.py's gpu_launches)
+#define MAVLM_LAUNCH_OK()                  \
+  do {                                     \
+    ++::mavlm::g_launches;                 \
+    MAVLM_CUDA_OK(cudaGetLastError());     \
+  } while (0)
 
 int sm_count();  // cached multiProcessorCount of the current device
 

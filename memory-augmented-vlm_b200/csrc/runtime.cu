@@ -11,6 +11,7 @@
 namespace mavlm {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -88,6 +89,8 @@ extern "C" {
 int mavlm_version(void) { return MAVLM_VERSION; }
 
 const char* mavlm_last_error_string(void) { return mavlm::g_err; }
+
+unsigned long long mavlm_launch_count(void) { return mavlm::g_launches; }
 
 int mavlm_check_device(int device) {
   int major = 0, minor = 0;

@@ -1,0 +1,97 @@
+"""Multi-GPU host logic: one process per GPU (torchrun), videos sharded over ranks.
+
+The recurrence is sequential in time, so the only axes that shard are (i) independent videos --
+each rank runs whole recurrences, weights replicated, NO data-path collective -- and (ii) the
+memory-independent pre-pass of one long video (projector + pool + PE per frame), whose pooled tokens
+are all-gathered once before the replicated recurrence.  NCCL (NVLink 5 / NVSwitch) is
+used only for those gathers; `gloo` runs the same code on CPU for the world_size-2 tests.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, rank: int, world: int) -> range:
+    """Contiguous balanced split: the first n % world ranks get one extra item."""
+    base, extra = divmod(n_items, world)
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))
+
+
+def all_gather_rows(local: torch.Tensor, counts: Optional[Sequence[int]] = None) -> torch.Tensor:
+    """Concatenate per-rank tensors along dim 0 (rank order).  Equal counts use one
+    all_gather_into_tensor (NCCL ring / NVLS); ragged counts pad to the max and trim."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return local
+    world = dist.get_world_size()
+    if counts is None:
+        counts = [local.shape[0]] * world
+    mx = max(counts)
+    if all(c == mx for c in counts):
+        out = local.new_empty((world * mx, *local.shape[1:]))
+        if dist.get_backend() == "nccl":
+            dist.all_gather_into_tensor(out, local.contiguous())
+        else:
+            parts = list(out.chunk(world, dim=0))
+            dist.all_gather(parts, local.contiguous())
+        return out
+    padded = local.new_zeros((mx, *local.shape[1:]))
+    padded[: local.shape[0]] = local
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded)
+    return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
+
+
+def max_over_ranks(value: float, device=None) -> float:
+    """Multi-GPU timings are reported as the max over ranks."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+@torch.no_grad()
+def encode_videos_sharded(pipe, tower_tokens: torch.Tensor, frame_idx: torch.Tensor, *, gather: bool = True):
+    """tower_tokens [V, F, 729, Dv] (same on every rank, or only the local shard is touched):
+    rank r runs videos shard_range(V, r, world); returns assembled sequences [V, L, D] on every rank
+    (gather=True) or the local shard."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    v = tower_tokens.shape[0]
+    mine = shard_range(v, rank, world)
+    dev = next(pipe.parameters()).device
+    if len(mine):
+        res = pipe(tower_tokens[mine.start:mine.stop].to(dev, non_blocking=True), frame_idx[mine.start:mine.stop],
+                   return_states=False)["sequence"]
+    else:
+        res = None
+    if not gather or world == 1:
+        return res
+    counts = [len(shard_range(v, r, world)) for r in range(world)]
+    if res is None:
+        n_chunks = -(-tower_tokens.shape[1] // pipe.chunk_size)
+        seq_len = pipe.sequence_length(min(n_chunks, pipe.recurrent_memory_transformer.cache_size),
+                                       min(pipe.max_fine_frames, tower_tokens.shape[1]))
+        d = pipe.recurrent_memory_transformer.hidden_size
+        res = torch.empty((0, seq_len, d), dtype=next(pipe.parameters()).dtype, device=dev)
+    return all_gather_rows(res, counts)
+
+
+@torch.no_grad()
+def encode_long_video_frame_sharded(pipe, tower_tokens: torch.Tensor, frame_idx: torch.Tensor):
+    """One long video [F, 729, Dv]: each rank projects + pools + PEs F/world frames, the pooled tokens
+    are all-gathered (1.4 MB per 7B frame), then every rank runs the (replicated) recurrence."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    f = tower_tokens.shape[0]
+    mine = shard_range(f, rank, world)
+    dev = next(pipe.parameters()).device
+    z_local = pipe.encode_frames(tower_tokens[mine.start:mine.stop].to(dev, non_blocking=True),
+                                 frame_idx[mine.start:mine.stop])
+    counts = [len(shard_range(f, r, world)) for r in range(world)]
+    z = all_gather_rows(z_local, counts)
+    return pipe.memory_forward(z[None])

@@ -139,10 +139,10 @@ def xattn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *, head
 def pool_pe(x: torch.Tensor, *, side: int, stride: int = 2, mode: str = "bilinear",
             pe_table: Optional[torch.Tensor] = None, frame_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
     """[F, side*side, D] -> [F, out*out, D] (+ pe_table[frame_idx] when given)."""
-    _need_cuda(x, pe_table, frame_idx)
     modes = {"bilinear": _lib.POOL_BILINEAR, "average": _lib.POOL_AVERAGE, "max": _lib.POOL_MAX}
     if mode not in modes:
         raise ValueError(f"Unexpected mm_spatial_pool_mode: {mode}")          # llava_arch.py:294
+    _need_cuda(x, pe_table, frame_idx)
     f, n, d = x.shape
     if n != side * side:
         raise RuntimeError(f"mavlm.pool_pe: {n} tokens is not {side}x{side}")

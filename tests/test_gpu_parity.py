@@ -1,0 +1,292 @@
+"""GPU parity tests (B200, sm_100a): the CUDA path, called through the C ABI, against
+  (1) the committed golden fixtures produced by the UNMODIFIED reference (tests/golden/), and
+  (2) the numpy oracle on the same seeded inputs, at sizes the oracle finishes in seconds,
+plus size-independent properties at BASELINE's full sizes.
+
+Tolerances (BASELINE.json north_star / SURVEY.md §8d), err(a,b) = max|a-b| / max|b| per tensor:
+  fp32 tier  <= 1e-5   (vs float64 oracle / fp32 reference goldens)
+  bf16 tier  <= 2e-2   on the assembled output tokens and the final memory state.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import mavlm_b200 as M
+from mavlm_b200 import ops, synthetic
+from oracle import vismem_oracle as O
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5
+BF16_TOL = 2e-2
+DEV = "cuda:0"
+
+
+def err(a, b):
+    if isinstance(a, torch.Tensor):
+        a = a.detach().double().cpu().numpy()
+    return O.normalized_max_error(a, b)
+
+
+def _golden(name):
+    z = np.load(os.path.join(GOLDEN, name))
+    w = {k[3:]: z[k] for k in z.files if k.startswith("w::")}
+    return z, w
+
+
+def _load_rmt(w, d, frame_scores=False, prefix="recurrent_memory_transformer."):
+    cfg = M.Config()
+    cfg.mm_hidden_size, cfg.mm_intermediate_size, cfg.depth, cfg.mm_dtype = d, 4 * d, 2, torch.float32
+    cfg.frame_scores = frame_scores
+    rmt = M.TransformerProjector(cfg)
+    sd = {k[len(prefix):]: torch.from_numpy(v) for k, v in w.items() if k.startswith(prefix)}
+    rmt.load_state_dict(sd, strict=True)          # reference state_dict loads unchanged
+    return rmt.to(DEV)
+
+
+# ------------------------------------------------------------------------------------------------
+# golden fixtures from the reference modules (fp32 tier)
+# ------------------------------------------------------------------------------------------------
+def test_rmt_module_against_reference_golden():
+    z, w = _golden("rmt_small.npz")
+    rmt = _load_rmt(w, 32, frame_scores=True)
+    frames = torch.from_numpy(z["frames"]).to(DEV)
+    rmt.memory_cache = []
+    for i in range(3):
+        cache, scores = rmt(frames[2 * i:2 * i + 2])        # same call signature as the reference
+    assert len(cache) == 3 and cache[0].shape == (8, 196, 32)
+    for i in range(3):
+        assert err(cache[i], z[f"state{i}"]) < FP32_TOL, i
+        assert err(scores[i], z[f"score{i}"]) < FP32_TOL, i
+    assert err(cache[2], z["f64_state_last"]) < FP32_TOL
+
+
+def test_rmt_stress_sharp_softmax_golden():
+    z, w = _golden("rmt_small.npz")
+    ws = {k: (v * 8.0 if "q_proj" in k else v) for k, v in w.items()}
+    rmt = _load_rmt(ws, 32)
+    frames = 4.0 * torch.from_numpy(z["frames"]).to(DEV)
+    rmt.memory_cache = []
+    for i in range(3):
+        cache, _ = rmt(frames[2 * i:2 * i + 2])
+    assert err(cache[0], z["stress_state_first"]) < 5e-5
+    # the reference's own fp32-vs-fp64 drift in this regime is ~2.5e-4 (tests/test_oracle_golden.py)
+    assert err(cache[-1], z["f64_stress_state_last"]) < 1e-3
+
+
+def test_rmt_cache_cap_golden():
+    z, w = _golden("rmt_small.npz")
+    rmt = _load_rmt(w, 32)
+    frames = torch.from_numpy(z["frames12"]).to(DEV)
+    rmt.memory_cache = []
+    for i in range(12):
+        cache, _ = rmt(frames[i:i + 1])
+    assert len(cache) == int(z["cap_len"]) == 10
+    assert err(cache[0], z["cap_state_first"]) < 5e-5
+    assert err(cache[-1], z["cap_state_last"]) < 5e-5
+
+
+def test_pool_pe_projector_fuser_golden():
+    z, _ = _golden("pool.npz")
+    x = torch.from_numpy(z["x"]).to(DEV)
+    assert err(M.get_2dPool(x), z["bilinear"]) < FP32_TOL
+    assert err(M.get_2dPool(x), z["bilinear_f64"]) < FP32_TOL
+    assert err(M.get_2dPool(x, mode="average"), z["average"]) < FP32_TOL
+    assert err(M.get_2dPool(x, mode="max"), z["max"]) == 0.0
+    assert err(M.get_2dPool(x, stride=3), z["bilinear_s3"]) < FP32_TOL
+    assert M.get_2dPool(x.bfloat16()).dtype == torch.bfloat16
+    assert err(M.get_2dPool(x.bfloat16()).float(), z["bilinear"]) < 1e-2
+
+    zp, _ = _golden("pe.npz")
+    pe = M.TemporalPositionalEncoding(600, 32, learnable=False).to(DEV)
+    xp = torch.from_numpy(zp["x"]).to(DEV)
+    assert err(pe(xp, torch.from_numpy(zp["idx"])), zp["y"]) < 1e-7
+    assert err(pe(xp), zp["y_default_idx"]) < 1e-7
+    assert err(pe(xp.bfloat16(), torch.from_numpy(zp["idx"])).float(), zp["y_bf16"]) < 1e-2
+    with pytest.raises(ValueError):
+        pe(xp, torch.tensor([0, 1, 2, 3, 600]))
+
+    zf, w = _golden("projector_fuser.npz")
+    import types
+    proj = M.build_vision_projector(types.SimpleNamespace(mm_projector_type="mlp2x_gelu", mm_hidden_size=48,
+                                                          hidden_size=32))
+    proj.load_state_dict({k[len("mm_projector."):]: torch.from_numpy(v) for k, v in w.items()
+                          if k.startswith("mm_projector.")})
+    assert err(proj.to(DEV)(torch.from_numpy(zf["proj_x"]).to(DEV)), zf["proj_y"]) < FP32_TOL
+    fuser = M.build_memory_fuser(32)
+    fuser.load_state_dict({k[len("memory_fuser."):]: torch.from_numpy(v) for k, v in w.items()
+                           if k.startswith("memory_fuser.")})
+    assert err(fuser.to(DEV)(torch.from_numpy(zf["fuser_x"]).to(DEV)), zf["fuser_y"]) < FP32_TOL
+
+
+@pytest.mark.parametrize("name,raw", [("full_path.npz", 70), ("full_path_short.npz", 5)])
+def test_full_path_against_reference_prepare_inputs(name, raw):
+    """The fused pipeline reproduces the embeddings the reference's own
+    prepare_inputs_labels_for_multimodal spliced in (70 raw frames -> 64 sampled -> 2 chunks; and a 5-frame
+    video: single ragged chunk, 5 fine frames)."""
+    zf, w = _golden("full_path.npz")
+    z = np.load(os.path.join(GOLDEN, name))
+    d, dv = 16, 4
+    pipe, _ = synthetic.build_pipeline(d, dv, dtype=torch.float32, device=DEV, vocab=50000)
+    pipe.recurrent_memory_transformer.load_state_dict(
+        {k[len("recurrent_memory_transformer."):]: torch.from_numpy(v) for k, v in w.items()
+         if k.startswith("recurrent_memory_transformer.")})
+    pipe.mm_projector.load_state_dict({k[len("mm_projector."):]: torch.from_numpy(v) for k, v in w.items()
+                                       if k.startswith("mm_projector.")})
+    pipe.memory_fuser.load_state_dict({k[len("memory_fuser."):]: torch.from_numpy(v) for k, v in w.items()
+                                       if k.startswith("memory_fuser.")})
+    pipe.token_type_embedding.load_state_dict({"weight": torch.from_numpy(w["token_type_embedding.weight"])})
+    pipe.image_newline = torch.from_numpy(w["image_newline"]).to(DEV)
+    tab = torch.from_numpy(w["_emb.weight"])
+    pipe.embed_tokens.weight.data = tab[torch.arange(50000) % tab.shape[0]].to(DEV)   # the harness embeds ids mod 64
+    video = torch.from_numpy(z["video"])
+    idx = M.sample_frame_indices(raw)
+    tower = video[idx].flatten(2).transpose(1, 2).contiguous()[None].to(DEV)        # fake tower of the golden harness
+    res = pipe(tower, idx[None])
+    ref = z["inputs_embeds"][0][2:-2]                                               # strip the 2+2 text tokens
+    assert res["sequence"].shape[1] == ref.shape[0]
+    assert err(res["sequence"][0], ref) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# oracle parity on seeded inputs (both tiers), incl. the mandatory stress variant
+# ------------------------------------------------------------------------------------------------
+def _run_vs_oracle(hidden, dv, dtype, frames, chunk, q_scale=1.0, x_scale=1.0, batch=1, pooled=False):
+    pipe, w = synthetic.build_pipeline(hidden, dv, dtype=dtype, chunk_size=chunk, device=DEV, q_scale=q_scale)
+    wq = synthetic.round_weights_like(w, dtype)
+    if pooled:
+        g = torch.Generator().manual_seed(1234)
+        x = (torch.randn(batch, frames, 196, hidden, generator=g) * x_scale).to(dtype)
+        res = pipe.memory_forward(x.to(DEV))
+    else:
+        x = (synthetic.synthetic_tower_tokens(batch, frames, dv, dtype=torch.float32) * x_scale).to(dtype)
+        res = pipe(x.to(DEV), torch.arange(frames)[None].expand(batch, frames))
+    torch.cuda.synchronize()
+    out = []
+    for b in range(batch):
+        if pooled:   # memory_forward takes pooled + PE'd frames as given
+            ref = _oracle_pooled(x[b].double().numpy(), wq, chunk)
+        else:
+            ref = O.visual_memory_path(x[b].double().numpy(), np.arange(frames), wq,
+                                       pe_table=wq["positional_encoding.frame_embed"],
+                                       prompt_mem=wq["embed_tokens.weight"][list(O.MEMORY_PROMPT_IDS)],
+                                       prompt_frm=wq["embed_tokens.weight"][list(O.FRAME_PROMPT_IDS)], chunk=chunk)
+        e_seq = err(res["sequence"][b], ref["sequence"])
+        e_mem = err(res["states"][b, -1].reshape(8, 196, hidden), ref["states"][-1])
+        out.append((e_seq, e_mem))
+    return out
+
+
+def _oracle_pooled(z, wq, chunk):
+    fine = z[O.fine_frame_indices(z.shape[0])]
+    cache, _ = O.rmt_video(z, wq, chunk=chunk)
+    fused = O.memory_fuser_mlp(np.concatenate(cache, axis=0), wq)
+    seq = O.assemble_sequence(fused, fine, wq, prompt_mem=wq["embed_tokens.weight"][list(O.MEMORY_PROMPT_IDS)],
+                              prompt_frm=wq["embed_tokens.weight"][list(O.FRAME_PROMPT_IDS)])
+    return {"sequence": seq, "states": cache}
+
+
+def test_config1_ov05b_fp32_32_frames_pooled_tokens():
+    """BASELINE config[0]: 0.5B dims, fp32, 1 video x 32 frames x 196 pooled tokens, memory module + fuser."""
+    (e_seq, e_mem), = _run_vs_oracle(896, 1152, torch.float32, 32, 32, pooled=True)
+    assert e_seq < FP32_TOL and e_mem < FP32_TOL, (e_seq, e_mem)
+
+
+def test_fp32_tier_full_path_two_chunks_and_ragged_tail():
+    for frames, chunk in ((12, 8), (5, 32)):
+        (e_seq, e_mem), = _run_vs_oracle(128, 64, torch.float32, frames, chunk)
+        assert e_seq < FP32_TOL and e_mem < FP32_TOL, (frames, chunk, e_seq, e_mem)
+
+
+def test_bf16_tier_ov05b_dims_padded_heads():
+    (e_seq, e_mem), = _run_vs_oracle(896, 1152, torch.bfloat16, 48, 16)          # 3 chunks, dh 112 -> 128
+    assert e_seq < BF16_TOL and e_mem < BF16_TOL, (e_seq, e_mem)
+
+
+def test_bf16_tier_stress_sharp_softmax():
+    """q_proj x8 and inputs x4: exercises the online-softmax max tracking / lazy rescale."""
+    (e_seq, e_mem), = _run_vs_oracle(896, 1152, torch.bfloat16, 32, 16, q_scale=8.0, x_scale=4.0, pooled=True)
+    assert e_seq < BF16_TOL and e_mem < 2 * BF16_TOL, (e_seq, e_mem)
+    (e_seq, e_mem), = _run_vs_oracle(896, 1152, torch.float32, 16, 8, q_scale=8.0, x_scale=4.0, pooled=True)
+    assert e_seq < 1e-3 and e_mem < 1e-3, (e_seq, e_mem)                         # fp32 noise floor of this regime
+
+
+def test_config2_ov7b_bf16_64_frames():
+    """BASELINE config[1]: 7B dims, bf16, 1 video x 64 frames, projector + pool + memory + fuser."""
+    (e_seq, e_mem), = _run_vs_oracle(3584, 1152, torch.bfloat16, 64, 32)
+    assert e_seq < BF16_TOL and e_mem < BF16_TOL, (e_seq, e_mem)
+
+
+def test_batched_videos_equal_independent_runs():
+    """Batch of videos (BASELINE config[2] shape, reduced): per-video results equal independent runs."""
+    pipe, _ = synthetic.build_pipeline(896, 1152, dtype=torch.bfloat16, chunk_size=16, device=DEV)
+    x = synthetic.synthetic_tower_tokens(3, 32, 1152).to(DEV)
+    idx = torch.arange(32)[None].expand(3, 32)
+    both = pipe(x, idx)
+    for b in range(3):
+        one = pipe(x[b:b + 1], idx[b:b + 1])
+        assert err(both["sequence"][b], one["sequence"][0].double().cpu().numpy()) < 1e-3
+        assert err(both["states"][b], one["states"][0].double().cpu().numpy()) < 1e-3
+
+
+def test_cache_ring_buffer_beyond_ten_chunks_matches_module_path():
+    """12 chunks (> cache depth 10): the pipeline's ring buffer equals the reference-shaped module loop."""
+    pipe, w = synthetic.build_pipeline(64, 16, dtype=torch.float32, chunk_size=1, device=DEV)
+    x = synthetic.synthetic_tower_tokens(1, 12, 16, dtype=torch.float32).to(DEV)
+    res = pipe(x, torch.arange(12)[None])
+    wq = synthetic.round_weights_like(w, torch.float32)
+    ref = O.visual_memory_path(x[0].double().cpu().numpy(), np.arange(12), wq,
+                               pe_table=wq["positional_encoding.frame_embed"],
+                               prompt_mem=wq["embed_tokens.weight"][list(O.MEMORY_PROMPT_IDS)],
+                               prompt_frm=wq["embed_tokens.weight"][list(O.FRAME_PROMPT_IDS)], chunk=1)
+    assert res["states"].shape[1] == 10 and len(ref["states"]) == 10
+    assert err(res["sequence"][0], ref["sequence"]) < 5e-5
+    assert err(res["states"][0, 0].reshape(8, 196, 64), ref["states"][0]) < 5e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# full-size properties (no oracle needed)
+# ------------------------------------------------------------------------------------------------
+def test_full_size_properties_7b():
+    torch.manual_seed(0)
+    h, dh, lq, lk = 8, 448, 1568, 6272
+    q = torch.randn(1, lq, h * dh, device=DEV).bfloat16()
+    k = torch.randn(1, lk, h * dh, device=DEV).bfloat16()
+    v = torch.randn(1, lk, h * dh, device=DEV).bfloat16()
+    o1, lse1, _ = ops.xattn(q, k, v, h, want_lse=True)
+    o2, lse2, _ = ops.xattn(q, k, v, h, want_lse=True)
+    assert torch.equal(o1, o2) and torch.equal(lse1, lse2)                       # deterministic
+    perm = torch.randperm(lk, device=DEV)                                        # key-order invariance (ring buffer relies on it)
+    o3, lse3, _ = ops.xattn(q, k[:, perm].contiguous(), v[:, perm].contiguous(), h, want_lse=True)
+    assert (o3.float() - o1.float()).abs().max() < 2e-2 * o1.float().abs().max()
+    assert (lse3 - lse1).abs().max() < 1e-4
+    ones = torch.ones_like(v)                                                    # softmax rows sum to one
+    o4, _, _ = ops.xattn(q, k, ones, h)
+    assert (o4.float() - 1).abs().max() < 1e-2
+    # linearity of the GEMM in A (exact in fp32 accumulation up to bf16 output rounding)
+    a = torch.randn(1568, 3584, device=DEV).bfloat16()
+    w = (torch.randn(3584, 3584, device=DEV) / 60).bfloat16()
+    y1 = ops.linear(a, w, None, out_dtype=torch.float32)
+    y2 = ops.linear((2 * a.float()).bfloat16(), w, None, out_dtype=torch.float32)
+    assert torch.equal(y2, 2 * y1)
+    # LayerNorm output statistics
+    g = torch.ones(3584, device=DEV)
+    y = ops.layernorm(y1, g, torch.zeros_like(g), 1e-12)
+    assert y.mean(-1).abs().max() < 1e-4 and (y.var(-1, unbiased=False) - 1).abs().max() < 1e-3
+
+
+def test_error_behaviour_on_device():
+    x = torch.zeros(2, 729, 8, device=DEV)
+    with pytest.raises(ValueError, match="Unexpected mm_spatial_pool_mode"):
+        M.get_2dPool(x, mode="nearest")
+    with pytest.raises(RuntimeError):
+        M.get_2dPool(torch.zeros(2, 700, 8, device=DEV))                         # not a square grid
+    with pytest.raises(RuntimeError):
+        ops.linear(torch.zeros(4, 8, device=DEV), torch.zeros(8, 16, device=DEV))
+    with pytest.raises(RuntimeError, match="head_dim"):
+        q = torch.zeros(1, 8, 8 * 64, device=DEV, dtype=torch.bfloat16)
+        ops.xattn(q, q, q, 8)                                                    # bf16 tier: head_dim 64 unsupported
