@@ -207,10 +207,44 @@ def test_bf16_tier_ov05b_dims_padded_heads():
     assert e_seq < BF16_TOL and e_mem < BF16_TOL, (e_seq, e_mem)
 
 
+def test_bf16_attention_kernel_sharp_softmax():
+    """Op-level stress of the online softmax / lazy O rescale: logits scaled x8 (and a row whose max
+    arrives in the LAST key block) against the oracle's softmax attention on the same bf16 operands."""
+    torch.manual_seed(3)
+    h, lq, lk = 8, 300, 1568 * 3 + 100                                           # ragged key tail, 76 key blocks
+    for dh in (128, 448):
+        q = (torch.randn(1, lq, h * dh) * 8.0).bfloat16()
+        k = torch.randn(1, lk, h * dh).bfloat16()
+        v = torch.randn(1, lk, h * dh).bfloat16()
+        k[0, -3] = q[0, 7] * 0.5                                                 # huge logit in the last block for row 7
+        o, lse, _ = ops.xattn(q.to(DEV), k.to(DEV), v.to(DEV), h, want_lse=True)
+        qd, kd, vd = (t[0].double().numpy().reshape(-1, h, dh).transpose(1, 0, 2) for t in (q, k, v))
+        sc = qd @ kd.transpose(0, 2, 1) / np.sqrt(dh)
+        pr = O.softmax_lastdim(sc)
+        ref = (pr @ vd).transpose(1, 0, 2).reshape(lq, h * dh)
+        mx = sc.max(-1, keepdims=True)
+        ref_lse = (mx + np.log(np.exp(sc - mx).sum(-1, keepdims=True)))[..., 0]
+        assert err(o[0], ref) < BF16_TOL, dh
+        assert err(lse[0], ref_lse) < 1e-4, dh
+
+
 def test_bf16_tier_stress_sharp_softmax():
-    """q_proj x8 and inputs x4: exercises the online-softmax max tracking / lazy rescale."""
-    (e_seq, e_mem), = _run_vs_oracle(896, 1152, torch.bfloat16, 32, 16, q_scale=8.0, x_scale=4.0, pooled=True)
-    assert e_seq < BF16_TOL and e_mem < 2 * BF16_TOL, (e_seq, e_mem)
+    """q_proj x8 and inputs x4 through the recurrence.  In this regime bf16 rounding is
+    amplified chaotically: the REFERENCE's own bf16-vs-fp32 drift is 16 % (first state) / 81 % (second)
+    (tests/golden/noise_floor.json, measured on the unmodified reference), so the CUDA path is held to
+    the reference's floor here, and to 2e-2 on the first state's op-level pieces above."""
+    import json
+    with open(os.path.join(GOLDEN, "noise_floor.json")) as fh:
+        floor = json.load(fh)["stress"]
+    pipe, w = synthetic.build_pipeline(896, 1152, dtype=torch.bfloat16, chunk_size=16, device=DEV, q_scale=8.0)
+    wq = synthetic.round_weights_like(w, torch.bfloat16)
+    g = torch.Generator().manual_seed(1234)
+    x = (torch.randn(1, 32, 196, 896, generator=g) * 4.0).bfloat16()
+    res = pipe.memory_forward(x.to(DEV))
+    ref = _oracle_pooled(x[0].double().numpy(), wq, 16)
+    e0 = err(res["states"][0, 0].reshape(8, 196, 896), ref["states"][0])
+    e1 = err(res["states"][0, 1].reshape(8, 196, 896), ref["states"][1])
+    assert e0 < floor["state0"] and e1 < floor["state1"], (e0, e1, floor)
     (e_seq, e_mem), = _run_vs_oracle(896, 1152, torch.float32, 16, 8, q_scale=8.0, x_scale=4.0, pooled=True)
     assert e_seq < 1e-3 and e_mem < 1e-3, (e_seq, e_mem)                         # fp32 noise floor of this regime
 
