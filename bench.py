@@ -195,6 +195,7 @@ def workload_config(world):
 def run_ours(args):
     import torch
     import torch.distributed as dist
+    import mavlm_b200 as M
     from mavlm_b200 import _lib, ops, synthetic
 
     steps = args.steps if args.steps is not None else 50
@@ -223,12 +224,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, n):
+    def timed(fn, n, after=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(n):
             fn()
+        if after is not None:                               # drain side streams: e1 must follow the last D2H
+            after()
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -236,30 +239,41 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    def step_device():
-        pipe(x_dev, idx, return_states=False)
+    graphed = pipe.graphed(1, FRAMES)                       # CUDA-graph replay of the whole step
+    graphed(x_dev, idx)                                     # loads the static input / index buffers once
+    streamer = M.HostStreamEncoder(pipe, 1, FRAMES)
 
-    def step_e2e():
-        x = x_host.to(dev, non_blocking=True)
-        res = pipe(x, idx, return_states=False)
-        out_host.copy_(res["sequence"], non_blocking=True)
+    def step_device():                                      # inputs resident in HBM (the graph's static buffer)
+        graphed(None, None)
+
+    def step_e2e():                                         # pinned host in -> pinned host out, copies overlapped
+        streamer.submit(x_host, None, out_host)
+
+    torch.cuda.synchronize()
+    l0 = lib.mavlm_launch_count()
+    pipe(x_dev, idx, return_states=False)                   # one eager step: counts the kernels a step launches
+    torch.cuda.synchronize()
+    launches_per_step = lib.mavlm_launch_count() - l0
 
     for _ in range(warmup):
         step_device()
     sampler = ClockSampler(local) if rank == 0 else None
     time.sleep(0.15)
-    l0 = lib.mavlm_launch_count()
     if sampler:
         sampler.mark_start()
     ms_total = timed(step_device, steps)
     if sampler:
         sampler.mark_end()
-    launches = lib.mavlm_launch_count() - l0
+    launches = launches_per_step * steps                    # kernels replayed inside the timed region
     clocks = sampler.stop() if sampler else None
 
     for _ in range(3):
         step_e2e()
-    ms_e2e = timed(step_e2e, steps)
+    streamer.synchronize()
+    ms_e2e = timed(lambda: step_e2e(), steps, after=streamer.synchronize)
+
+    def step_eager():
+        pipe(x_dev, idx, return_states=False)
 
     # ---- instrumented pass: per-launch CUDA-event timing of the dominant kernel (tcgen05 GEMM) ----
     recs = []
@@ -280,7 +294,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         e0.record()
         for _ in range(prof_steps):
-            step_device()
+            step_eager()
         e1.record()
         torch.cuda.synchronize()
         prof_ms = e0.elapsed_time(e1)
@@ -331,7 +345,8 @@ def run_ours(args):
             "dtype": "bf16", "data": "synthetic", "config": workload_config(world), "clocks": clocks,
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": x_host.numel() * x_host.element_size(),
                     "d2h_bytes_per_step": out_host.numel() * out_host.element_size(), "ms_per_step": ms_e2e / steps},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": int(launches), "launch_mode": "one CUDA graph replay per step (kernels counted from an "
+            "eager step)", "roofline": roofline, "cpu_baseline": cpu,
             "algorithmic_gflop_per_step": gflop_step,
             "path_tflops": gflop_step * 1e9 / (ms_total / steps * 1e-3) / 1e12,
             "path_frac_of_peak": gflop_step * 1e9 / (ms_total / steps * 1e-3) / 1e12 / peaks["tflops"]}

@@ -12,11 +12,12 @@ from . import _lib  # noqa: F401
 from .modules import (Attention, Config, MemoryFuserMLP, Residual, TemporalPositionalEncoding, TransformerLayer,
                       TransformerProjector, VisionProjector, build_memory_fuser, build_vision_projector,
                       fine_frame_indices, get_2dPool, sample_frame_indices, uniform_segment_variant)
-from .pipeline import FRAME_PROMPT_IDS, MEMORY_PROMPT_IDS, VisualMemoryPipeline
+from .pipeline import (FRAME_PROMPT_IDS, MEMORY_PROMPT_IDS, GraphedPipeline, HostStreamEncoder,
+                       VisualMemoryPipeline)
 
 __all__ = [
     "Attention", "Config", "MemoryFuserMLP", "Residual", "TemporalPositionalEncoding", "TransformerLayer",
     "TransformerProjector", "VisionProjector", "build_memory_fuser", "build_vision_projector", "fine_frame_indices",
-    "get_2dPool", "sample_frame_indices", "uniform_segment_variant", "VisualMemoryPipeline", "MEMORY_PROMPT_IDS",
+    "get_2dPool", "sample_frame_indices", "uniform_segment_variant", "VisualMemoryPipeline", "GraphedPipeline", "HostStreamEncoder", "MEMORY_PROMPT_IDS",
     "FRAME_PROMPT_IDS",
 ]

@@ -14,6 +14,10 @@ struct Vec<float> {
     float4 t = __ldg(reinterpret_cast<const float4*>(p));
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   }
+  __device__ static void load_plain(const float* p, float (&v)[4]) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
   __device__ static void store(float* p, const float (&v)[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   }
@@ -23,6 +27,15 @@ struct Vec<__nv_bfloat16> {
   static constexpr int N = 8;
   __device__ static void load(const __nv_bfloat16* p, float (&v)[8]) {
     uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+  __device__ static void load_plain(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 t = *reinterpret_cast<const uint4*>(p);
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -104,7 +117,7 @@ __global__ void __launch_bounds__(256) pool_pe_kernel(const T* __restrict__ x, T
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) add_pe_kernel(const T* __restrict__ x, T* __restrict__ y,
+__global__ void __launch_bounds__(256) add_pe_kernel(const T* x, T* y,  // y may alias x (in place)
                                                      const float* __restrict__ pe, const int64_t* __restrict__ fidx,
                                                      int frames, int tokens, int dim) {
   constexpr int V = Vec<T>::N;
@@ -116,7 +129,7 @@ __global__ void __launch_bounds__(256) add_pe_kernel(const T* __restrict__ x, T*
     const long long row = i / groups;
     const int f = static_cast<int>(row / tokens);
     float v[V];
-    Vec<T>::load(x + row * dim + g * V, v);
+    Vec<T>::load_plain(x + row * dim + g * V, v);
     const float* p = pe + fidx[f] * dim + g * V;
 #pragma unroll
     for (int k = 0; k < V; ++k) v[k] += __ldg(p + k);

@@ -159,12 +159,16 @@ def pool_pe(x: torch.Tensor, *, side: int, stride: int = 2, mode: str = "bilinea
     return y
 
 
-def add_pe(x: torch.Tensor, pe_table: torch.Tensor, frame_idx: torch.Tensor) -> torch.Tensor:
-    """x [T, N, C] + pe_table[frame_idx][:, None, :]."""
+def add_pe(x: torch.Tensor, pe_table: torch.Tensor, frame_idx: torch.Tensor,
+           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [T, N, C] + pe_table[frame_idx][:, None, :]  (out may alias x: the kernel is elementwise)."""
     _need_cuda(x, pe_table, frame_idx)
     t, n, c = x.shape
-    x = x.contiguous()
-    y = torch.empty_like(x)
+    if not x.is_contiguous():
+        if out is x:
+            raise RuntimeError("mavlm.add_pe: in-place needs a contiguous tensor")
+        x = x.contiguous()
+    y = torch.empty_like(x) if out is None else out
     frame_idx = frame_idx.to(device=x.device, dtype=torch.int64).contiguous()
     st = _lib.load().mavlm_add_pe_fwd(_ptr(x), _ptr(y), _ptr(pe_table), _ptr(frame_idx), t, n, c, dtype_code(x),
                                       _stream())

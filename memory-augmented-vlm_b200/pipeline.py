@@ -41,7 +41,7 @@ class VisualMemoryPipeline(nn.Module):
                  memory_fuser: MemoryFuserMLP, positional_encoding: TemporalPositionalEncoding,
                  token_type_embedding: nn.Embedding, image_newline: torch.Tensor, embed_tokens: nn.Embedding,
                  chunk_size: int = 32, max_fine_frames: int = 32, num_patches_per_side: int = 27,
-                 pool_stride: int = 2, projector_frames_per_pass: int = 64):
+                 pool_stride: int = 2, projector_frames_per_pass: int = 64, pool_before_w2: bool = True):
         super().__init__()
         self.mm_projector = mm_projector
         self.recurrent_memory_transformer = recurrent_memory_transformer
@@ -55,6 +55,8 @@ class VisualMemoryPipeline(nn.Module):
         self.side = num_patches_per_side
         self.pool_stride = pool_stride
         self.projector_frames_per_pass = projector_frames_per_pass
+        self.pool_before_w2 = pool_before_w2
+        self.pool_mode = "bilinear"
         self._consts: Dict = {}
 
     # ------------------------------------------------------------------------------------------
@@ -87,20 +89,34 @@ class VisualMemoryPipeline(nn.Module):
 
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def encode_frames(self, tower_tokens: torch.Tensor, frame_idx: torch.Tensor) -> torch.Tensor:
+    def encode_frames(self, tower_tokens: torch.Tensor, frame_idx: torch.Tensor, *, validate: bool = True) -> torch.Tensor:
         """[N, side*side, Dv] tower tokens (+ original frame indices [N]) -> pooled + PE'd [N, P, D]
-        (encode_images -> get_2dPool -> positional_encoding, llava_arch.py:481-511)."""
+        (encode_images -> get_2dPool -> positional_encoding, llava_arch.py:481-511).
+
+        Bilinear pooling is a fixed convex combination of tokens, so it commutes with the projector's
+        second (affine) layer: pool(h W2^T + b2) = pool(h) W2^T + b2 (tap weights sum to 1; verified to
+        5e-16 in fp64).  With `pool_before_w2` (default) the second GEMM runs on 196 instead
+        of 729 rows per frame (3.7x fewer); `pool_before_w2=False` keeps the reference's operation order."""
         pe = self.positional_encoding
-        pe.validate(frame_idx)
+        if validate:
+            pe.validate(frame_idx)
         frame_idx = frame_idx.to(tower_tokens.device)
         n = tower_tokens.shape[0]
         outs = []
         step = max(1, self.projector_frames_per_pass)
         table = pe.table()
+        mp = self.mm_projector
         for i in range(0, n, step):
-            y = self.mm_projector(tower_tokens[i:i + step])
-            outs.append(ops.pool_pe(y, side=self.side, stride=self.pool_stride, mode="bilinear", pe_table=table,
-                                    frame_idx=frame_idx[i:i + step]))
+            x = tower_tokens[i:i + step]
+            if self.pool_before_w2 and self.pool_mode == "bilinear":
+                h = ops.linear(x, mp[0].weight, mp[0].bias, act=ACT_GELU_ERF)
+                hp = ops.pool_pe(h, side=self.side, stride=self.pool_stride, mode="bilinear")
+                y = ops.linear(hp, mp[2].weight, mp[2].bias)
+                outs.append(ops.add_pe(y, table, frame_idx[i:i + step], out=y))
+            else:
+                y = mp(x)
+                outs.append(ops.pool_pe(y, side=self.side, stride=self.pool_stride, mode=self.pool_mode,
+                                        pe_table=table, frame_idx=frame_idx[i:i + step]))
         return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
 
     @torch.no_grad()
@@ -161,7 +177,10 @@ class VisualMemoryPipeline(nn.Module):
         # fuser + assembly: state written at chunk t sits in slot t % cap; reference order is oldest first
         first = n_chunks - n_keep
         n_fine = min(self.max_fine_frames, f)
-        fine_idx = fine_frame_indices(f, self.max_fine_frames).to(dev)
+        fkey = ("fine", f, str(dev))
+        if fkey not in self._consts:                                    # cached: no H2D copy on the hot path / in graphs
+            self._consts[fkey] = fine_frame_indices(f, self.max_fine_frames).to(dev)
+        fine_idx = self._consts[fkey]
         seq_len = self.sequence_length(n_keep, n_fine, drop_frames)
         if seq_out is None:
             seq_out = torch.empty((b, seq_len, d), dtype=dtype, device=dev)
@@ -180,13 +199,104 @@ class VisualMemoryPipeline(nn.Module):
                          self.embed_tokens.weight.detach(), pm_ids, pf_ids, drop_frames)
         out = {"sequence": seq_out}
         if return_states:
-            order = [(first + i) % cap for i in range(n_keep)]
-            out["states"] = ring_states[:, order]                       # [B, n_keep, Lq, D], oldest first
+            if first == 0:
+                out["states"] = ring_states[:, :n_keep]                 # [B, n_keep, Lq, D], oldest first
+            else:
+                order = [(first + i) % cap for i in range(n_keep)]
+                out["states"] = torch.cat([ring_states[:, s_:s_ + 1] for s_ in order], dim=1)
         return out
 
     @torch.no_grad()
-    def forward(self, tower_tokens: torch.Tensor, frame_idx: torch.Tensor, **kw) -> Dict[str, torch.Tensor]:
+    def forward(self, tower_tokens: torch.Tensor, frame_idx: torch.Tensor, *, validate: bool = True,
+                **kw) -> Dict[str, torch.Tensor]:
         """tower_tokens [B, F, side*side, Dv], frame_idx [B, F] (original-video indices for the PE)."""
         b, f = tower_tokens.shape[:2]
-        z = self.encode_frames(tower_tokens.reshape(b * f, *tower_tokens.shape[2:]), frame_idx.reshape(-1))
+        z = self.encode_frames(tower_tokens.reshape(b * f, *tower_tokens.shape[2:]), frame_idx.reshape(-1),
+                               validate=validate)
         return self.memory_forward(z.reshape(b, f, *z.shape[1:]), **kw)
+
+    def graphed(self, batch: int, frames: int, *, return_states: bool = False) -> "GraphedPipeline":
+        """CUDA-graph replay of forward() for a fixed (batch, frames): the ~45 dependent launches of a step
+        become one graph launch (the recurrence is launch-latency sensitive: ~25 kernels per chunk)."""
+        key = ("graph", batch, frames, return_states)
+        if key not in self._consts:
+            self._consts[key] = GraphedPipeline(self, batch, frames, return_states=return_states)
+        return self._consts[key]
+
+
+class GraphedPipeline:
+    """forward() captured once into a CUDA graph (static input / output buffers owned here)."""
+
+    def __init__(self, pipe: VisualMemoryPipeline, batch: int, frames: int, *, return_states: bool = False):
+        self.pipe = pipe
+        p0 = pipe.mm_projector[0].weight
+        dev, dtype = p0.device, p0.dtype
+        self.x = torch.zeros((batch, frames, pipe.side * pipe.side, p0.shape[1]), dtype=dtype, device=dev)
+        self.idx = torch.zeros((batch, frames), dtype=torch.int64, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                                   # warm-up: packs weights, fills constant caches
+            for _ in range(2):
+                pipe.forward(self.x, self.idx, validate=False, return_states=return_states)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = pipe.forward(self.x, self.idx, validate=False, return_states=return_states)
+
+    @torch.no_grad()
+    def __call__(self, tower_tokens: Optional[torch.Tensor], frame_idx: Optional[torch.Tensor]):
+        """Copy the inputs into the static buffers (skipped when they ARE the static buffers / None) and
+        replay.  The returned tensors are overwritten by the next call."""
+        if frame_idx is not None and frame_idx is not self.idx:
+            self.pipe.positional_encoding.validate(frame_idx)           # host-side, like position_encoding.py:73-76
+            self.idx.copy_(frame_idx.reshape(self.idx.shape), non_blocking=True)
+        if tower_tokens is not None and tower_tokens is not self.x:
+            self.x.copy_(tower_tokens.reshape(self.x.shape), non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+
+class HostStreamEncoder:
+    """Host-buffer front end: pinned host tower tokens in, pinned host sequence out, with the H2D copy of
+    video i+1 and the D2H copy of result i-1 overlapped with the graph replay of video i on three
+    streams (copy-in / compute / copy-out).  This is the public end-to-end call bench.py's `e2e` times."""
+
+    def __init__(self, pipe: VisualMemoryPipeline, batch: int, frames: int):
+        self.g = pipe.graphed(batch, frames)
+        dev = self.g.x.device
+        self.dev = dev
+        self.stage_in = torch.empty_like(self.g.x)
+        self.stage_out = torch.empty_like(self.g.out["sequence"])
+        self.s_in, self.s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        self.ev_in, self.ev_x_free = torch.cuda.Event(), torch.cuda.Event()
+        self.ev_out_ready, self.ev_out_free = torch.cuda.Event(), torch.cuda.Event()
+        self._first = True
+
+    @torch.no_grad()
+    def submit(self, host_tokens: torch.Tensor, frame_idx: torch.Tensor, host_out: torch.Tensor) -> None:
+        """Enqueue one batch: host_tokens (pinned) -> device -> path -> host_out (pinned).  Asynchronous;
+        call synchronize() before reading host_out."""
+        cur = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self.s_in):
+            if not self._first:
+                self.s_in.wait_event(self.ev_x_free)                    # staging buffer consumed by the previous step
+            self.stage_in.copy_(host_tokens.reshape(self.stage_in.shape), non_blocking=True)
+            self.ev_in.record(self.s_in)
+        cur.wait_event(self.ev_in)
+        self.g.x.copy_(self.stage_in, non_blocking=True)
+        self.ev_x_free.record(cur)
+        out = self.g(None, frame_idx if frame_idx is not None else None)
+        if not self._first:
+            cur.wait_event(self.ev_out_free)                            # previous D2H finished reading stage_out
+        self.stage_out.copy_(out["sequence"], non_blocking=True)
+        self.ev_out_ready.record(cur)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.ev_out_ready)
+            host_out.copy_(self.stage_out, non_blocking=True)
+            self.ev_out_free.record(self.s_out)
+        self._first = False
+
+    def synchronize(self) -> None:
+        self.s_out.synchronize()
+        torch.cuda.current_stream(self.dev).synchronize()

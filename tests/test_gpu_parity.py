@@ -324,3 +324,40 @@ def test_error_behaviour_on_device():
     with pytest.raises(RuntimeError, match="head_dim"):
         q = torch.zeros(1, 8, 8 * 64, device=DEV, dtype=torch.bfloat16)
         ops.xattn(q, q, q, 8)                                                    # bf16 tier: head_dim 64 unsupported
+
+
+def test_graph_replay_and_host_streaming_match_eager():
+    pipe, _ = synthetic.build_pipeline(896, 1152, dtype=torch.bfloat16, chunk_size=16, device=DEV)
+    x = synthetic.synthetic_tower_tokens(1, 32, 1152, pin=True)
+    idx = torch.arange(32)[None]
+    eager = pipe(x.to(DEV), idx)["sequence"].clone()
+    g = pipe.graphed(1, 32)
+    out1 = g(x.to(DEV), idx)["sequence"].clone()
+    out2 = g(None, None)["sequence"].clone()                                     # replay on the static buffers
+    assert torch.equal(out1, eager) and torch.equal(out2, eager)
+    enc = M.HostStreamEncoder(pipe, 1, 32)
+    host_out = [torch.empty(eager.shape, dtype=eager.dtype, pin_memory=True) for _ in range(3)]
+    xs = [x, (x.float() * 0.5).bfloat16().pin_memory(), x]
+    for xi, ho in zip(xs, host_out):
+        enc.submit(xi, None, ho)
+    enc.synchronize()
+    assert torch.equal(host_out[0], eager.cpu()) and torch.equal(host_out[2], eager.cpu())
+    assert not torch.equal(host_out[1], eager.cpu())
+    with pytest.raises(ValueError):
+        g(x.to(DEV), torch.full((1, 32), 600))                                   # PE index check survives the graph path
+
+
+def test_pool_before_w2_equals_reference_order():
+    """pool(h) W2^T + b2 == pool(h W2^T + b2): the commuted projector (default) and the reference's
+    operation order agree to fp32 rounding, and both match the oracle."""
+    pipe, w = synthetic.build_pipeline(128, 64, dtype=torch.float32, chunk_size=8, device=DEV)
+    x = synthetic.synthetic_tower_tokens(1, 8, 64, dtype=torch.float32).to(DEV)
+    idx = torch.arange(8, device=DEV)
+    pipe.pool_before_w2 = True
+    z1 = pipe.encode_frames(x[0], idx)
+    pipe.pool_before_w2 = False
+    z2 = pipe.encode_frames(x[0], idx)
+    wq = synthetic.round_weights_like(w, torch.float32)
+    ref = O.add_temporal_pe(O.get_2d_pool(O.mm_projector(x[0].double().cpu().numpy(), wq)), np.arange(8),
+                            wq["positional_encoding.frame_embed"])
+    assert err(z1, ref) < FP32_TOL and err(z2, ref) < FP32_TOL
