@@ -12,6 +12,7 @@ from . import _lib  # noqa: F401
 from .modules import (Attention, Config, MemoryFuserMLP, Residual, TemporalPositionalEncoding, TransformerLayer,
                       TransformerProjector, VisionProjector, build_memory_fuser, build_vision_projector,
                       fine_frame_indices, get_2dPool, sample_frame_indices, uniform_segment_variant)
+from .patch import convert_rmt, patch_llava
 from .pipeline import (FRAME_PROMPT_IDS, MEMORY_PROMPT_IDS, GraphedPipeline, HostStreamEncoder,
                        VisualMemoryPipeline)
 
@@ -19,5 +20,5 @@ __all__ = [
     "Attention", "Config", "MemoryFuserMLP", "Residual", "TemporalPositionalEncoding", "TransformerLayer",
     "TransformerProjector", "VisionProjector", "build_memory_fuser", "build_vision_projector", "fine_frame_indices",
     "get_2dPool", "sample_frame_indices", "uniform_segment_variant", "VisualMemoryPipeline", "GraphedPipeline", "HostStreamEncoder", "MEMORY_PROMPT_IDS",
-    "FRAME_PROMPT_IDS",
+    "FRAME_PROMPT_IDS", "patch_llava", "convert_rmt",
 ]
