@@ -132,7 +132,10 @@ __global__ void __launch_bounds__(256) add_pe_kernel(const T* x, T* y,  // y may
     Vec<T>::load_plain(x + row * dim + g * V, v);
     const float* p = pe + fidx[f] * dim + g * V;
 #pragma unroll
-    for (int k = 0; k < V; ++k) v[k] += __ldg(p + k);
+    for (int k = 0; k < V; k += 4) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(p + k));
+      v[k] += q.x; v[k + 1] += q.y; v[k + 2] += q.z; v[k + 3] += q.w;
+    }
     Vec<T>::store(y + row * dim + g * V, v);
   }
 }

@@ -5,17 +5,22 @@
 //   warp 1  : MMA issuer    (one elected lane issues tcgen05.mma cta_group::1, M=128 x N=BN x K=16;
 //                            accumulators double-buffered in TMEM so the epilogue of tile i overlaps
 //                            the main loop of tile i+1; tcgen05.commit releases smem stages)
-//   warps 2-5: epilogue     (tcgen05.ld 32x32b -> registers -> bias / GELU(erf) / ReLU / residual ->
-//                            bf16 or fp32 rows, 16-byte vector stores)
-// Tiles are walked m-fastest so that the CTAs running concurrently share one W slab (read once from
-// HBM, re-used out of L2) while A (a few MB) stays L2 resident.
+//   warps 2-9: epilogue     (tcgen05.ld 32x32b -> registers -> bias / GELU(erf) / ReLU / residual ->
+//                            bf16 or fp32 rows, 16-byte vector stores); two warps per TMEM lane quadrant,
+//                            each taking half of the tile's columns (the erf epilogue of the K=1152
+//                            projector GEMM was epilogue-bound with four warps: 55 % tensor-active)
+// Tiles are rasterised in groups of 16 M-tiles, m-fastest inside a group and sweeping N, so the ~148
+// tiles in flight share ~16 A row-blocks and ~9 W slabs (L2-resident working set of ~30 MB); plain
+// m-fastest order re-read A once per N-slab wave (3.2 GB of DRAM reads for the 12544x14336x3584 GEMM).
 #include "common.cuh"
 
 namespace mavlm {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 8;                         // two warps per TMEM lane quadrant, splitting the columns
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;   // 320
+constexpr int GEMM_GROUP_M = 16;                         // tile rasterisation: sweep N inside groups of 16 M-tiles
 
 struct GemmTcParams {
   int M, N, K;
@@ -41,6 +46,15 @@ struct GemmCfg {
   // ring | bias[2][BN] | addv[2][BN] | barriers | tmem ptr ; +1024 for manual alignment
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * BN * 4 + (2 * STAGES + 4) * 8 + 16 + 1024;
 };
+
+__device__ __forceinline__ void gemm_tile_coords(int tile, int m_tiles, int n_tiles, int& m_blk, int& n_blk) {
+  const int per_group = GEMM_GROUP_M * n_tiles;
+  const int g = tile / per_group, r = tile - g * per_group;
+  const int first_m = g * GEMM_GROUP_M;
+  const int gm = min(GEMM_GROUP_M, m_tiles - first_m);
+  m_blk = first_m + r % gm;
+  n_blk = r / gm;
+}
 
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -72,7 +86,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);
+      mbar_init(&tempty[a], GEMM_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -87,7 +101,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % p.m_tiles) * GEMM_BM, n0 = (tile / p.m_tiles) * BN;
+        int m_blk, n_blk;
+        gemm_tile_coords(tile, p.m_tiles, p.n_tiles, m_blk, n_blk);
+        const int m0 = m_blk * GEMM_BM, n0 = n_blk * BN;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
@@ -125,26 +141,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     const int q = warp & 3;                     // TMEM lane quadrant this warp may access
-    const int et = (warp - 2) * 32 + lane;      // 0..127 within the epilogue group
+    const int half = (warp - 2) >> 2;           // which half of the tile's columns this warp converts
+    const int et = (warp - 2) * 32 + lane;      // 0..255 within the epilogue group
     const int row_in_tile = q * 32 + lane;
+    constexpr int CHUNKS = BN / 32, CPH = CHUNKS / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile % p.m_tiles) * GEMM_BM, n0 = (tile / p.m_tiles) * BN;
+      int m_blk, n_blk;
+      gemm_tile_coords(tile, p.m_tiles, p.n_tiles, m_blk, n_blk);
+      const int m0 = m_blk * GEMM_BM, n0 = n_blk * BN;
       float* bs = bias_s + acc * BN;
       float* as = addv_s + acc * BN;
-      for (int j = et; j < BN; j += 128) {
+      for (int j = et; j < BN; j += 32 * GEMM_EPI_WARPS) {
         const int n = n0 + j;
         bs[j] = (p.bias != nullptr && n < p.N) ? __bfloat162float(p.bias[n]) : 0.f;
         as[j] = (p.addvec != nullptr && n < p.N) ? __bfloat162float(p.addvec[n]) : 0.f;
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 32 * GEMM_EPI_WARPS);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const int row = m0 + row_in_tile;
       const bool row_ok = row < p.M;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half * CPH; c < (half + 1) * CPH; ++c) {
         uint32_t r[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::ACC_STRIDE + c * 32, r);
         tmem_ld_wait();
