@@ -134,6 +134,17 @@ def host_weights_fp32(seed=0):
     return {k: v.astype(np.float32) for k, v in w.items()}
 
 
+def use_all_host_cores() -> None:
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must use every host core."""
+    n = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n, user_api="blas")
+        threadpool_limits(limits=n, user_api="openmp")
+    except Exception:
+        pass
+
+
 def blas_threads() -> int:
     try:
         from threadpoolctl import threadpool_info
@@ -150,6 +161,7 @@ def run_reference(args):
     if rank != 0:
         return
     import numpy as np
+    use_all_host_cores()
     steps = args.steps if args.steps is not None else 3
     warmup = args.warmup if args.warmup is not None else 1
     w32 = host_weights_fp32()
@@ -177,7 +189,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * t / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(1), "gpu_launches": 0,
+            "config": workload_config(int(os.environ.get("WORLD_SIZE", "1"))), "gpu_launches": 0,
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -328,6 +340,7 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         import numpy as np
+        use_all_host_cores()
         w32 = {k: v.astype(np.float32) for k, v in weights.items()}
         x32 = x_host[0].float().numpy()
         oracle_pass(2, CHUNK, w32, x32, w32["positional_encoding.frame_embed"])   # BLAS warm-up

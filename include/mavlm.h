@@ -73,6 +73,9 @@ MAVLM_API int mavlm_gemm_bias_act_fwd(const void* A, int64_t lda, const void* W,
                             int64_t ldr, const void* addvec, void* C, int64_t ldc, int M, int N, int K, int act,
                             int dtype, int out_dtype, void* stream);
 
+/* ---- tensor.to(dtype) between the two tiers (fp32 <-> bf16), contiguous n elements. */
+MAVLM_API int mavlm_cast_fwd(const void* x, void* y, int64_t n, int src_dtype, int dst_dtype, void* stream);
+
 /* ---- nn.LayerNorm over the last dim (MemoryController.py:24,28): y = (x-mean)/sqrt(var+eps)*g+b.
  * x in x_dtype (MAVLM_F32 pre-LN sums or `dtype`), gamma/beta and y in dtype. */
 MAVLM_API int mavlm_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, int rows, int dim, float eps,

@@ -9,7 +9,7 @@ interface), `pipeline.py` (chunk scheduler + fused path), `patch.py` (drop-in fo
 `dist.py` (video sharding over ranks).
 """
 from . import _lib  # noqa: F401
-from .modules import (Attention, Config, MemoryFuserMLP, Residual, TemporalPositionalEncoding, TransformerLayer,
+from .modules import (Attention, Config, MemoryFuser, MemoryFuserMLP, Residual, TemporalPositionalEncoding, TransformerLayer,
                       TransformerProjector, VisionProjector, build_memory_fuser, build_vision_projector,
                       fine_frame_indices, get_2dPool, sample_frame_indices, uniform_segment_variant)
 from .patch import convert_rmt, patch_llava
@@ -17,7 +17,7 @@ from .pipeline import (FRAME_PROMPT_IDS, MEMORY_PROMPT_IDS, GraphedPipeline, Hos
                        VisualMemoryPipeline)
 
 __all__ = [
-    "Attention", "Config", "MemoryFuserMLP", "Residual", "TemporalPositionalEncoding", "TransformerLayer",
+    "Attention", "Config", "MemoryFuser", "MemoryFuserMLP", "Residual", "TemporalPositionalEncoding", "TransformerLayer",
     "TransformerProjector", "VisionProjector", "build_memory_fuser", "build_vision_projector", "fine_frame_indices",
     "get_2dPool", "sample_frame_indices", "uniform_segment_variant", "VisualMemoryPipeline", "GraphedPipeline", "HostStreamEncoder", "MEMORY_PROMPT_IDS",
     "FRAME_PROMPT_IDS", "patch_llava", "convert_rmt",

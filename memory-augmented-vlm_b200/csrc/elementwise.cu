@@ -275,6 +275,38 @@ __global__ void __launch_bounds__(128) assemble_kernel(T* __restrict__ seq, cons
   }
 }
 
+// dtype conversion (fp32 <-> bf16), 8 elements per thread
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long n) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 8;
+  for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 8; i < n; i += stride) {
+    if (i + 8 <= n) {
+      float v[8];
+      if (sizeof(TI) == 4) {
+        const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + i);
+        const float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + i + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      } else {
+        Vec<__nv_bfloat16>::load(reinterpret_cast<const __nv_bfloat16*>(x) + i, v);
+      }
+      if (sizeof(TO) == 4) {
+        float* o = reinterpret_cast<float*>(y) + i;
+        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      } else {
+        Vec<__nv_bfloat16>::store(reinterpret_cast<__nv_bfloat16*>(y) + i, v);
+      }
+    } else {
+      for (long long k = i; k < n; ++k) {
+        float f = sizeof(TI) == 4 ? reinterpret_cast<const float*>(x)[k]
+                                  : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[k]);
+        if (sizeof(TO) == 4) reinterpret_cast<float*>(y)[k] = f;
+        else reinterpret_cast<__nv_bfloat16*>(y)[k] = __float2bfloat16(f);
+      }
+    }
+  }
+}
+
 static int grid_for(long long total_threads, int block) {
   long long b = (total_threads + block - 1) / block;
   const long long cap = static_cast<long long>(sm_count()) * 32;  // grid-stride beyond 32 CTAs/SM
@@ -365,6 +397,24 @@ int mavlm_add_pe_fwd(const void* x, void* y, const float* pe_table, const int64_
     add_pe_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x),
                                                        static_cast<__nv_bfloat16*>(y), pe_table, frame_idx, frames,
                                                        tokens, dim);
+  MAVLM_LAUNCH_OK();
+  return MAVLM_OK;
+}
+
+int mavlm_cast_fwd(const void* x, void* y, int64_t n, int src_dtype, int dst_dtype, void* stream) {
+  MAVLM_REQUIRE((src_dtype == MAVLM_F32 || src_dtype == MAVLM_BF16) && (dst_dtype == MAVLM_F32 || dst_dtype == MAVLM_BF16) &&
+                    src_dtype != dst_dtype, MAVLM_E_INVALID, "cast: dtypes must be f32 <-> bf16");
+  MAVLM_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
+                MAVLM_E_INVALID, "cast: pointers must be 16-byte aligned");
+  if (n == 0) return MAVLM_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = grid_for((n + 7) / 8, 256);
+  if (src_dtype == MAVLM_F32)
+    cast_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const float*>(x),
+                                                             static_cast<__nv_bfloat16*>(y), n);
+  else
+    cast_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x),
+                                                             static_cast<float*>(y), n);
   MAVLM_LAUNCH_OK();
   return MAVLM_OK;
 }

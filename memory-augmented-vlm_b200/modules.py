@@ -150,9 +150,17 @@ class Attention(nn.Module):
             src = src if src.dim() == 3 else src.unsqueeze(0)
             kv_projected = self.project_kv(src)
         hd = h * dhp
+        scale = 1.0 / math.sqrt(self.attention_head_size)
         q = ops.linear(x, p["wq"], p["bq"])
-        ctx, _, cs = ops.xattn(q, kv_projected[..., :hd], kv_projected[..., hd:], h, head_dim=dhp,
-                               scale=1.0 / math.sqrt(self.attention_head_size), want_col_scores=col_scores)
+        fp32 = q.dtype == torch.float32
+        ctx, _, cs = ops.xattn(q, kv_projected[..., :hd], kv_projected[..., hd:], h, head_dim=dhp, scale=scale,
+                               want_col_scores=col_scores and fp32)
+        if col_scores and not fp32:
+            # frame scores (MemoryController.py:135) need normalised probabilities, which the fused bf16 kernel
+            # never forms: diagnostics-only second pass through the fp32 tier on the same q / k.
+            qf = ops.cast(q, torch.float32)
+            kf = ops.cast(kv_projected[..., :hd].contiguous(), torch.float32)
+            _, _, cs = ops.xattn(qf, kf, kf, h, head_dim=dhp, scale=scale, want_col_scores=True)
         self.last_col_scores = cs
         out = self.residual(ctx, x, weight=p["wo"])
         return out.reshape(hidden_states.shape), None
@@ -186,8 +194,8 @@ class TransformerProjector(nn.Module):
     """Recurrent memory transformer   (MemoryController.py:74-158).
 
     forward(image_features [C, P, D]) -> (memory_cache, frame_attn_scores): the live cache list (<= cache_size
-    states of [M, P, D]) and the list of per-chunk frame scores ([C] each, only filled when
-    config.frame_scores and the fp32 tier is active).  State lives on the module like the reference
+    states of [M, P, D]) and the list of per-chunk frame scores ([C] each, filled when config.frame_scores;
+    in bf16 they cost an extra fp32-tier pass over the last layer's scores).  State lives on the module like the reference
     (`rmt.memory_cache = []` resets it, llava_arch.py:532); frame_attn_scores is cleared with it."""
 
     def __init__(self, config=None):
@@ -248,7 +256,7 @@ class TransformerProjector(nn.Module):
             memory_tokens = self.initial_state(dtype)
         memory_2d = memory_tokens.reshape(1, self.num_memory_tokens * p, d)
         image_2d = image_features.reshape(1, f * p, d)
-        want_scores = bool(getattr(self.config, "frame_scores", False)) and dtype == torch.float32
+        want_scores = bool(getattr(self.config, "frame_scores", False))
         last = len(self.layers) - 1
         for i, layer in enumerate(self.layers):
             memory_2d, _ = layer(memory_2d, image_2d, col_scores=want_scores and i == last)
@@ -325,6 +333,52 @@ class VisionProjector(_FusedMLP):
 
 class MemoryFuserMLP(_FusedMLP):
     """The live memory_fuser   (llava_arch.py:132-136)."""
+
+
+class MemoryFuser(nn.Module):
+    """The reference's encoder-style fuser (MemoryFuser.py:4-30; imported by llava_arch.py:40, use commented
+    out at :137-143): Linear -> nn.TransformerEncoder (post-LN, GELU(erf) FFN 4D, `num_heads` heads, LN eps
+    1e-5) -> Linear, self-attention over the tokens of each batch row.  Same constructor, same state_dict keys
+    (the nn.TransformerEncoder modules are kept as parameter containers).  Inference mode only: train-mode
+    dropout (0.1) is not implemented on this path."""
+
+    def __init__(self, hidden_dim, num_layers=2, num_heads=4, dropout=0.1, device="cuda"):
+        super().__init__()
+        self.device = device
+        self.num_heads = num_heads
+        self.dropout = dropout
+        self.input_proj = nn.Linear(hidden_dim, hidden_dim)
+        encoder_layer = nn.TransformerEncoderLayer(d_model=hidden_dim, nhead=num_heads, dim_feedforward=hidden_dim * 4,
+                                                   dropout=dropout, batch_first=True, activation="gelu")
+        self.transformer_encoder = nn.TransformerEncoder(encoder_layer, num_layers=num_layers,
+                                                         enable_nested_tensor=False)
+        self.output_proj = nn.Linear(hidden_dim, hidden_dim)
+
+    def forward(self, memory_tokens: torch.Tensor) -> torch.Tensor:
+        if self.training and self.dropout > 0:
+            raise NotImplementedError("MemoryFuser: train-mode dropout is not implemented on the B200 path; "
+                                      "call .eval()")
+        x = ops.linear(memory_tokens, self.input_proj.weight, self.input_proj.bias)
+        b, s_len, d = x.shape
+        h = self.num_heads
+        dh = d // h
+        dt = x.dtype
+        tc = dt == torch.bfloat16 and dh in (128, 448)          # head dims the fused tensor-core kernel handles
+        for layer in self.transformer_encoder.layers:
+            sa = layer.self_attn
+            if tc or dt == torch.float32:
+                qkv = ops.linear(x, sa.in_proj_weight, sa.in_proj_bias)
+                ctx, _, _ = ops.xattn(qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:], h)
+            else:                                                # e.g. 7B: dh = 896 -> fp32-tier attention on fp32 q/k/v
+                qkv = ops.linear(x, sa.in_proj_weight, sa.in_proj_bias, out_dtype=torch.float32)
+                ctx32, _, _ = ops.xattn(qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:], h)
+                ctx = ops.cast(ctx32, dt)
+            pre = ops.linear(ctx, sa.out_proj.weight, sa.out_proj.bias, resid=x, out_dtype=torch.float32)
+            x = ops.layernorm(pre, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, out_dtype=dt)
+            f = ops.linear(x, layer.linear1.weight, layer.linear1.bias, act=ACT_GELU_ERF)
+            pre = ops.linear(f, layer.linear2.weight, layer.linear2.bias, resid=x, out_dtype=torch.float32)
+            x = ops.layernorm(pre, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps, out_dtype=dt)
+        return ops.linear(x, self.output_proj.weight, self.output_proj.bias)
 
 
 def build_vision_projector(config, delay_load=False, **kwargs):

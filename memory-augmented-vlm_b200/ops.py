@@ -91,6 +91,18 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     return out2.reshape(*lead, n)
 
 
+def cast(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """x.to(dtype) for fp32 <-> bf16 (the hand-off between the tensor-core tier and the fp32 tier)."""
+    if x.dtype == dtype:
+        return x
+    _need_cuda(x)
+    x = x.contiguous()
+    y = torch.empty(x.shape, dtype=dtype, device=x.device)
+    st = _lib.load().mavlm_cast_fwd(_ptr(x), _ptr(y), x.numel(), dtype_code(x), _DTYPES[dtype], _stream())
+    _lib.check(st, "cast_fwd")
+    return y
+
+
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
               out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     _need_cuda(x, gamma, beta)

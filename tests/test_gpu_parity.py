@@ -361,3 +361,50 @@ def test_pool_before_w2_equals_reference_order():
     ref = O.add_temporal_pe(O.get_2d_pool(O.mm_projector(x[0].double().cpu().numpy(), wq)), np.arange(8),
                             wq["positional_encoding.frame_embed"])
     assert err(z1, ref) < FP32_TOL and err(z2, ref) < FP32_TOL
+
+
+def test_memory_fuser_encoder_variant_golden():
+    """MemoryFuser (MemoryFuser.py:4-30, the commented-out fuser mode): reference eval-mode goldens, fp32 and
+    bf16 (dh = 8 -> the bf16 path takes the fp32-tier attention hand-off)."""
+    z, w = _golden("projector_fuser.npz")
+    for nl in (1, 2):
+        enc = M.MemoryFuser(32, num_layers=nl, num_heads=4)
+        enc.load_state_dict({k[len(f"enc{nl}."):]: torch.from_numpy(v) for k, v in w.items()
+                             if k.startswith(f"enc{nl}.")}, strict=True)
+        enc = enc.to(DEV).eval()
+        x = torch.from_numpy(z[f"enc{nl}_x"]).to(DEV)
+        assert err(enc(x), z[f"enc{nl}_y"]) < 2e-5, nl
+        assert err(enc.bfloat16()(x.bfloat16()).float(), z[f"enc{nl}_y"]) < 3e-2, nl
+    enc.train()
+    with pytest.raises(NotImplementedError):
+        enc(x.bfloat16())
+    # OV-0.5B dims: dh = 224 (fp32-tier attention inside the bf16 module) against the oracle
+    torch.manual_seed(0)
+    enc = M.MemoryFuser(896, num_layers=1, num_heads=4).eval()
+    wn = {k: v.detach().double().numpy() for k, v in enc.state_dict().items()}
+    x = torch.randn(4, 196, 896)
+    ref = O.memory_fuser_encoder(x.double().numpy(), wn, num_layers=1, heads=4)
+    assert err(enc.to(DEV)(x.to(DEV)), ref) < FP32_TOL
+    wq = {k: torch.from_numpy(v).bfloat16().double().numpy() for k, v in wn.items()}
+    refq = O.memory_fuser_encoder(x.bfloat16().double().numpy(), wq, num_layers=1, heads=4)
+    assert err(enc.bfloat16()(x.bfloat16().to(DEV)).float(), refq) < BF16_TOL
+
+
+def test_frame_scores_bf16_tier():
+    """K9 (MemoryController.py:135-139) in the bf16 tier: frame scores sum to H*Lq/P = 64 and match the oracle."""
+    cfg = M.Config()
+    cfg.mm_hidden_size, cfg.mm_intermediate_size, cfg.depth, cfg.mm_dtype = 896, 3584, 2, torch.float32
+    cfg.frame_scores = True
+    torch.manual_seed(0)
+    rmt = M.TransformerProjector(cfg)
+    w = {"recurrent_memory_transformer." + k: v.detach().bfloat16().double().numpy() for k, v in rmt.state_dict().items()}
+    rmt = rmt.to(DEV).bfloat16()
+    x = torch.randn(6, 196, 896).bfloat16()
+    rmt.memory_cache = []
+    cache, scores = rmt(x.to(DEV))
+    ref_cache, ref_score = O.rmt_chunk(x.double().numpy(), [], w, want_scores=True)
+    assert len(scores) == 1 and scores[0].shape == (6,)
+    assert abs(float(scores[0].sum()) - 64.0) < 0.05
+    assert err(scores[0], ref_score) < BF16_TOL
+    rmt.memory_cache = []
+    assert rmt.frame_attn_scores == []

@@ -1,0 +1,89 @@
+#!/usr/bin/env python
+"""Sweeps for BASELINE configs 3 and 5 (parity-test / reporting cases, not the headline bench line):
+
+  config 3: OV-7B, 256 frames in 16-frame chunks, 8 videos per GPU batch (sharded over ranks by bench.py-style
+            weak scaling when run under torchrun), pooled-token input.
+  config 5: OV-7B, 1024 frames, memory slots M in {8, 32, 64} (Lq = 196*M; 128/256 with --big) x chunk in
+            {8, 16, 32}, pooled-token input, max_frames 1024.
+
+    python tools/sweep.py [config3] [config5] [--big]      -> gpurun_out/sweep.json (+ stdout table)
+Per point: ms, frames/s, algorithmic TFLOP/s (SURVEY.md §8d formulas, memory path only) and its fraction of
+the measured sustained bf16 peak.
+"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from mavlm_b200 import synthetic  # noqa: E402
+
+
+def algo_gflop(frames, chunk, lq, d=3584, p=196, depth=2, cap=10):
+    n_chunks = -(-frames // chunk)
+    fl = 0.0
+    for t in range(n_chunks):
+        c = min(chunk, frames - t * chunk)
+        fl += depth * (4.0 * lq * d * d + 4.0 * c * p * d * d + 4.0 * lq * c * p * d + 16.0 * lq * d * d)
+        if t > 0:
+            fl += 8.0 * lq * d * d + 4.0 * lq * (min(t, cap) * lq) * d
+    fl += 16.0 * min(n_chunks, cap) * lq * d * d
+    return fl / 1e9
+
+
+def run_point(batch, frames, chunk, slots, iters=3):
+    pipe, _ = synthetic.build_pipeline(3584, 1152, dtype=torch.bfloat16, chunk_size=chunk, device="cuda:0",
+                                       num_memory_tokens=slots, max_frames=max(600, frames))
+    g = torch.Generator(device="cuda:0").manual_seed(1234)
+    z = torch.randn(batch, frames, 196, 3584, device="cuda:0", generator=g, dtype=torch.float32).bfloat16()
+    pipe.memory_forward(z, return_states=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        pipe.memory_forward(z, return_states=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    gf = batch * algo_gflop(frames, chunk, 196 * slots)
+    del pipe, z
+    torch.cuda.empty_cache()
+    return {"batch": batch, "frames": frames, "chunk": chunk, "slots": slots, "lq": 196 * slots, "ms": ms,
+            "frames_per_s": batch * frames / ms * 1e3, "algorithmic_tflops": gf / ms, "gflop": gf}
+
+
+def main():
+    peak = 1357.8
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peak = json.load(open(pk)).get("bf16_tflops_sustained", peak)
+    which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["config3", "config5"]
+    out = []
+    if "config3" in which:
+        for b in (1, 8):
+            out.append(dict(run_point(b, 256, 16, 8), config=3))
+    if "config5" in which:
+        slots = (8, 32, 64) + ((128, 256) if "--big" in sys.argv else ())
+        for m in slots:
+            for c in (8, 16, 32):
+                if m >= 64 and c == 8:
+                    continue                      # 128 chunks x 12.5k-row states: minutes per point
+                out.append(dict(run_point(1, 1024, c, m, iters=1 if m >= 32 else 2), config=5))
+                print(json.dumps(out[-1]), flush=True)
+    for r in out:
+        r["frac_of_peak"] = r["algorithmic_tflops"] / peak
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "sweep.json"), "w") as fh:
+        json.dump({"peak_tflops_sustained": peak, "points": out}, fh, indent=1)
+    print(f"{'cfg':>3} {'B':>2} {'F':>5} {'C':>3} {'M':>4} {'ms':>9} {'frames/s':>10} {'TFLOP/s':>8} {'frac':>5}")
+    for r in out:
+        print(f"{r['config']:>3} {r['batch']:>2} {r['frames']:>5} {r['chunk']:>3} {r['slots']:>4} {r['ms']:>9.2f} "
+              f"{r['frames_per_s']:>10.0f} {r['algorithmic_tflops']:>8.0f} {r['frac_of_peak']:>5.2f}")
+
+
+if __name__ == "__main__":
+    main()
