@@ -14,8 +14,9 @@ int xattn_fp32(const float* Q, long long ldq, long long qb, const float* K, long
                int batch, int heads, int lq, int lk, int dh, float scale, void* ws, size_t ws_bytes, cudaStream_t st);
 int xattn_bf16_tc(const __nv_bfloat16* Q, long long ldq, long long qb, const __nv_bfloat16* K, long long ldk,
                   long long kb, const __nv_bfloat16* V, long long ldv, long long vb, __nv_bfloat16* O, long long ldo,
-                  long long ob, float* lse, int batch, int heads, int lq, int lk, int dh, float scale,
-                  cudaStream_t st);
+                  long long ob, float* lse, int batch, int heads, int lq, int lk, int dh, float scale, void* ws,
+                  size_t ws_bytes, cudaStream_t st);
+size_t xattn_bf16_workspace_bytes(int batch, int heads, int lq, int lk, int dh);
 }  // namespace mavlm
 
 using namespace mavlm;
@@ -44,9 +45,9 @@ int mavlm_gemm_bias_act_fwd(const void* A, int64_t lda, const void* W, int64_t l
 }
 
 size_t mavlm_xattn_workspace_bytes(int batch, int heads, int lq, int lk, int head_dim, int dtype) {
-  (void)head_dim;
   if (dtype == MAVLM_F32) return static_cast<size_t>(batch) * heads * lq * static_cast<size_t>(lk) * sizeof(float);
-  return 0;
+  if (batch <= 0 || lq <= 0 || lk <= 0) return 0;
+  return xattn_bf16_workspace_bytes(batch, heads, lq, lk, head_dim);
 }
 
 int mavlm_xattn_fwd(const void* Q, int64_t ldq, int64_t q_batch_stride, const void* K, int64_t ldk,
@@ -66,7 +67,7 @@ int mavlm_xattn_fwd(const void* Q, int64_t ldq, int64_t q_batch_stride, const vo
   return xattn_bf16_tc(static_cast<const __nv_bfloat16*>(Q), ldq, q_batch_stride,
                        static_cast<const __nv_bfloat16*>(K), ldk, k_batch_stride,
                        static_cast<const __nv_bfloat16*>(V), ldv, v_batch_stride, static_cast<__nv_bfloat16*>(O), ldo,
-                       o_batch_stride, lse, batch, heads, lq, lk, head_dim, scale, st);
+                       o_batch_stride, lse, batch, heads, lq, lk, head_dim, scale, workspace, workspace_bytes, st);
 }
 
 /* development knob (not part of the reference-facing surface): force the GEMM N tile (0 = heuristic) */

@@ -20,6 +20,13 @@
 //              fma(raw, scale*log2e, -m)) with LAZY rescaling of O (O in TMEM is only rescaled when a
 //              row max grows by more than 2^8), P -> bf16 -> 128B-swizzled smem (double buffered).
 // TMEM budget at DH=448: 448 (O) + 64 (S) = 512 columns, which is why the key block is 64.
+//
+// Scheduling: persistent, balanced over (item, key block) units ("stream-K"): item = (batch, head, q tile),
+// U = items * key blocks; CTA c owns the contiguous unit range [c*U/G, (c+1)*U/G).  One OV-7B video is only
+// 13 q tiles x 8 heads = 104 items for 148 SMs, so an item-per-CTA grid leaves 30 % of the SMs idle.  A CTA
+// walks its range as segments (item, j0..j1): a segment that covers its whole item writes O / LSE directly,
+// a partial segment writes unnormalised fp32 (O, m, l) to a workspace slot (at most two per CTA) and
+// attn_merge_kernel combines the partials of split items with the usual log-sum-exp weights.
 #include "common.cuh"
 
 namespace mavlm {
@@ -38,8 +45,18 @@ struct AttnTcParams {
   __nv_bfloat16* O;
   long long ldo, o_batch;
   float* lse;
-  int heads;
+  int heads, qtiles, items;
+  long long units;   // items * kv_blocks
+  float* ws;         // partial slots: [grid][2] x { O fp32 [128][DH], m [128], l [128] }
 };
+
+template <int DH>
+__host__ __device__ constexpr long long attn_slot_floats() { return static_cast<long long>(ATT_BQ) * DH + 2 * ATT_BQ; }
+
+__device__ __forceinline__ void attn_cta_range(const AttnTcParams& p, int c, int grid, long long& u0, long long& u1) {
+  u0 = static_cast<long long>(c) * p.units / grid;
+  u1 = static_cast<long long>(c + 1) * p.units / grid;
+}
 
 template <int DH>
 struct AttnCfg {
@@ -49,7 +66,7 @@ struct AttnCfg {
   static constexpr int RING = (DH == 448) ? 5 : 6;
   static constexpr int TMEM_COLS = (DH + 64 <= 256) ? 256 : 512;
   static constexpr int S_COL = DH;
-  static constexpr int NBARS = 2 * RING + 7;
+  static constexpr int NBARS = 2 * RING + 9;
   static constexpr int XCHG_BYTES = 2 * 2 * ATT_BQ * 4;
   static constexpr int SMEM_BYTES = Q_BYTES + 2 * ATT_P_BYTES + RING * ATT_SLOT_BYTES + XCHG_BYTES + NBARS * 8 + 16;
 };
@@ -79,12 +96,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint64_t* s_full = q_full + 1;
   uint64_t* s_free = s_full + 1;
   uint64_t* p_full = s_free + 1;  // [2]
-  uint64_t* o_done = p_full + 2;  // [2]: PV(j) commits to o_done[j & 1] so that a parity wait is never ambiguous
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* o_done = p_full + 2;  // [2]: PV(n) commits to o_done[n & 1] so that a parity wait is never ambiguous
+  uint64_t* q_free = o_done + 2;  // all QK MMAs of a segment done: Q smem may be overwritten
+  uint64_t* o_free = q_free + 1;  // epilogue of a segment has read O out of TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * ATT_BQ, h = blockIdx.y, b = blockIdx.z;
   const int J = p.kv_blocks;
+  long long u_begin, u_end;
+  attn_cta_range(p, blockIdx.x, gridDim.x, u_begin, u_end);
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) {  // 128B-swizzle atoms need 1024-byte aligned tiles
@@ -105,6 +125,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     mbar_init(&p_full[1], ATT_SM_WARPS);
     mbar_init(&o_done[0], 1);
     mbar_init(&o_done[1], 1);
+    mbar_init(q_free, 1);
+    mbar_init(o_free, ATT_SM_WARPS);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -115,10 +137,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
   if (warp == 0) {
     if (elect_one()) {
-      mbar_expect_tx(q_full, Cfg::Q_BYTES);
-      for (int s = 0; s < NS; ++s) tma_load_3d(sQ + s * (ATT_BQ * 128), &tmQ, q_full, h * DH + 64 * s, q0, b);
       int stage = 0;
       uint32_t phase = 0;
+      int b = 0, h = 0;
       auto load_block = [&](const CUtensorMap* tm, int jj) {
         for (int ps = 0; ps < NPS; ++ps) {
           const int nsl = (NS - 2 * ps) >= 2 ? 2 : 1;
@@ -130,12 +151,25 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           if (++stage == RING) { stage = 0; phase ^= 1; }
         }
       };
-      load_block(&tmK, 0);
-      for (int j = 1; j < J; ++j) {
-        load_block(&tmK, j);
-        load_block(&tmV, j - 1);
+      int seg = 0;
+      for (long long u = u_begin; u < u_end; ++seg) {
+        const int item = static_cast<int>(u / J), j0 = static_cast<int>(u - static_cast<long long>(item) * J);
+        const int j1 = static_cast<int>(min(static_cast<long long>(J), j0 + (u_end - u)));
+        const int qt = item % p.qtiles;
+        h = (item / p.qtiles) % p.heads;
+        b = item / (p.qtiles * p.heads);
+        load_block(&tmK, j0);
+        mbar_wait(q_free, (seg & 1) ^ 1);  // previous segment's QK MMAs no longer read sQ
+        mbar_expect_tx(q_full, Cfg::Q_BYTES);
+        for (int s = 0; s < NS; ++s)
+          tma_load_3d(sQ + s * (ATT_BQ * 128), &tmQ, q_full, h * DH + 64 * s, qt * ATT_BQ, b);
+        for (int j = j0 + 1; j < j1; ++j) {
+          load_block(&tmK, j);
+          load_block(&tmV, j - 1);
+        }
+        load_block(&tmV, j1 - 1);
+        u += j1 - j0;
       }
-      load_block(&tmV, J - 1);
     }
   } else if (warp == 1) {
     if (elect_one()) {
@@ -145,10 +179,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const uint32_t s_tmem = tmem_base + Cfg::S_COL;
       int stage = 0;
       uint32_t phase = 0;
-      auto issue_pv = [&](int jj) {
-        mbar_wait(&p_full[jj & 1], (jj >> 1) & 1);
+      int n = 0;  // key blocks processed by this CTA so far (all segments): indexes the P / barrier parities
+      auto issue_pv = [&](int nn, bool first_of_segment) {
+        mbar_wait(&p_full[nn & 1], (nn >> 1) & 1);
         tc_fence_after();
-        const uint64_t p_desc = umma_desc_kmajor(smem_u32(sP + (jj & 1) * ATT_P_BYTES));
+        const uint64_t p_desc = umma_desc_kmajor(smem_u32(sP + (nn & 1) * ATT_P_BYTES));
         for (int ps = 0; ps < NPS; ++ps) {
           const bool pair = (NS - 2 * ps) >= 2;
           mbar_wait(&kv_full[stage], phase);
@@ -158,37 +193,55 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < ATT_BKV / 16; ++k)  // 16 keys per MMA: +32 B in P rows, +2 k-atoms (2 KB) in V
             umma_bf16(tmem_base + ps * 128, p_desc + 2 * k, v_desc + 128 * k, pair ? idesc_pv128 : idesc_pv64,
-                      (jj | k) != 0);
+                      !first_of_segment || k != 0);
           umma_commit(&kv_empty[stage]);
           if (++stage == RING) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&o_done[jj & 1]);
+        umma_commit(&o_done[nn & 1]);
       };
-      mbar_wait(q_full, 0);
-      tc_fence_after();
-      for (int j = 0; j < J; ++j) {
-        if (j > 0) {
-          mbar_wait(s_free, (j - 1) & 1);
-          tc_fence_after();
-        }
-        for (int ps = 0; ps < NPS; ++ps) {
-          const int nsl = (NS - 2 * ps) >= 2 ? 2 : 1;
-          mbar_wait(&kv_full[stage], phase);
-          tc_fence_after();
-          for (int e = 0; e < nsl; ++e) {
-            const int s = 2 * ps + e;
-            const uint64_t q_desc = umma_desc_kmajor(smem_u32(sQ + s * (ATT_BQ * 128)));
-            const uint64_t k_desc = umma_desc_kmajor(smem_u32(sKV + stage * ATT_SLOT_BYTES + e * ATT_SLICE_BYTES));
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(s_tmem, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, (s | k) != 0);
+      int seg = 0;
+      for (long long u = u_begin; u < u_end; ++seg) {
+        const int item = static_cast<int>(u / J), j0 = static_cast<int>(u - static_cast<long long>(item) * J);
+        const int j1 = static_cast<int>(min(static_cast<long long>(J), j0 + (u_end - u)));
+        mbar_wait(q_full, seg & 1);
+        tc_fence_after();
+        for (int j = j0; j < j1; ++j, ++n) {
+          if (n > 0) {
+            mbar_wait(s_free, (n - 1) & 1);
+            tc_fence_after();
           }
-          umma_commit(&kv_empty[stage]);
-          if (++stage == RING) { stage = 0; phase ^= 1; }
+          for (int ps = 0; ps < NPS; ++ps) {
+            const int nsl = (NS - 2 * ps) >= 2 ? 2 : 1;
+            mbar_wait(&kv_full[stage], phase);
+            tc_fence_after();
+            for (int e = 0; e < nsl; ++e) {
+              const int s = 2 * ps + e;
+              const uint64_t q_desc = umma_desc_kmajor(smem_u32(sQ + s * (ATT_BQ * 128)));
+              const uint64_t k_desc =
+                  umma_desc_kmajor(smem_u32(sKV + stage * ATT_SLOT_BYTES + e * ATT_SLICE_BYTES));
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_bf16(s_tmem, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, (s | k) != 0);
+            }
+            umma_commit(&kv_empty[stage]);
+            if (++stage == RING) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(s_full);
+          if (j == j1 - 1) umma_commit(q_free);
+          if (j > j0) {
+            if (j == j0 + 1) {  // first PV of the segment overwrites O: the previous epilogue must be done with it
+              mbar_wait(o_free, (seg & 1) ^ 1);
+              tc_fence_after();
+            }
+            issue_pv(n - 1, j == j0 + 1);
+          }
         }
-        umma_commit(s_full);
-        if (j > 0) issue_pv(j - 1);
+        if (j1 - j0 == 1) {
+          mbar_wait(o_free, (seg & 1) ^ 1);
+          tc_fence_after();
+        }
+        issue_pv(n - 1, j1 - j0 == 1);
+        u += j1 - j0;
       }
-      issue_pv(J - 1);
     }
   } else {
     const int qd = warp & 3;             // TMEM lane quadrant
@@ -196,110 +249,140 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int row = qd * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
     constexpr int OCH = DH / 64;         // 32-column O chunks per half
-    float m_used = -INFINITY, l = 0.f;
-    for (int j = 0; j < J; ++j) {
-      mbar_wait(s_full, j & 1);
+    int n = 0;  // key blocks processed by this CTA so far (all segments)
+    for (long long u = u_begin; u < u_end;) {
+      const int item = static_cast<int>(u / J), j0 = static_cast<int>(u - static_cast<long long>(item) * J);
+      const int j1 = static_cast<int>(min(static_cast<long long>(J), j0 + (u_end - u)));
+      const int qt = item % p.qtiles, h = (item / p.qtiles) % p.heads, b = item / (p.qtiles * p.heads);
+      float m_used = -INFINITY, l = 0.f;
+      for (int j = j0; j < j1; ++j, ++n) {
+        mbar_wait(s_full, n & 1);
+        tc_fence_after();
+        uint32_t r[32];
+        tmem_ld32(tmem_base + lane_off + Cfg::S_COL + 32 * half, r);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_free);
+        float s[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(r[i]);
+        if (j == J - 1) {
+          const int valid = p.lk - j * ATT_BKV - 32 * half;  // keys beyond lk were zero-filled by TMA
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i >= valid) s[i] = -INFINITY;
+        }
+        float mx = s[0];
+#pragma unroll
+        for (int i = 1; i < 32; ++i) mx = fmaxf(mx, s[i]);
+        float* xb = xchg + (n & 1) * (2 * ATT_BQ);
+        xb[half * ATT_BQ + row] = mx;
+        named_bar_sync(1, 32 * ATT_SM_WARPS);
+        mx = fmaxf(mx, xb[(half ^ 1) * ATT_BQ + row]) * p.scale_log2;  // scale > 0: max commutes with scaling
+        if (j == j0) {
+          m_used = mx;
+        } else {
+          const bool need = mx > m_used + 8.f;
+          if (__any_sync(0xffffffffu, need)) {  // identical in both warps of a quadrant (same rows, same mx)
+            // PV(n-1) finished => O is quiescent until P(n) is published.  s_full(n) implies PV(n-2) and
+            // older are complete, so o_done[(n-1)&1] is at most one completion behind: parity is exact.
+            mbar_wait(&o_done[(n - 1) & 1], ((n - 1) >> 1) & 1);
+            tc_fence_after();
+            const float alpha = need ? ex2_approx(m_used - mx) : 1.f;
+#pragma unroll 1
+            for (int c = half * OCH; c < (half + 1) * OCH; ++c) {
+              uint32_t o[32];
+              tmem_ld32(tmem_base + lane_off + c * 32, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st32(tmem_base + lane_off + c * 32, o);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            if (need) {
+              l *= alpha;
+              m_used = mx;
+            }
+          }
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          s[i] = ex2_approx(fmaf(s[i], p.scale_log2, -m_used));
+          sum += s[i];
+        }
+        l += sum;
+        uint8_t* prow = sP + (n & 1) * ATT_P_BYTES + row * 128;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 t;
+          t.x = pack_bf16x2(s[8 * c], s[8 * c + 1]);
+          t.y = pack_bf16x2(s[8 * c + 2], s[8 * c + 3]);
+          t.z = pack_bf16x2(s[8 * c + 4], s[8 * c + 5]);
+          t.w = pack_bf16x2(s[8 * c + 6], s[8 * c + 7]);
+          *reinterpret_cast<uint4*>(prow + (((4 * half + c) ^ (row & 7)) << 4)) = t;  // 128B swizzle (K-major A)
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[n & 1]);
+      }
+      // ---- segment epilogue.  row sum = the two halves' partial sums (both used the same m_used)
+      // (exchange through the buffer the NEXT key block will not use, so a fast thread cannot overwrite it)
+      float* xl = xchg + ((n & 1) ^ 1) * (2 * ATT_BQ);
+      named_bar_sync(1, 32 * ATT_SM_WARPS);
+      xl[half * ATT_BQ + row] = l;
+      named_bar_sync(1, 32 * ATT_SM_WARPS);
+      l += xl[(half ^ 1) * ATT_BQ + row];
+      mbar_wait(&o_done[(n - 1) & 1], ((n - 1) >> 1) & 1);  // PV(n-3) known complete (s_full(n-1)): exact as above
       tc_fence_after();
-      uint32_t r[32];
-      tmem_ld32(tmem_base + lane_off + Cfg::S_COL + 32 * half, r);
-      tmem_ld_wait();
+      const int q = qt * ATT_BQ + row;
+      if (j0 == 0 && j1 == J) {  // the segment covers the whole item: final result
+        const float inv = 1.f / l;
+        __nv_bfloat16* orow = p.O + b * p.o_batch + static_cast<long long>(q) * p.ldo + h * DH;
+#pragma unroll 1
+        for (int c = half * OCH; c < (half + 1) * OCH; ++c) {
+          uint32_t o[32];
+          tmem_ld32(tmem_base + lane_off + c * 32, o);
+          tmem_ld_wait();
+          if (q < p.lq) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 t;
+              t.x = pack_bf16x2(__uint_as_float(o[8 * g]) * inv, __uint_as_float(o[8 * g + 1]) * inv);
+              t.y = pack_bf16x2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv);
+              t.z = pack_bf16x2(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv);
+              t.w = pack_bf16x2(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv);
+              reinterpret_cast<uint4*>(orow + c * 32)[g] = t;
+            }
+          }
+        }
+        if (half == 0 && p.lse != nullptr && q < p.lq)
+          p.lse[(static_cast<long long>(b) * p.heads + h) * p.lq + q] = (m_used + log2f(l)) * 0.69314718055994530942f;
+      } else {  // partial: unnormalised fp32 O + (m, l) into this CTA's workspace slot
+        const int slot = (u == u_begin) ? 0 : 1;
+        float* wsb = p.ws + (static_cast<long long>(blockIdx.x) * 2 + slot) * attn_slot_floats<DH>();
+        float* wrow = wsb + static_cast<long long>(row) * DH;
+#pragma unroll 1
+        for (int c = half * OCH; c < (half + 1) * OCH; ++c) {
+          uint32_t o[32];
+          tmem_ld32(tmem_base + lane_off + c * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            reinterpret_cast<uint4*>(wrow + c * 32)[g] = make_uint4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+        }
+        if (half == 0) {
+          wsb[static_cast<long long>(ATT_BQ) * DH + row] = m_used;
+          wsb[static_cast<long long>(ATT_BQ) * DH + ATT_BQ + row] = l;
+        }
+      }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(s_free);
-      float s[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(r[i]);
-      if (j == J - 1) {
-        const int valid = p.lk - j * ATT_BKV - 32 * half;  // keys beyond lk were zero-filled by TMA
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (i >= valid) s[i] = -INFINITY;
-      }
-      float mx = s[0];
-#pragma unroll
-      for (int i = 1; i < 32; ++i) mx = fmaxf(mx, s[i]);
-      float* xb = xchg + (j & 1) * (2 * ATT_BQ);
-      xb[half * ATT_BQ + row] = mx;
-      named_bar_sync(1, 32 * ATT_SM_WARPS);
-      mx = fmaxf(mx, xb[(half ^ 1) * ATT_BQ + row]) * p.scale_log2;  // scale > 0: max commutes with scaling
-      if (j == 0) {
-        m_used = mx;
-      } else {
-        const bool need = mx > m_used + 8.f;
-        if (__any_sync(0xffffffffu, need)) {  // identical in both warps of a quadrant (same rows, same mx)
-          // PV(j-1) finished => O is quiescent until P(j) is published.  s_full(j) implies PV(j-2) and
-          // older are complete, so o_done[(j-1)&1] is at most one completion behind: parity is exact.
-          mbar_wait(&o_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
-          tc_fence_after();
-          const float alpha = need ? ex2_approx(m_used - mx) : 1.f;
-#pragma unroll 1
-          for (int c = half * OCH; c < (half + 1) * OCH; ++c) {
-            uint32_t o[32];
-            tmem_ld32(tmem_base + lane_off + c * 32, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(tmem_base + lane_off + c * 32, o);
-          }
-          tmem_st_wait();
-          tc_fence_before();
-          if (need) {
-            l *= alpha;
-            m_used = mx;
-          }
-        }
-      }
-      float sum = 0.f;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        s[i] = ex2_approx(fmaf(s[i], p.scale_log2, -m_used));
-        sum += s[i];
-      }
-      l += sum;
-      uint8_t* prow = sP + (j & 1) * ATT_P_BYTES + row * 128;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint4 t;
-        t.x = pack_bf16x2(s[8 * c], s[8 * c + 1]);
-        t.y = pack_bf16x2(s[8 * c + 2], s[8 * c + 3]);
-        t.z = pack_bf16x2(s[8 * c + 4], s[8 * c + 5]);
-        t.w = pack_bf16x2(s[8 * c + 6], s[8 * c + 7]);
-        *reinterpret_cast<uint4*>(prow + (((4 * half + c) ^ (row & 7)) << 4)) = t;  // 128B swizzle (K-major A)
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[j & 1]);
+      if (lane == 0) mbar_arrive(o_free);
+      u += j1 - j0;
     }
-    // row sum = the two halves' partial sums (both used the same m_used)
-    named_bar_sync(1, 32 * ATT_SM_WARPS);
-    xchg[half * ATT_BQ + row] = l;
-    named_bar_sync(1, 32 * ATT_SM_WARPS);
-    l += xchg[(half ^ 1) * ATT_BQ + row];
-    mbar_wait(&o_done[(J - 1) & 1], ((J - 1) >> 1) & 1);  // PV(J-3) known complete (s_full(J-1)): exact as above
-    tc_fence_after();
-    const float inv = 1.f / l;
-    const int q = q0 + row;
-    __nv_bfloat16* orow = p.O + b * p.o_batch + static_cast<long long>(q) * p.ldo + h * DH;
-#pragma unroll 1
-    for (int c = half * OCH; c < (half + 1) * OCH; ++c) {
-      uint32_t o[32];
-      tmem_ld32(tmem_base + lane_off + c * 32, o);
-      tmem_ld_wait();
-      if (q < p.lq) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 t;
-          t.x = pack_bf16x2(__uint_as_float(o[8 * g]) * inv, __uint_as_float(o[8 * g + 1]) * inv);
-          t.y = pack_bf16x2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv);
-          t.z = pack_bf16x2(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv);
-          t.w = pack_bf16x2(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv);
-          reinterpret_cast<uint4*>(orow + c * 32)[g] = t;
-        }
-      }
-    }
-    if (half == 0 && p.lse != nullptr && q < p.lq)
-      p.lse[(static_cast<long long>(b) * p.heads + h) * p.lq + q] = (m_used + log2f(l)) * 0.69314718055994530942f;
-    tc_fence_before();
   }
   __syncthreads();
   if (warp == 1) {
@@ -308,9 +391,76 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
 }
 
+// Combine the partial segments of every item that was split across CTAs (log-sum-exp weights).
+template <int DH>
+__global__ void __launch_bounds__(256) attn_merge_kernel(AttnTcParams p, int grid) {
+  const int item = blockIdx.x;
+  const int J = p.kv_blocks;
+  const long long i0 = static_cast<long long>(item) * J, i1 = i0 + J;
+  int c_lo = static_cast<int>(i0 * grid / p.units);
+  long long u0, u1;
+  while (c_lo > 0) {
+    attn_cta_range(p, c_lo, grid, u0, u1);
+    if (u0 <= i0) break;
+    --c_lo;
+  }
+  for (;;) {
+    attn_cta_range(p, c_lo, grid, u0, u1);
+    if (u1 > i0) break;
+    ++c_lo;
+  }
+  attn_cta_range(p, c_lo, grid, u0, u1);
+  if (u0 <= i0 && u1 >= i1) return;  // one CTA covered the whole item and wrote the final result itself
+  int c_hi = c_lo;
+  for (;;) {
+    attn_cta_range(p, c_hi, grid, u0, u1);
+    if (u1 >= i1) break;
+    ++c_hi;
+  }
+  const int qt = item % p.qtiles, h = (item / p.qtiles) % p.heads, b = item / (p.qtiles * p.heads);
+  const long long slot_f = attn_slot_floats<DH>();
+  auto slot_of = [&](int c) {
+    attn_cta_range(p, c, grid, u0, u1);
+    const long long s0 = u0 > i0 ? u0 : i0;
+    return p.ws + (static_cast<long long>(c) * 2 + (s0 == u0 ? 0 : 1)) * slot_f;
+  };
+  for (int idx = threadIdx.x; idx < ATT_BQ * (DH / 8); idx += blockDim.x) {
+    const int row = idx / (DH / 8), cg = idx % (DH / 8);
+    const int q = qt * ATT_BQ + row;
+    if (q >= p.lq) continue;
+    float m = -INFINITY;
+    for (int c = c_lo; c <= c_hi; ++c) m = fmaxf(m, slot_of(c)[static_cast<long long>(ATT_BQ) * DH + row]);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float lsum = 0.f;
+    for (int c = c_lo; c <= c_hi; ++c) {
+      const float* sl = slot_of(c);
+      const float w = ex2_approx(sl[static_cast<long long>(ATT_BQ) * DH + row] - m);
+      lsum += w * sl[static_cast<long long>(ATT_BQ) * DH + ATT_BQ + row];
+      const float4 a = *reinterpret_cast<const float4*>(sl + static_cast<long long>(row) * DH + cg * 8);
+      const float4 d = *reinterpret_cast<const float4*>(sl + static_cast<long long>(row) * DH + cg * 8 + 4);
+      acc[0] += w * a.x; acc[1] += w * a.y; acc[2] += w * a.z; acc[3] += w * a.w;
+      acc[4] += w * d.x; acc[5] += w * d.y; acc[6] += w * d.z; acc[7] += w * d.w;
+    }
+    const float inv = 1.f / lsum;
+    uint4 t;
+    t.x = pack_bf16x2(acc[0] * inv, acc[1] * inv);
+    t.y = pack_bf16x2(acc[2] * inv, acc[3] * inv);
+    t.z = pack_bf16x2(acc[4] * inv, acc[5] * inv);
+    t.w = pack_bf16x2(acc[6] * inv, acc[7] * inv);
+    *reinterpret_cast<uint4*>(p.O + b * p.o_batch + static_cast<long long>(q) * p.ldo + h * DH + cg * 8) = t;
+    if (cg == 0 && p.lse != nullptr)
+      p.lse[(static_cast<long long>(b) * p.heads + h) * p.lq + q] = (m + log2f(lsum)) * 0.69314718055994530942f;
+  }
+}
+
+static int attn_grid(long long units) {
+  const int sms = sm_count();
+  return static_cast<int>(units < sms ? units : sms);
+}
+
 template <int DH>
 static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnTcParams& p,
-                       int batch, cudaStream_t st) {
+                       cudaStream_t st) {
   using Cfg = AttnCfg<DH>;
   static_assert(Cfg::SMEM_BYTES <= 232448, "attention smem budget exceeded");
   static bool configured = false;
@@ -319,16 +469,27 @@ static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUt
                                        Cfg::SMEM_BYTES));
     configured = true;
   }
-  dim3 grid(ceil_div(p.lq, ATT_BQ), p.heads, batch);
+  const int grid = attn_grid(p.units);
   attn_tc_kernel<DH><<<grid, ATT_THREADS, Cfg::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
   MAVLM_LAUNCH_OK();
+  if (p.units % grid != 0 || (p.units / grid) % p.kv_blocks != 0) {  // some item is split across CTAs
+    attn_merge_kernel<DH><<<p.items, 256, 0, st>>>(p, grid);
+    MAVLM_LAUNCH_OK();
+  }
   return MAVLM_OK;
+}
+
+size_t xattn_bf16_workspace_bytes(int batch, int heads, int lq, int lk, int dh) {
+  const long long items = static_cast<long long>(batch) * heads * ceil_div(lq, ATT_BQ);
+  const long long units = items * ceil_div(lk, ATT_BKV);
+  const long long slot = static_cast<long long>(ATT_BQ) * dh + 2 * ATT_BQ;
+  return static_cast<size_t>(attn_grid(units)) * 2 * slot * sizeof(float);
 }
 
 int xattn_bf16_tc(const __nv_bfloat16* Q, long long ldq, long long qb, const __nv_bfloat16* K, long long ldk,
                   long long kb, const __nv_bfloat16* V, long long ldv, long long vb, __nv_bfloat16* O, long long ldo,
-                  long long ob, float* lse, int batch, int heads, int lq, int lk, int dh, float scale,
-                  cudaStream_t st) {
+                  long long ob, float* lse, int batch, int heads, int lq, int lk, int dh, float scale, void* ws,
+                  size_t ws_bytes, cudaStream_t st) {
   if (batch == 0 || lq == 0) return MAVLM_OK;
   MAVLM_REQUIRE(dh == 128 || dh == 448, MAVLM_E_INVALID,
                 "bf16 xattn: head_dim %d not supported by the tcgen05 kernel (128 or 448; 112 is padded to 128 by "
@@ -351,11 +512,18 @@ int xattn_bf16_tc(const __nv_bfloat16* Q, long long ldq, long long qb, const __n
   if ((rc = mk(&tmQ, Q, ldq, qb, lq, ATT_BQ))) return rc;
   if ((rc = mk(&tmK, K, ldk, kb, lk, ATT_BKV))) return rc;
   if ((rc = mk(&tmV, V, ldv, vb, lk, ATT_BKV))) return rc;
+  const size_t need = xattn_bf16_workspace_bytes(batch, heads, lq, lk, dh);
+  MAVLM_REQUIRE(ws != nullptr && ws_bytes >= need && (reinterpret_cast<uintptr_t>(ws) & 15) == 0, MAVLM_E_WORKSPACE,
+                "bf16 xattn: 16-byte aligned workspace of %zu bytes needed, %zu given", need, ws_bytes);
   AttnTcParams p{};
   p.lq = lq; p.lk = lk; p.kv_blocks = ceil_div(lk, ATT_BKV);
   p.scale_log2 = scale * 1.44269504088896340736f;
   p.O = O; p.ldo = ldo; p.o_batch = ob; p.lse = lse; p.heads = heads;
-  return dh == 448 ? launch_attn<448>(tmQ, tmK, tmV, p, batch, st) : launch_attn<128>(tmQ, tmK, tmV, p, batch, st);
+  p.qtiles = ceil_div(lq, ATT_BQ);
+  p.items = batch * heads * p.qtiles;
+  p.units = static_cast<long long>(p.items) * p.kv_blocks;
+  p.ws = static_cast<float*>(ws);
+  return dh == 448 ? launch_attn<448>(tmQ, tmK, tmV, p, st) : launch_attn<128>(tmQ, tmK, tmV, p, st);
 }
 
 }  // namespace mavlm

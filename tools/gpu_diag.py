@@ -215,6 +215,9 @@ def fam_attn():
         _attn_case(1, 8, 1568, 6272, dh)
         _attn_case(1, 8, 1568, 6272, dh, qscale=8.0)   # sharp softmax: exercises the lazy O rescale
         _attn_case(1, 2, 200, 3 * 1568, dh, qscale=4.0)
+        _attn_case(1, 8, 1568, 15680, dh, qscale=2.0)      # evolution-sized key set, split items
+        _attn_case(3, 8, 1568, 3136, dh, strided=True)     # 312 items over 148 CTAs: ~2 items + partials each
+        _attn_case(1, 8, 130, 64, dh)                       # 16 units < 148 CTAs, one key block each
 
 
 def _build_models(d, dv, dtype, seed=0, chunk=32, frames=64, depth=2):
