@@ -21,12 +21,16 @@
 //              row max grows by more than 2^8), P -> bf16 -> 128B-swizzled smem (double buffered).
 // TMEM budget at DH=448: 448 (O) + 64 (S) = 512 columns, which is why the key block is 64.
 //
-// Scheduling: persistent, balanced over (item, key block) units ("stream-K"): item = (batch, head, q tile),
-// U = items * key blocks; CTA c owns the contiguous unit range [c*U/G, (c+1)*U/G).  One OV-7B video is only
-// 13 q tiles x 8 heads = 104 items for 148 SMs, so an item-per-CTA grid leaves 30 % of the SMs idle.  A CTA
-// walks its range as segments (item, j0..j1): a segment that covers its whole item writes O / LSE directly,
-// a partial segment writes unnormalised fp32 (O, m, l) to a workspace slot (at most two per CTA) and
-// attn_merge_kernel combines the partials of split items with the usual log-sum-exp weights.
+// Scheduling: persistent and balanced ("stream-K" over key blocks), in GROUPS of CTAs that share K/V.
+// One OV-7B video is only 13 q tiles x 8 heads = 104 (b,h,q-tile) items for 148 SMs: an item-per-CTA grid
+// leaves 30 % of the SMs idle.  A group = `gs` CTAs, one per q tile of a q-tile group (gs = 13 here), that walk
+// the SAME (batch, head, key block) sequence in lockstep-ish order, so a K/V block is pulled from HBM once and
+// served to the whole group out of L2 (a per-CTA stream-K range destroys exactly this sharing: measured 40 %
+// slower per key block).  Group g owns the contiguous range [g*U/G, (g+1)*U/G) of U = B*H*ngq*J
+// (b, h, q-group, key block) units.  A CTA walks its group's range as segments (item, j0..j1): a segment that
+// covers its whole item writes O / LSE directly, a partial segment writes unnormalised fp32 (O, m, l) to a
+// workspace slot (at most two per CTA) and attn_merge_kernel combines the partials of split items with the
+// usual log-sum-exp weights.
 #include "common.cuh"
 
 namespace mavlm {
@@ -46,16 +50,18 @@ struct AttnTcParams {
   long long ldo, o_batch;
   float* lse;
   int heads, qtiles, items;
-  long long units;   // items * kv_blocks
-  float* ws;         // partial slots: [grid][2] x { O fp32 [128][DH], m [128], l [128] }
+  int gs, ngq, groups;  // CTAs per group (q tiles of one q-group), q-groups per (b,h), number of groups
+  long long units;      // batch * heads * ngq * kv_blocks  (group-level units)
+  float* ws;            // partial slots: [grid][2] x { O fp32 [128][DH], m [128], l [128] }
 };
 
 template <int DH>
 __host__ __device__ constexpr long long attn_slot_floats() { return static_cast<long long>(ATT_BQ) * DH + 2 * ATT_BQ; }
 
-__device__ __forceinline__ void attn_cta_range(const AttnTcParams& p, int c, int grid, long long& u0, long long& u1) {
-  u0 = static_cast<long long>(c) * p.units / grid;
-  u1 = static_cast<long long>(c + 1) * p.units / grid;
+// unit range of group g
+__device__ __forceinline__ void attn_group_range(const AttnTcParams& p, int g, long long& u0, long long& u1) {
+  u0 = static_cast<long long>(g) * p.units / p.groups;
+  u1 = static_cast<long long>(g + 1) * p.units / p.groups;
 }
 
 template <int DH>
@@ -103,8 +109,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int J = p.kv_blocks;
+  const int grp = blockIdx.x / p.gs, grp_r = blockIdx.x % p.gs;  // group, and this CTA's q tile inside a q-group
   long long u_begin, u_end;
-  attn_cta_range(p, blockIdx.x, gridDim.x, u_begin, u_end);
+  attn_group_range(p, grp, u_begin, u_end);
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) {  // 128B-swizzle atoms need 1024-byte aligned tiles
@@ -155,9 +162,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       for (long long u = u_begin; u < u_end; ++seg) {
         const int item = static_cast<int>(u / J), j0 = static_cast<int>(u - static_cast<long long>(item) * J);
         const int j1 = static_cast<int>(min(static_cast<long long>(J), j0 + (u_end - u)));
-        const int qt = item % p.qtiles;
-        h = (item / p.qtiles) % p.heads;
-        b = item / (p.qtiles * p.heads);
+        const int qt = (item % p.ngq) * p.gs + grp_r;  // may be >= qtiles: TMA zero-fills, nothing is stored
+        h = (item / p.ngq) % p.heads;
+        b = item / (p.ngq * p.heads);
         load_block(&tmK, j0);
         mbar_wait(q_free, (seg & 1) ^ 1);  // previous segment's QK MMAs no longer read sQ
         mbar_expect_tx(q_full, Cfg::Q_BYTES);
@@ -253,7 +260,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     for (long long u = u_begin; u < u_end;) {
       const int item = static_cast<int>(u / J), j0 = static_cast<int>(u - static_cast<long long>(item) * J);
       const int j1 = static_cast<int>(min(static_cast<long long>(J), j0 + (u_end - u)));
-      const int qt = item % p.qtiles, h = (item / p.qtiles) % p.heads, b = item / (p.qtiles * p.heads);
+      const int qt = (item % p.ngq) * p.gs + grp_r, h = (item / p.ngq) % p.heads, b = item / (p.ngq * p.heads);
       float m_used = -INFINITY, l = 0.f;
       for (int j = j0; j < j1; ++j, ++n) {
         mbar_wait(s_full, n & 1);
@@ -391,49 +398,51 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
 }
 
-// Combine the partial segments of every item that was split across CTAs (log-sum-exp weights).
+// Combine the partial segments of every item that was split across groups (log-sum-exp weights).
+// One block per (b, h, q tile).
 template <int DH>
-__global__ void __launch_bounds__(256) attn_merge_kernel(AttnTcParams p, int grid) {
-  const int item = blockIdx.x;
+__global__ void __launch_bounds__(256) attn_merge_kernel(AttnTcParams p) {
+  const int qt = blockIdx.x % p.qtiles, h = (blockIdx.x / p.qtiles) % p.heads, b = blockIdx.x / (p.qtiles * p.heads);
   const int J = p.kv_blocks;
-  const long long i0 = static_cast<long long>(item) * J, i1 = i0 + J;
-  int c_lo = static_cast<int>(i0 * grid / p.units);
+  const int r = qt % p.gs;
+  const long long gi = (static_cast<long long>(b) * p.heads + h) * p.ngq + qt / p.gs;  // group-level item
+  const long long i0 = gi * J, i1 = i0 + J;
+  int g_lo = static_cast<int>(i0 * p.groups / p.units);
   long long u0, u1;
-  while (c_lo > 0) {
-    attn_cta_range(p, c_lo, grid, u0, u1);
+  while (g_lo > 0) {
+    attn_group_range(p, g_lo, u0, u1);
     if (u0 <= i0) break;
-    --c_lo;
+    --g_lo;
   }
   for (;;) {
-    attn_cta_range(p, c_lo, grid, u0, u1);
+    attn_group_range(p, g_lo, u0, u1);
     if (u1 > i0) break;
-    ++c_lo;
+    ++g_lo;
   }
-  attn_cta_range(p, c_lo, grid, u0, u1);
-  if (u0 <= i0 && u1 >= i1) return;  // one CTA covered the whole item and wrote the final result itself
-  int c_hi = c_lo;
+  attn_group_range(p, g_lo, u0, u1);
+  if (u0 <= i0 && u1 >= i1) return;  // one group covered the whole item: its CTA wrote the final result itself
+  int g_hi = g_lo;
   for (;;) {
-    attn_cta_range(p, c_hi, grid, u0, u1);
+    attn_group_range(p, g_hi, u0, u1);
     if (u1 >= i1) break;
-    ++c_hi;
+    ++g_hi;
   }
-  const int qt = item % p.qtiles, h = (item / p.qtiles) % p.heads, b = item / (p.qtiles * p.heads);
   const long long slot_f = attn_slot_floats<DH>();
-  auto slot_of = [&](int c) {
-    attn_cta_range(p, c, grid, u0, u1);
+  auto slot_of = [&](int g) {
+    attn_group_range(p, g, u0, u1);
     const long long s0 = u0 > i0 ? u0 : i0;
-    return p.ws + (static_cast<long long>(c) * 2 + (s0 == u0 ? 0 : 1)) * slot_f;
+    return p.ws + ((static_cast<long long>(g) * p.gs + r) * 2 + (s0 == u0 ? 0 : 1)) * slot_f;
   };
   for (int idx = threadIdx.x; idx < ATT_BQ * (DH / 8); idx += blockDim.x) {
     const int row = idx / (DH / 8), cg = idx % (DH / 8);
     const int q = qt * ATT_BQ + row;
     if (q >= p.lq) continue;
     float m = -INFINITY;
-    for (int c = c_lo; c <= c_hi; ++c) m = fmaxf(m, slot_of(c)[static_cast<long long>(ATT_BQ) * DH + row]);
+    for (int g = g_lo; g <= g_hi; ++g) m = fmaxf(m, slot_of(g)[static_cast<long long>(ATT_BQ) * DH + row]);
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float lsum = 0.f;
-    for (int c = c_lo; c <= c_hi; ++c) {
-      const float* sl = slot_of(c);
+    for (int g = g_lo; g <= g_hi; ++g) {
+      const float* sl = slot_of(g);
       const float w = ex2_approx(sl[static_cast<long long>(ATT_BQ) * DH + row] - m);
       lsum += w * sl[static_cast<long long>(ATT_BQ) * DH + ATT_BQ + row];
       const float4 a = *reinterpret_cast<const float4*>(sl + static_cast<long long>(row) * DH + cg * 8);
@@ -453,9 +462,22 @@ __global__ void __launch_bounds__(256) attn_merge_kernel(AttnTcParams p, int gri
   }
 }
 
-static int attn_grid(long long units) {
-  const int sms = sm_count();
-  return static_cast<int>(units < sms ? units : sms);
+// Group geometry: q tiles are split into ngq q-groups of gs <= 16 tiles; as many groups as fit on the SMs.
+struct AttnGeom {
+  int qtiles, ngq, gs, groups;
+  long long units;
+};
+static AttnGeom attn_geometry(int batch, int heads, int lq, int lk) {
+  AttnGeom g;
+  g.qtiles = ceil_div(lq, ATT_BQ);
+  g.ngq = ceil_div(g.qtiles, 16);
+  g.gs = ceil_div(g.qtiles, g.ngq);
+  g.units = static_cast<long long>(batch) * heads * g.ngq * ceil_div(lk, ATT_BKV);
+  long long groups = sm_count() / g.gs;
+  if (groups < 1) groups = 1;
+  if (groups > g.units) groups = g.units;
+  g.groups = static_cast<int>(groups);
+  return g;
 }
 
 template <int DH>
@@ -469,21 +491,19 @@ static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUt
                                        Cfg::SMEM_BYTES));
     configured = true;
   }
-  const int grid = attn_grid(p.units);
-  attn_tc_kernel<DH><<<grid, ATT_THREADS, Cfg::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
+  attn_tc_kernel<DH><<<p.groups * p.gs, ATT_THREADS, Cfg::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
   MAVLM_LAUNCH_OK();
-  if (p.units % grid != 0 || (p.units / grid) % p.kv_blocks != 0) {  // some item is split across CTAs
-    attn_merge_kernel<DH><<<p.items, 256, 0, st>>>(p, grid);
+  if (p.units % p.groups != 0 || (p.units / p.groups) % p.kv_blocks != 0) {  // some item is split across groups
+    attn_merge_kernel<DH><<<p.items, 256, 0, st>>>(p);
     MAVLM_LAUNCH_OK();
   }
   return MAVLM_OK;
 }
 
 size_t xattn_bf16_workspace_bytes(int batch, int heads, int lq, int lk, int dh) {
-  const long long items = static_cast<long long>(batch) * heads * ceil_div(lq, ATT_BQ);
-  const long long units = items * ceil_div(lk, ATT_BKV);
+  const AttnGeom g = attn_geometry(batch, heads, lq, lk);
   const long long slot = static_cast<long long>(ATT_BQ) * dh + 2 * ATT_BQ;
-  return static_cast<size_t>(attn_grid(units)) * 2 * slot * sizeof(float);
+  return static_cast<size_t>(g.groups) * g.gs * 2 * slot * sizeof(float);
 }
 
 int xattn_bf16_tc(const __nv_bfloat16* Q, long long ldq, long long qb, const __nv_bfloat16* K, long long ldk,
@@ -519,9 +539,9 @@ int xattn_bf16_tc(const __nv_bfloat16* Q, long long ldq, long long qb, const __n
   p.lq = lq; p.lk = lk; p.kv_blocks = ceil_div(lk, ATT_BKV);
   p.scale_log2 = scale * 1.44269504088896340736f;
   p.O = O; p.ldo = ldo; p.o_batch = ob; p.lse = lse; p.heads = heads;
-  p.qtiles = ceil_div(lq, ATT_BQ);
+  const AttnGeom geo = attn_geometry(batch, heads, lq, lk);
+  p.qtiles = geo.qtiles; p.ngq = geo.ngq; p.gs = geo.gs; p.groups = geo.groups; p.units = geo.units;
   p.items = batch * heads * p.qtiles;
-  p.units = static_cast<long long>(p.items) * p.kv_blocks;
   p.ws = static_cast<float*>(ws);
   return dh == 448 ? launch_attn<448>(tmQ, tmK, tmV, p, st) : launch_attn<128>(tmQ, tmK, tmV, p, st);
 }
