@@ -44,6 +44,7 @@ PROTOTYPES = {
     "mavlm_assemble_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mavlm_debug_force_gemm_bn": (c_int, [c_int]),
+    "mavlm_debug_force_attn_groups": (c_int, [c_int]),
 }
 
 _lib = None

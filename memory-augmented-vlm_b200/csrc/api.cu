@@ -17,6 +17,7 @@ int xattn_bf16_tc(const __nv_bfloat16* Q, long long ldq, long long qb, const __n
                   long long ob, float* lse, int batch, int heads, int lq, int lk, int dh, float scale, void* ws,
                   size_t ws_bytes, cudaStream_t st);
 size_t xattn_bf16_workspace_bytes(int batch, int heads, int lq, int lk, int dh);
+void attn_force_groups(int n);
 }  // namespace mavlm
 
 using namespace mavlm;
@@ -74,6 +75,12 @@ int mavlm_xattn_fwd(const void* Q, int64_t ldq, int64_t q_batch_stride, const vo
 MAVLM_API int mavlm_debug_force_gemm_bn(int bn) {
   MAVLM_REQUIRE(bn == 0 || bn == 64 || bn == 128 || bn == 192 || bn == 256, MAVLM_E_INVALID, "bad BN %d", bn);
   gemm_tc_force_bn(bn);
+  return MAVLM_OK;
+}
+
+/* development knob: force the number of attention CTA groups (0 = as many as fit on the SMs) */
+MAVLM_API int mavlm_debug_force_attn_groups(int n) {
+  attn_force_groups(n);
   return MAVLM_OK;
 }
 

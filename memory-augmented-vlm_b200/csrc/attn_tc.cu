@@ -399,54 +399,65 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 }
 
 // Combine the partial segments of every item that was split across groups (log-sum-exp weights).
-// One block per (b, h, q tile).
+// grid = (items, ATT_BQ / MERGE_ROWS): one block per 16 query rows of a (b, h, q tile); the slot pointers of
+// the item's parts are resolved once per block.
+constexpr int MERGE_ROWS = 16;
+constexpr int MERGE_MAX_PARTS = 16;
 template <int DH>
 __global__ void __launch_bounds__(256) attn_merge_kernel(AttnTcParams p) {
-  const int qt = blockIdx.x % p.qtiles, h = (blockIdx.x / p.qtiles) % p.heads, b = blockIdx.x / (p.qtiles * p.heads);
-  const int J = p.kv_blocks;
-  const int r = qt % p.gs;
-  const long long gi = (static_cast<long long>(b) * p.heads + h) * p.ngq + qt / p.gs;  // group-level item
-  const long long i0 = gi * J, i1 = i0 + J;
-  int g_lo = static_cast<int>(i0 * p.groups / p.units);
-  long long u0, u1;
-  while (g_lo > 0) {
+  __shared__ const float* parts[MERGE_MAX_PARTS];
+  __shared__ int n_parts;
+  const int item = blockIdx.x;
+  const int qt = item % p.qtiles, h = (item / p.qtiles) % p.heads, b = item / (p.qtiles * p.heads);
+  if (threadIdx.x == 0) {
+    const int J = p.kv_blocks;
+    const int r = qt % p.gs;
+    const long long gi = (static_cast<long long>(b) * p.heads + h) * p.ngq + qt / p.gs;  // group-level item
+    const long long i0 = gi * J, i1 = i0 + J;
+    int g_lo = static_cast<int>(i0 * p.groups / p.units);
+    long long u0, u1;
+    while (g_lo > 0) {
+      attn_group_range(p, g_lo, u0, u1);
+      if (u0 <= i0) break;
+      --g_lo;
+    }
+    for (;;) {
+      attn_group_range(p, g_lo, u0, u1);
+      if (u1 > i0) break;
+      ++g_lo;
+    }
+    int n = 0;
     attn_group_range(p, g_lo, u0, u1);
-    if (u0 <= i0) break;
-    --g_lo;
+    if (!(u0 <= i0 && u1 >= i1)) {  // else: one group covered the whole item and wrote the final result itself
+      const long long slot_f = attn_slot_floats<DH>();
+      for (int g = g_lo; n < MERGE_MAX_PARTS; ++g) {
+        attn_group_range(p, g, u0, u1);
+        const long long s0 = u0 > i0 ? u0 : i0;
+        parts[n++] = p.ws + ((static_cast<long long>(g) * p.gs + r) * 2 + (s0 == u0 ? 0 : 1)) * slot_f;
+        if (u1 >= i1) break;
+      }
+    }
+    n_parts = n;
   }
-  for (;;) {
-    attn_group_range(p, g_lo, u0, u1);
-    if (u1 > i0) break;
-    ++g_lo;
-  }
-  attn_group_range(p, g_lo, u0, u1);
-  if (u0 <= i0 && u1 >= i1) return;  // one group covered the whole item: its CTA wrote the final result itself
-  int g_hi = g_lo;
-  for (;;) {
-    attn_group_range(p, g_hi, u0, u1);
-    if (u1 >= i1) break;
-    ++g_hi;
-  }
-  const long long slot_f = attn_slot_floats<DH>();
-  auto slot_of = [&](int g) {
-    attn_group_range(p, g, u0, u1);
-    const long long s0 = u0 > i0 ? u0 : i0;
-    return p.ws + ((static_cast<long long>(g) * p.gs + r) * 2 + (s0 == u0 ? 0 : 1)) * slot_f;
-  };
-  for (int idx = threadIdx.x; idx < ATT_BQ * (DH / 8); idx += blockDim.x) {
-    const int row = idx / (DH / 8), cg = idx % (DH / 8);
+  __syncthreads();
+  const int np = n_parts;
+  if (np == 0) return;
+  constexpr int CG = DH / 8;
+  const int row0 = blockIdx.y * MERGE_ROWS;
+  for (int idx = threadIdx.x; idx < MERGE_ROWS * CG; idx += blockDim.x) {
+    const int row = row0 + idx / CG, cg = idx % CG;
     const int q = qt * ATT_BQ + row;
     if (q >= p.lq) continue;
     float m = -INFINITY;
-    for (int g = g_lo; g <= g_hi; ++g) m = fmaxf(m, slot_of(g)[static_cast<long long>(ATT_BQ) * DH + row]);
+    for (int i = 0; i < np; ++i) m = fmaxf(m, parts[i][static_cast<long long>(ATT_BQ) * DH + row]);
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float lsum = 0.f;
-    for (int g = g_lo; g <= g_hi; ++g) {
-      const float* sl = slot_of(g);
+    for (int i = 0; i < np; ++i) {
+      const float* sl = parts[i];
       const float w = ex2_approx(sl[static_cast<long long>(ATT_BQ) * DH + row] - m);
       lsum += w * sl[static_cast<long long>(ATT_BQ) * DH + ATT_BQ + row];
-      const float4 a = *reinterpret_cast<const float4*>(sl + static_cast<long long>(row) * DH + cg * 8);
-      const float4 d = *reinterpret_cast<const float4*>(sl + static_cast<long long>(row) * DH + cg * 8 + 4);
+      const float4 a = __ldg(reinterpret_cast<const float4*>(sl + static_cast<long long>(row) * DH + cg * 8));
+      const float4 d = __ldg(reinterpret_cast<const float4*>(sl + static_cast<long long>(row) * DH + cg * 8 + 4));
       acc[0] += w * a.x; acc[1] += w * a.y; acc[2] += w * a.z; acc[3] += w * a.w;
       acc[4] += w * d.x; acc[5] += w * d.y; acc[6] += w * d.z; acc[7] += w * d.w;
     }
@@ -467,6 +478,8 @@ struct AttnGeom {
   int qtiles, ngq, gs, groups;
   long long units;
 };
+static int g_force_groups = 0;
+void attn_force_groups(int n) { g_force_groups = n; }
 static AttnGeom attn_geometry(int batch, int heads, int lq, int lk) {
   AttnGeom g;
   g.qtiles = ceil_div(lq, ATT_BQ);
@@ -474,6 +487,10 @@ static AttnGeom attn_geometry(int batch, int heads, int lq, int lk) {
   g.gs = ceil_div(g.qtiles, g.ngq);
   g.units = static_cast<long long>(batch) * heads * g.ngq * ceil_div(lk, ATT_BKV);
   long long groups = sm_count() / g.gs;
+  if (g_force_groups > 0) groups = g_force_groups;
+  // an item (one (b,h,q-group), J units) must not be cut into more than MERGE_MAX_PARTS parts
+  const long long bh = static_cast<long long>(batch) * heads * g.ngq;
+  if (groups > bh * (MERGE_MAX_PARTS - 2)) groups = bh * (MERGE_MAX_PARTS - 2);
   if (groups < 1) groups = 1;
   if (groups > g.units) groups = g.units;
   g.groups = static_cast<int>(groups);
@@ -494,7 +511,7 @@ static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUt
   attn_tc_kernel<DH><<<p.groups * p.gs, ATT_THREADS, Cfg::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
   MAVLM_LAUNCH_OK();
   if (p.units % p.groups != 0 || (p.units / p.groups) % p.kv_blocks != 0) {  // some item is split across groups
-    attn_merge_kernel<DH><<<p.items, 256, 0, st>>>(p);
+    attn_merge_kernel<DH><<<dim3(p.items, ATT_BQ / MERGE_ROWS), 256, 0, st>>>(p);
     MAVLM_LAUNCH_OK();
   }
   return MAVLM_OK;

@@ -337,6 +337,18 @@ def fam_perf():
         ms = timeit(lambda: ops.xattn(q, k, v, h))
         fl = 4.0 * bsz * h * lq * lk * dh
         print(f"xattn B{bsz} {lq}x{lk} dh{dh}: {ms * 1e3:.0f}us {fl / ms / 1e9:.0f}TF", flush=True)
+    h = 8
+    for (bsz, lq, lk, dh) in ((1, 1568, 6272, 448), (8, 1568, 6272, 448)):
+        q = torch.randn(bsz, lq, h * dh, device=dev).bfloat16()
+        k = torch.randn(bsz, lk, h * dh, device=dev).bfloat16()
+        v = torch.randn(bsz, lk, h * dh, device=dev).bfloat16()
+        line = f"xattn B{bsz} groups sweep:"
+        for g in (4, 6, 8, 9, 10, 11):
+            lib.mavlm_debug_force_attn_groups(g)
+            ms = timeit(lambda: ops.xattn(q, k, v, h))
+            line += f"  g{g}: {ms * 1e3:.0f}us"
+        lib.mavlm_debug_force_attn_groups(0)
+        print(line, flush=True)
     for frames in (64, 256):
         x = torch.randn(frames, 729, 3584, device=dev).bfloat16()
         table = torch.randn(600, 3584, device=dev)
