@@ -362,7 +362,37 @@ def fam_perf():
     print(f"layernorm 1568x3584 f32->bf16: {ms * 1e3:.1f}us {1568 * 3584 * 6 / ms / 1e6:.0f}GB/s")
 
 
-FAMS = {"elem": fam_elem, "simt": fam_simt, "gemm": fam_gemm, "attn": fam_attn, "pipe": fam_pipe, "perf": fam_perf}
+def fam_ab():
+    """A/B of scheduling knobs on the full bench step, alternating within one process (box-to-box and
+    thermal variation between separate runs is +-5 %)."""
+    import torch
+    from mavlm_b200 import _lib, synthetic
+    lib = _lib.load()
+    pipe, _ = synthetic.build_pipeline(3584, 1152, dtype=torch.bfloat16, chunk_size=32, device="cuda:0")
+    x = synthetic.synthetic_tower_tokens(1, 64).to("cuda:0")
+    idx = torch.arange(64, device="cuda:0")[None]
+
+    def run(n=10):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            pipe(x, idx, validate=False, return_states=False)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    run(5)
+    for rnd in range(4):
+        line = f"round {rnd}:"
+        for g in (8, 0, 10, 11):
+            lib.mavlm_debug_force_attn_groups(g)
+            line += f"  attn_groups={g}: {run():.3f} ms"
+        print(line, flush=True)
+    lib.mavlm_debug_force_attn_groups(0)
+
+
+FAMS = {"ab": fam_ab, "elem": fam_elem, "simt": fam_simt, "gemm": fam_gemm, "attn": fam_attn, "pipe": fam_pipe, "perf": fam_perf}
 
 if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[1] == "--child":
