@@ -103,6 +103,37 @@ MAVLM_API int mavlm_assemble_fwd(void* seq, const void* mem, int64_t n_mem_rows,
                        const int64_t* prompt_mem_ids, int n_prompt_mem, const int64_t* prompt_frm_ids,
                        int n_prompt_frm, int dim, int drop_frames, int dtype, void* stream);
 
+/* ======================= backward pass (training: BPTT through the memory, fuser) =======================
+ * The reference trains this path with PyTorch autograd (train.py:1694-1728 unfreezes recurrent_memory_transformer,
+ * memory_fuser, token_type_embedding; frame features are detached, llava_arch.py:302).  These entry points are
+ * what the autograd.Functions of the host modules call. */
+
+/* General GEMM: C[M,N] (+)= alpha * op(A) op(B).  trans_a = 0: A is [M,K]; 1: A is [K,M].  trans_b = 1: B is [N,K]
+ * (nn.Linear weight layout); 0: B is [K,N].  Batched over outer*inner problems; strides (elements) =
+ * {a_outer, a_inner, b_outer, b_inner, c_outer, c_inner} or NULL.  dgrad: dX = dY W (trans_b = 0);
+ * wgrad: dW (+)= dY^T X (trans_a = 1, trans_b = 0, accumulate over chunks). */
+MAVLM_API int mavlm_gemm_ex(const void* A, int64_t lda, int trans_a, const void* B, int64_t ldb, int trans_b, void* C,
+                            int64_t ldc, int M, int N, int K, float alpha, int accumulate, int outer, int inner,
+                            const int64_t* host_strides, int dtype, void* stream);
+/* out[n] (+)= sum_m x[m,n]  (fp32 out): bias / type-embedding / newline gradients. */
+MAVLM_API int mavlm_colsum(const void* x, int64_t ld, float* out, int M, int N, int accumulate, int dtype, void* stream);
+/* LayerNorm backward from the saved fp32 pre-LN sum: dpre (fp32), dgamma/dbeta (fp32, ACCUMULATED into). */
+MAVLM_API int mavlm_layernorm_bwd(const float* pre, const void* gamma, const void* dy, float* dpre, float* dgamma,
+                                  float* dbeta, int rows, int dim, float eps, int dtype, void* stream);
+/* Unfused activation (training keeps the GELU pre-activation) and its backward (ref = output for ReLU,
+ * pre-activation for GELU). */
+MAVLM_API int mavlm_act_fwd(const void* x, void* y, int64_t n, int act, int dtype, void* stream);
+MAVLM_API int mavlm_act_bwd(const void* dy, const void* ref, void* dx, int64_t n, int act, int dtype, void* stream);
+/* Attention backward (MemoryController.py:51-54): from q, k, v, o, dO and the forward's LSE to dQ, dK, dV in the
+ * layouts of q, k, v. */
+MAVLM_API size_t mavlm_xattn_bwd_workspace_bytes(int batch, int heads, int lq, int lk, int head_dim, int dtype);
+MAVLM_API int mavlm_xattn_bwd(const void* Q, int64_t ldq, int64_t qb, const void* K, int64_t ldk, int64_t kb,
+                              const void* V, int64_t ldv, int64_t vb, const void* O, int64_t ldo, int64_t ob,
+                              const void* dO, int64_t lddo, int64_t dob, const float* lse, void* dQ, int64_t lddq,
+                              int64_t dqb, void* dK, int64_t lddk, int64_t dkb, void* dV, int64_t lddv, int64_t dvb,
+                              int batch, int heads, int lq, int lk, int head_dim, float scale, int dtype,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

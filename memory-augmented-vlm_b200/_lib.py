@@ -43,6 +43,18 @@ PROTOTYPES = {
                                 c_float, c_int, c_void_p, c_size_t, c_void_p]),
     "mavlm_assemble_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mavlm_gemm_ex": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int, c_int,
+                              c_float, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "mavlm_colsum": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mavlm_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
+                                    c_int, c_void_p]),
+    "mavlm_act_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "mavlm_act_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "mavlm_xattn_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "mavlm_xattn_bwd": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64,
+                                c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64,
+                                c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int,
+                                c_int, c_int, c_float, c_int, c_void_p, c_size_t, c_void_p]),
     "mavlm_debug_force_gemm_bn": (c_int, [c_int]),
     "mavlm_debug_force_attn_groups": (c_int, [c_int]),
 }

@@ -12,14 +12,15 @@ struct SimtGemmParams {
   const float* B; long long ldb; long long b_batch;      // B_NK: B[n][k] (k contiguous); B_KN: B[k][n] (n contiguous)
   float* C; long long ldc; long long c_batch;
   const float* bias; const float* resid; long long ldr; const float* addvec;
-  int M, N, K; int act; float alpha;
+  int M, N, K; int act; float alpha; int accumulate;   // accumulate: C += result (gradient accumulation)
   int inner_batch;            // blockIdx.z = outer * inner_batch + inner
   long long a_batch2, b_batch2, c_batch2;  // strides of the inner batch index (heads)
 };
 
 constexpr int SBM = 128, SBN = 64, SBK = 16, STHREADS = 256;
 
-template <bool B_KN>
+// A_KM: A stored [k][m] (m contiguous) instead of [m][k];  B_KN: B stored [k][n] instead of [n][k].
+template <bool A_KM, bool B_KN>
 __global__ void __launch_bounds__(STHREADS) simt_gemm_kernel(SimtGemmParams p) {
   __shared__ __align__(16) float As[SBK][SBM + 4];
   __shared__ __align__(16) float Bs[SBK][SBN + 4];
@@ -37,24 +38,45 @@ __global__ void __launch_bounds__(STHREADS) simt_gemm_kernel(SimtGemmParams p) {
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
   for (int k0 = 0; k0 < p.K; k0 += SBK) {
-    // A tile: 128 rows x 16 k -> 512 float4, two per thread, stored transposed
+    if (!A_KM) {
+      // A tile: 128 rows x 16 k -> 512 float4, two per thread, stored transposed
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
-      const int q = tid + it * STHREADS;
-      const int r = q / 4, kk = (q % 4) * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      const int gm = m0 + r, gk = k0 + kk;
-      if (gm < p.M) {
-        if (gk + 3 < p.K && (reinterpret_cast<uintptr_t>(A + gm * p.lda + gk) & 15) == 0) {
-          v = *reinterpret_cast<const float4*>(A + gm * p.lda + gk);
-        } else {
-          float t[4] = {0.f, 0.f, 0.f, 0.f};
-          for (int e = 0; e < 4; ++e)
-            if (gk + e < p.K) t[e] = A[gm * p.lda + gk + e];
-          v = make_float4(t[0], t[1], t[2], t[3]);
+      for (int it = 0; it < 2; ++it) {
+        const int q = tid + it * STHREADS;
+        const int r = q / 4, kk = (q % 4) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int gm = m0 + r, gk = k0 + kk;
+        if (gm < p.M) {
+          if (gk + 3 < p.K && (reinterpret_cast<uintptr_t>(A + gm * p.lda + gk) & 15) == 0) {
+            v = *reinterpret_cast<const float4*>(A + gm * p.lda + gk);
+          } else {
+            float t[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int e = 0; e < 4; ++e)
+              if (gk + e < p.K) t[e] = A[gm * p.lda + gk + e];
+            v = make_float4(t[0], t[1], t[2], t[3]);
+          }
         }
+        As[kk + 0][r] = v.x; As[kk + 1][r] = v.y; As[kk + 2][r] = v.z; As[kk + 3][r] = v.w;
       }
-      As[kk + 0][r] = v.x; As[kk + 1][r] = v.y; As[kk + 2][r] = v.z; As[kk + 3][r] = v.w;
+    } else {
+      // A stored [k][m]: 16 k x 128 m -> 512 float4 along m, two per thread
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int q = tid + it * STHREADS;
+        const int kk = q / 32, c = (q % 32) * 4;
+        float t[4] = {0.f, 0.f, 0.f, 0.f};
+        const int gk = k0 + kk, gm = m0 + c;
+        if (gk < p.K) {
+          if (gm + 3 < p.M && (reinterpret_cast<uintptr_t>(A + gk * p.lda + gm) & 15) == 0) {
+            const float4 v = *reinterpret_cast<const float4*>(A + gk * p.lda + gm);
+            t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+          } else {
+            for (int e = 0; e < 4; ++e)
+              if (gm + e < p.M) t[e] = A[gk * p.lda + gm + e];
+          }
+        }
+        *reinterpret_cast<float4*>(&As[kk][c]) = make_float4(t[0], t[1], t[2], t[3]);
+      }
     }
     if (!B_KN) {
       const int r = tid / 4, kk = (tid % 4) * 4;  // 64 rows x 16 k
@@ -116,18 +138,24 @@ __global__ void __launch_bounds__(STHREADS) simt_gemm_kernel(SimtGemmParams p) {
       else if (p.act == MAVLM_ACT_RELU) v = fmaxf(v, 0.f);
       if (p.resid) v += p.resid[gm * p.ldr + gn];
       if (p.addvec) v += p.addvec[gn];
+      if (p.accumulate) v += C[gm * p.ldc + gn];
       C[gm * p.ldc + gn] = v;
     }
   }
 }
 
-int simt_gemm_launch(const SimtGemmParams& p, bool b_kn, int batches, cudaStream_t st) {
+int simt_gemm_launch(const SimtGemmParams& p, bool b_kn, int batches, cudaStream_t st, bool a_km = false) {
   if (p.M == 0 || p.N == 0 || batches == 0) return MAVLM_OK;
   // unaligned rows (e.g. head_dim 2 in the tiny golden fixtures) take the scalar load path in-kernel
   dim3 grid(ceil_div(p.N, SBN), ceil_div(p.M, SBM), batches);
   MAVLM_REQUIRE(grid.y <= 65535 && grid.z <= 65535, MAVLM_E_INVALID, "fp32 gemm: grid too large");
-  if (b_kn) simt_gemm_kernel<true><<<grid, STHREADS, 0, st>>>(p);
-  else simt_gemm_kernel<false><<<grid, STHREADS, 0, st>>>(p);
+  if (a_km) {
+    if (b_kn) simt_gemm_kernel<true, true><<<grid, STHREADS, 0, st>>>(p);
+    else simt_gemm_kernel<true, false><<<grid, STHREADS, 0, st>>>(p);
+  } else {
+    if (b_kn) simt_gemm_kernel<false, true><<<grid, STHREADS, 0, st>>>(p);
+    else simt_gemm_kernel<false, false><<<grid, STHREADS, 0, st>>>(p);
+  }
   MAVLM_LAUNCH_OK();
   return MAVLM_OK;
 }
@@ -238,6 +266,23 @@ int xattn_fp32(const float* Q, long long ldq, long long qb, const float* K, long
   g.C = O; g.ldc = ldo; g.c_batch = ob; g.c_batch2 = dh;
   g.M = lq; g.N = dh; g.K = lk; g.act = MAVLM_ACT_NONE; g.alpha = 1.f; g.inner_batch = heads;
   return simt_gemm_launch(g, true, batch * heads, st);
+}
+
+// General fp32 GEMM of the backward pass: C[M,N] (+)= alpha * op(A) op(B), with (outer, inner) batching.
+int gemm_ex_fp32(const float* A, long long lda, int trans_a, const float* B, long long ldb, int trans_b, float* C,
+                 long long ldc, int M, int N, int K, float alpha, int accumulate, int outer, int inner,
+                 const long long* strides /* a_o, a_i, b_o, b_i, c_o, c_i */, cudaStream_t st) {
+  SimtGemmParams p{};
+  p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc;
+  p.M = M; p.N = N; p.K = K; p.act = MAVLM_ACT_NONE; p.alpha = alpha; p.accumulate = accumulate;
+  p.inner_batch = inner < 1 ? 1 : inner;
+  if (strides != nullptr) {
+    p.a_batch = strides[0]; p.a_batch2 = strides[1];
+    p.b_batch = strides[2]; p.b_batch2 = strides[3];
+    p.c_batch = strides[4]; p.c_batch2 = strides[5];
+  }
+  // trans_b = 1: B is [N,K] (nn.Linear weight layout, the kernel's native B_NK); 0: B is [K,N]
+  return simt_gemm_launch(p, trans_b == 0, (outer < 1 ? 1 : outer) * p.inner_batch, st, trans_a != 0);
 }
 
 int gemm_fp32(const float* A, long long lda, const float* W, long long ldw, const float* bias, const float* resid,

@@ -102,36 +102,44 @@ class Attention(nn.Module):
         self.last_col_scores: Optional[torch.Tensor] = None
 
     # ---- weight packing: [Wk;Wv] fused, heads padded for the tensor-core tier --------------------
+    def _params(self):
+        return (self.q_proj.weight, self.q_proj.bias, self.k_proj.weight, self.k_proj.bias, self.v_proj.weight,
+                self.v_proj.bias, self.residual.dense.weight)
+
+    def _build_pack(self):
+        """[Wk;Wv] fused and heads padded.  Built from differentiable torch ops, so the same code serves the
+        cached inference pack (under no_grad) and the per-forward training pack (gradients flow to q/k/v_proj)."""
+        h, dh, d = self.num_attention_heads, self.attention_head_size, self.hidden_size
+        dhp = _padded_head_dim(dh, self.q_proj.weight.dtype)
+
+        def pad_rows(w, b):
+            if dhp == dh:
+                return w, b
+            z = w.new_zeros(h, dhp - dh, d)
+            zb = b.new_zeros(h, dhp - dh)
+            return (torch.cat([w.view(h, dh, d), z], dim=1).reshape(h * dhp, d),
+                    torch.cat([b.view(h, dh), zb], dim=1).reshape(h * dhp))
+
+        wq, bq = pad_rows(self.q_proj.weight, self.q_proj.bias)
+        wk, bk = pad_rows(self.k_proj.weight, self.k_proj.bias)
+        wv, bv = pad_rows(self.v_proj.weight, self.v_proj.bias)
+        wkv = torch.cat([wk, wv], dim=0)
+        bkv = torch.cat([bk, bv], dim=0)
+        wo = self.residual.dense.weight
+        if dhp != dh:
+            wo = torch.cat([wo.view(d, h, dh), wo.new_zeros(d, h, dhp - dh)], dim=2).reshape(d, h * dhp)
+        return {"wq": wq.contiguous(), "bq": bq.contiguous(), "wkv": wkv.contiguous(), "bkv": bkv.contiguous(),
+                "wo": wo.contiguous(), "dhp": dhp}
+
     def packed(self):
-        ps = (self.q_proj.weight, self.q_proj.bias, self.k_proj.weight, self.k_proj.bias, self.v_proj.weight,
-              self.v_proj.bias, self.residual.dense.weight)
+        ps = self._params()
+        if torch.is_grad_enabled() and any(p.requires_grad for p in ps):
+            return self._build_pack()                                   # training: part of the autograd graph
         key = tuple((p.data_ptr(), p._version, p.dtype, p.device) for p in ps)
         if self._pack_key == key:
             return self._pack
-        h, dh, d = self.num_attention_heads, self.attention_head_size, self.hidden_size
-        dhp = _padded_head_dim(dh, self.q_proj.weight.dtype)
         with torch.no_grad():
-            def pad_rows(w, b):
-                if dhp == dh:
-                    return w.detach(), b.detach()
-                wp = w.new_zeros(h, dhp, d)
-                wp[:, :dh] = w.view(h, dh, d)
-                bp = b.new_zeros(h, dhp)
-                bp[:, :dh] = b.view(h, dh)
-                return wp.view(h * dhp, d), bp.view(h * dhp)
-
-            wq, bq = pad_rows(self.q_proj.weight, self.q_proj.bias)
-            wk, bk = pad_rows(self.k_proj.weight, self.k_proj.bias)
-            wv, bv = pad_rows(self.v_proj.weight, self.v_proj.bias)
-            wkv = torch.cat([wk, wv], dim=0).contiguous()
-            bkv = torch.cat([bk, bv], dim=0).contiguous()
-            wo = self.residual.dense.weight.detach()
-            if dhp != dh:
-                wop = wo.new_zeros(d, h, dhp)
-                wop[:, :, :dh] = wo.view(d, h, dh)
-                wo = wop.view(d, h * dhp)
-        self._pack = {"wq": wq.contiguous(), "bq": bq.contiguous(), "wkv": wkv, "bkv": bkv, "wo": wo.contiguous(),
-                      "dhp": dhp}
+            self._pack = self._build_pack()
         self._pack_key = key
         return self._pack
 
@@ -229,9 +237,8 @@ class TransformerProjector(nn.Module):
     def initial_state(self, dtype: torch.dtype) -> torch.Tensor:
         """(initial_memory + memory_pos_embed).to(dtype)   (MemoryController.py:123-124) via the PE-add kernel."""
         im = self.initial_memory
-        idx = torch.arange(self.num_memory_tokens, device=im.device)
-        table = self.memory_pos_embed.detach().reshape(self.num_memory_tokens, self.hidden_size).float().contiguous()
-        return ops.add_pe(im.detach().to(dtype), table, idx)
+        table = self.memory_pos_embed.reshape(self.num_memory_tokens, self.hidden_size)
+        return ops.add_rows(im if im.dtype == dtype else im.to(dtype), table)
 
     def _update_memory_tokens_with_cache(self, current_memory: torch.Tensor) -> torch.Tensor:
         """Memory evolution (MemoryController.py:89-115): Q = last state, K/V = all cached states.

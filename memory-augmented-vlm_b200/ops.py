@@ -50,10 +50,26 @@ def _rowmajor2d(t: torch.Tensor, name: str) -> torch.Tensor:
     return t
 
 
+def _grad_needed(*ts: Optional[torch.Tensor]) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts)
+
+
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: int = ACT_NONE,
            resid: Optional[torch.Tensor] = None, addvec: Optional[torch.Tensor] = None,
            out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
-    """y = act(x @ weight.T + bias) (+ resid) (+ addvec);  x [..., K], weight [N, K] (nn.Linear layout)."""
+    """y = act(x @ weight.T + bias) (+ resid) (+ addvec);  x [..., K], weight [N, K] (nn.Linear layout).
+    Differentiable (autograd.py) when an operand requires grad."""
+    if _grad_needed(x, weight, bias, resid, addvec):
+        if out is not None:
+            raise RuntimeError("mavlm.linear: out= cannot be combined with autograd")
+        from . import autograd as ag
+        return ag.linear(x, weight, bias, act, resid, addvec, out_dtype)
+    return _linear_raw(x, weight, bias, act=act, resid=resid, addvec=addvec, out=out, out_dtype=out_dtype)
+
+
+def _linear_raw(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: int = ACT_NONE,
+                resid: Optional[torch.Tensor] = None, addvec: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     _need_cuda(x, weight, bias, resid, addvec, out)
     lead = x.shape[:-1]
     k = x.shape[-1]
@@ -105,6 +121,14 @@ def cast(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
               out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    if _grad_needed(x, gamma, beta):
+        from . import autograd as ag
+        return ag.LayerNormFn.apply(x, gamma, beta, eps, out_dtype)
+    return _layernorm_raw(x, gamma, beta, eps, out_dtype)
+
+
+def _layernorm_raw(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
+                   out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     _need_cuda(x, gamma, beta)
     d = x.shape[-1]
     x2 = x.reshape(-1, d)
@@ -123,6 +147,20 @@ def xattn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *, head
           want_col_scores: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:
     """softmax(q k^T * scale) v per head.  q [B, Lq, H*dh], k/v [B, Lk, H*dh] (last dim contiguous; row /
     batch strides free, so k and v may be column slices of one fused projection buffer)."""
+    if _grad_needed(q, k, v):
+        if want_lse or want_col_scores:
+            raise RuntimeError("mavlm.xattn: lse / col_scores outputs are not available under autograd")
+        from . import autograd as ag
+        dh = head_dim or q.shape[-1] // heads
+        sc = scale if scale is not None else 1.0 / math.sqrt(dh)
+        return ag.XAttnFn.apply(q, k, v, heads, dh, sc), None, None
+    return _xattn_raw(q, k, v, heads, head_dim=head_dim, scale=scale, want_lse=want_lse,
+                      want_col_scores=want_col_scores)
+
+
+def _xattn_raw(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *, head_dim: Optional[int] = None,
+               scale: Optional[float] = None, want_lse: bool = False,
+               want_col_scores: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:
     _need_cuda(q, k, v)
     if q.dim() != 3 or k.dim() != 3 or v.dim() != 3:
         raise RuntimeError("mavlm.xattn: q, k, v must be [B, L, H*dh]")
@@ -171,9 +209,22 @@ def pool_pe(x: torch.Tensor, *, side: int, stride: int = 2, mode: str = "bilinea
     return y
 
 
+def add_rows(x: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
+    """y[t, n, :] = x[t, n, :] + table[t, :]  (differentiable in x and table)."""
+    if _grad_needed(x, table):
+        from . import autograd as ag
+        return ag.AddRowsFn.apply(x, table)
+    return _add_pe_raw(x.contiguous(), table.detach().float().contiguous(), torch.arange(x.shape[0], device=x.device))
+
+
 def add_pe(x: torch.Tensor, pe_table: torch.Tensor, frame_idx: torch.Tensor,
            out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x [T, N, C] + pe_table[frame_idx][:, None, :]  (out may alias x: the kernel is elementwise)."""
+    return _add_pe_raw(x, pe_table, frame_idx, out)
+
+
+def _add_pe_raw(x: torch.Tensor, pe_table: torch.Tensor, frame_idx: torch.Tensor,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _need_cuda(x, pe_table, frame_idx)
     t, n, c = x.shape
     if not x.is_contiguous():

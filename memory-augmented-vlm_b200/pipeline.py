@@ -215,6 +215,38 @@ class VisualMemoryPipeline(nn.Module):
                                validate=validate)
         return self.memory_forward(z.reshape(b, f, *z.shape[1:]), **kw)
 
+    def memory_forward_train(self, z: torch.Tensor, *, drop_frames: bool = False) -> Dict[str, torch.Tensor]:
+        """Differentiable version of memory_forward for training (BPTT): list-based state cache like the
+        reference (MemoryController.py:152-154), every op an autograd.Function backed by libmavlm.so.
+        z [B, F, P, D] are the (detached) pooled + PE'd frames; gradients reach the recurrent memory
+        transformer, the fuser, token_type_embedding, image_newline and embed_tokens (prompt rows)."""
+        rmt = self.recurrent_memory_transformer
+        b, f, p, d = z.shape
+        dev = z.device
+        z = z.detach()                                                  # llava_arch.py:302,481
+        pm_ids, pf_ids = self._const_ids(dev)
+        fine_idx = fine_frame_indices(f, self.max_fine_frames).to(dev)
+        emb = self.token_type_embedding.weight
+        newline = self.image_newline
+        fz = self.memory_fuser
+        bounds = uniform_segment_variant(f, self.chunk_size)
+        seqs, states = [], []
+        for bi in range(b):
+            rmt.memory_cache = []
+            for i in range(len(bounds) - 1):
+                cache, _ = rmt(z[bi, bounds[i]:bounds[i + 1]])
+            cat = torch.cat(cache, dim=0)                               # [n*M, P, D]   llava_arch.py:545
+            hid = ops.linear(cat.reshape(-1, d), fz[0].weight, fz[0].bias, act=ACT_GELU_ERF)
+            mem = ops.linear(hid, fz[2].weight, fz[2].bias, addvec=emb[0])          # + token_type_embedding[0]
+            parts = [self.embed_tokens(pm_ids), mem, newline[None].to(mem.dtype)]
+            if not drop_frames:
+                fine = ops.add_rows(z[bi][fine_idx].reshape(1, -1, d), emb[1][None])  # + token_type_embedding[1]
+                parts += [self.embed_tokens(pf_ids), fine[0], newline[None].to(mem.dtype)]
+            seqs.append(torch.cat(parts, dim=0))
+            states.append(torch.stack(list(cache), dim=0))
+            rmt.memory_cache = []
+        return {"sequence": torch.stack(seqs, dim=0), "states": torch.stack(states, dim=0)}
+
     def graphed(self, batch: int, frames: int, *, return_states: bool = False) -> "GraphedPipeline":
         """CUDA-graph replay of forward() for a fixed (batch, frames): the ~45 dependent launches of a step
         become one graph launch (the recurrence is launch-latency sensitive: ~25 kernels per chunk)."""

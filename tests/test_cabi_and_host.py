@@ -109,6 +109,9 @@ def test_padded_head_packing_is_exact():
     cfg.mm_hidden_size, cfg.mm_intermediate_size, cfg.mm_dtype = 896, 3584, torch.bfloat16
     torch.manual_seed(0)
     att = M.Attention(cfg)
+    pg = att.packed()                                                  # grad enabled: differentiable, not cached
+    assert pg["wq"].requires_grad and pg["wkv"].requires_grad and att.packed() is not pg
+    torch.set_grad_enabled(False)
     p = att.packed()
     assert p["dhp"] == 128 and p["wq"].shape == (1024, 896) and p["wkv"].shape == (2048, 896)
     x = torch.randn(5, 896).bfloat16()
@@ -121,10 +124,10 @@ def test_padded_head_packing_is_exact():
     o = ctx.reshape(5, 896) @ att.residual.dense.weight.float().T
     op = ctxp.reshape(5, 1024) @ p["wo"].float().T
     assert torch.allclose(o, op, atol=1e-5)
-    assert att.packed() is p                                           # cached until a weight changes
-    with torch.no_grad():
-        att.q_proj.weight.mul_(2.0)
+    assert att.packed() is p and not p["wq"].requires_grad             # inference: cached until a weight changes
+    att.q_proj.weight.mul_(2.0)
     assert att.packed() is not p
+    torch.set_grad_enabled(True)
     cfg32 = M.Config()
     cfg32.mm_hidden_size, cfg32.mm_intermediate_size, cfg32.mm_dtype = 896, 3584, torch.float32
     assert M.Attention(cfg32).packed()["dhp"] == 112                   # fp32 tier: no padding

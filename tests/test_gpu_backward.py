@@ -1,0 +1,140 @@
+"""Backward / training parity (BASELINE config[3] shape class): gradients of the CUDA path (autograd
+Functions whose forward AND backward run in libmavlm.so) against golden gradients produced by the
+unmodified reference under PyTorch autograd in float64 (tools/gen_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import mavlm_b200 as M
+from mavlm_b200 import ops, synthetic
+from oracle import vismem_oracle as O
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GRAD_TOL = 2e-4        # fp32 tier vs float64 reference autograd, err = max|a-b| / max|b| per parameter
+
+
+def err(a, b):
+    return O.normalized_max_error(a.detach().double().cpu().numpy(), b)
+
+
+def _load(name):
+    z = np.load(os.path.join(GOLDEN, name))
+    w = {k[3:]: z[k] for k in z.files if k.startswith("w::")}
+    g = {k[3:]: z[k] for k in z.files if k.startswith("g::")}
+    return z, w, g
+
+
+def _rmt(w, d, prefix="recurrent_memory_transformer."):
+    cfg = M.Config()
+    cfg.mm_hidden_size, cfg.mm_intermediate_size, cfg.depth, cfg.mm_dtype = d, 4 * d, 2, torch.float32
+    rmt = M.TransformerProjector(cfg)
+    rmt.load_state_dict({k[len(prefix):]: torch.from_numpy(v).float() for k, v in w.items() if k.startswith(prefix)})
+    return rmt.to(DEV)
+
+
+def test_op_level_gradients_match_torch_autograd():
+    """Each autograd.Function against torch's own autograd of the same math (fp32)."""
+    torch.manual_seed(0)
+    x = torch.randn(70, 48, device=DEV, requires_grad=True)
+    w = torch.randn(36, 48, device=DEV, requires_grad=True)
+    b = torch.randn(36, device=DEV, requires_grad=True)
+    r = torch.randn(70, 36, device=DEV, requires_grad=True)
+    av = torch.randn(36, device=DEV, requires_grad=True)
+    for act, fn in ((0, lambda t: t), (2, torch.relu), (1, torch.nn.functional.gelu)):
+        use_r = act == 0
+        y = ops.linear(x, w, b, act=act, resid=r if use_r else None, addvec=av if use_r else None)
+        ref = fn(x @ w.T + b) + (r + av if use_r else 0)
+        go = torch.randn_like(ref)
+        got = torch.autograd.grad(y, [x, w, b] + ([r, av] if use_r else []), go)
+        exp = torch.autograd.grad(ref, [x, w, b] + ([r, av] if use_r else []), go)
+        for a_, e_ in zip(got, exp):
+            assert err(a_, e_.double().cpu().numpy()) < 1e-5, act
+    pre = torch.randn(33, 64, device=DEV, requires_grad=True)
+    g = torch.randn(64, device=DEV, requires_grad=True)
+    be = torch.randn(64, device=DEV, requires_grad=True)
+    y = ops.layernorm(pre, g, be, 1e-12)
+    ref = torch.nn.functional.layer_norm(pre, (64,), g, be, 1e-12)
+    go = torch.randn_like(ref)
+    for a_, e_ in zip(torch.autograd.grad(y, [pre, g, be], go), torch.autograd.grad(ref, [pre, g, be], go)):
+        assert err(a_, e_.double().cpu().numpy()) < 1e-5
+    h, dh = 4, 8
+    q = torch.randn(2, 50, h * dh, device=DEV, requires_grad=True)
+    kv = torch.randn(2, 77, 2 * h * dh, device=DEV, requires_grad=True)
+    o, _, _ = ops.xattn(q, kv[..., :h * dh], kv[..., h * dh:], h)
+    qh = q.view(2, 50, h, dh).transpose(1, 2)
+    kh = kv[..., :h * dh].reshape(2, 77, h, dh).transpose(1, 2)
+    vh = kv[..., h * dh:].reshape(2, 77, h, dh).transpose(1, 2)
+    ref = ((qh @ kh.transpose(-1, -2) / dh ** 0.5).softmax(-1) @ vh).transpose(1, 2).reshape(2, 50, h * dh)
+    go = torch.randn_like(ref)
+    assert err(o, ref.detach().double().cpu().numpy()) < 1e-5
+    for a_, e_ in zip(torch.autograd.grad(o, [q, kv], go), torch.autograd.grad(ref, [q, kv], go)):
+        assert err(a_, e_.double().cpu().numpy()) < 1e-5
+
+
+def test_rmt_bptt_gradients_against_reference_golden():
+    """2 chunks (formation x2 + evolution): every RMT parameter's gradient vs the reference's autograd."""
+    z, w, g = _load("rmt_grads.npz")
+    rmt = _rmt(w, 16)
+    frames = torch.from_numpy(z["frames"]).float().to(DEV)
+    rmt.memory_cache = []
+    for i in range(2):
+        cache, _ = rmt(frames[2 * i:2 * i + 2])
+    loss = sum((s * s).mean() for s in cache)
+    assert abs(float(loss) - float(z["loss"])) < 1e-5 * abs(float(z["loss"]))
+    loss.backward()
+    n = 0
+    for name, p in rmt.named_parameters():
+        ref = g["recurrent_memory_transformer." + name]
+        assert p.grad is not None, name
+        assert err(p.grad, ref) < GRAD_TOL, (name, err(p.grad, ref))
+        n += 1
+    assert n == len(g)
+
+
+def test_whole_path_gradients_against_reference_golden():
+    """loss = mean(sequence^2) through memory (3 chunks) + fuser + type embeddings + newline + prompt embeddings."""
+    z, w, g = _load("path_grads.npz")
+    d = 16
+    pipe, _ = synthetic.build_pipeline(d, 4, dtype=torch.float32, chunk_size=2, device=DEV, vocab=50000)
+    pipe.recurrent_memory_transformer.load_state_dict(
+        {k[len("recurrent_memory_transformer."):]: torch.from_numpy(v).float() for k, v in w.items()
+         if k.startswith("recurrent_memory_transformer.")})
+    pipe.memory_fuser.load_state_dict({k[len("memory_fuser."):]: torch.from_numpy(v).float() for k, v in w.items()
+                                       if k.startswith("memory_fuser.")})
+    pipe.token_type_embedding.load_state_dict({"weight": torch.from_numpy(w["token_type_embedding.weight"]).float()})
+    pipe.image_newline = torch.nn.Parameter(torch.from_numpy(w["image_newline"]).float().to(DEV))
+    rows = torch.from_numpy(z["embed_rows"])
+    with torch.no_grad():
+        pipe.embed_tokens.weight[rows] = torch.from_numpy(w["embed_rows"]).float().to(DEV)
+    zz = torch.from_numpy(z["z"]).float().to(DEV)[None]
+    out = pipe.memory_forward_train(zz)
+    assert err(out["sequence"][0], z["sequence"]) < 2e-5
+    loss = (out["sequence"] ** 2).mean()
+    loss.backward()
+    for pref, mod in (("recurrent_memory_transformer.", pipe.recurrent_memory_transformer),
+                      ("memory_fuser.", pipe.memory_fuser), ("token_type_embedding.", pipe.token_type_embedding)):
+        for name, p in mod.named_parameters():
+            assert err(p.grad, g[pref + name]) < GRAD_TOL, (pref + name, err(p.grad, g[pref + name]))
+    assert err(pipe.image_newline.grad, g["image_newline"]) < GRAD_TOL
+    assert err(pipe.embed_tokens.weight.grad[rows.to(DEV)], g["embed_rows"]) < GRAD_TOL
+    # inference path == training path forward
+    with torch.no_grad():
+        inf = pipe.memory_forward(zz)
+    assert err(inf["sequence"][0], out["sequence"][0].detach().double().cpu().numpy()) < 1e-5
+
+
+def test_single_chunk_leaves_evolution_attention_without_gradient():
+    """SURVEY.md §3.2 (probed on the reference): with one chunk memory_update_attention gets no gradient."""
+    z, w, _ = _load("rmt_grads.npz")
+    rmt = _rmt(w, 16)
+    rmt.memory_cache = []
+    cache, _ = rmt(torch.from_numpy(z["frames"]).float().to(DEV))
+    (cache[-1] ** 2).mean().backward()
+    assert all(p.grad is None for p in rmt.memory_update_attention.parameters())
+    assert all(p.grad is not None for p in rmt.layers.parameters())
+    assert rmt.initial_memory.grad is not None and rmt.memory_pos_embed.grad is not None

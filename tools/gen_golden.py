@@ -152,6 +152,44 @@ def gen_rmt_grads(MC):
     np.savez(os.path.join(OUT, "rmt_grads.npz"), **out, **{"w::" + k: v for k, v in w.items()})
 
 
+def gen_path_grads(MC):
+    """Gradients of loss = mean(sequence^2) for memory + fuser + type embeddings + newline + prompt embeddings
+    (reference TransformerProjector; the glue below follows llava_arch.py:545-557, 620-629, 708-731), fp64.
+    6 pooled frames in chunks of 2 -> 3 chunks (formation x3, evolution x2), 6 fine frames."""
+    d = 16
+    rmt = build_rmt(MC, d, seed=11).double()
+    torch.manual_seed(12)
+    fuser = torch.nn.Sequential(torch.nn.Linear(d, 4 * d), torch.nn.GELU(), torch.nn.Linear(4 * d, d)).double()
+    tte = torch.nn.Embedding(2, d).double()
+    newline = torch.nn.Parameter(torch.randn(d, dtype=torch.float64) * d ** -0.5)
+    emb = torch.nn.Embedding(50000, d).double()
+    z = torch.randn(6, 196, d, dtype=torch.float64)
+    rmt.memory_cache = []
+    for i in range(3):
+        cache, _ = rmt(z[2 * i:2 * i + 2])
+    mem = fuser(torch.cat(cache, dim=0))
+    mem = mem + tte(torch.zeros((mem.shape[0], 196), dtype=torch.long))
+    fine_idx = torch.clamp(torch.round(torch.linspace(0, 5, steps=6)).long(), 0, 5)
+    fine = z[fine_idx] + tte(torch.ones((6, 196), dtype=torch.long))
+    pm = emb(torch.tensor([1986, 374, 264, 1550, 11591, 12126, 315, 279, 2766, 25]))
+    pf = emb(torch.tensor([9485, 525, 48876, 9124, 14087, 504, 279, 2766, 25]))
+    seq = torch.cat([pm, mem.flatten(0, 1), newline[None], pf, fine.flatten(0, 1), newline[None]], dim=0)
+    loss = (seq * seq).mean()
+    loss.backward()
+    out = {"z": z.numpy(), "loss": np.array(float(loss.detach())), "sequence": seq.detach().numpy()}
+    for pref, mod in (("recurrent_memory_transformer.", rmt), ("memory_fuser.", fuser), ("token_type_embedding.", tte)):
+        for n, p_ in mod.named_parameters():
+            out["w::" + pref + n] = p_.detach().numpy().copy()
+            out["g::" + pref + n] = p_.grad.numpy().copy()
+    out["w::image_newline"] = newline.detach().numpy().copy()
+    out["g::image_newline"] = newline.grad.numpy().copy()
+    rows = sorted(set([1986, 374, 264, 1550, 11591, 12126, 315, 279, 2766, 25, 9485, 525, 48876, 9124, 14087, 504]))
+    out["embed_rows"] = np.array(rows)
+    out["w::embed_rows"] = emb.weight.detach().numpy()[rows].copy()
+    out["g::embed_rows"] = emb.weight.grad.numpy()[rows].copy()
+    np.savez(os.path.join(OUT, "path_grads.npz"), **out)
+
+
 def gen_pe(PE):
     out = {}
     for d in (32, 896, 3584):
@@ -325,6 +363,7 @@ def main():
     ARCH = importlib.import_module("llava.model.llava_arch")
     gen_rmt(MC)
     gen_rmt_grads(MC)
+    gen_path_grads(MC)
     gen_pe(PE)
     gen_projector_fuser(PB, MF)
     gen_pool_and_full(ARCH, PB)
