@@ -18,8 +18,11 @@ DEV = "cuda:0"
 GRAD_TOL = 2e-4        # fp32 tier vs float64 reference autograd, err = max|a-b| / max|b| per parameter
 
 
-def err(a, b):
-    return O.normalized_max_error(a.detach().double().cpu().numpy(), b)
+def err(a, b, floor=0.0):
+    """max|a-b| / max(max|b|, floor).  `floor` guards parameters whose true gradient is exactly zero (k_proj.bias:
+    softmax is invariant to a per-query constant), where the reference holds 1e-20 noise and fp32 holds 1e-10."""
+    a = a.detach().double().cpu().numpy()
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), floor, 1e-30))
 
 
 def _load(name):
@@ -88,10 +91,12 @@ def test_rmt_bptt_gradients_against_reference_golden():
     assert abs(float(loss) - float(z["loss"])) < 1e-5 * abs(float(z["loss"]))
     loss.backward()
     n = 0
+    gmax = max(np.abs(v).max() for v in g.values())
     for name, p in rmt.named_parameters():
         ref = g["recurrent_memory_transformer." + name]
         assert p.grad is not None, name
-        assert err(p.grad, ref) < GRAD_TOL, (name, err(p.grad, ref))
+        floor = gmax * (1e-2 if name.endswith("k_proj.bias") else 1e-6)     # k bias: true gradient is exactly 0
+        assert err(p.grad, ref, floor) < GRAD_TOL, (name, err(p.grad, ref, floor))
         n += 1
     assert n == len(g)
 
@@ -116,12 +121,15 @@ def test_whole_path_gradients_against_reference_golden():
     assert err(out["sequence"][0], z["sequence"]) < 2e-5
     loss = (out["sequence"] ** 2).mean()
     loss.backward()
+    gmax = max(np.abs(v).max() for v in g.values())
+    floor = 1e-6 * gmax
     for pref, mod in (("recurrent_memory_transformer.", pipe.recurrent_memory_transformer),
                       ("memory_fuser.", pipe.memory_fuser), ("token_type_embedding.", pipe.token_type_embedding)):
         for name, p in mod.named_parameters():
-            assert err(p.grad, g[pref + name]) < GRAD_TOL, (pref + name, err(p.grad, g[pref + name]))
-    assert err(pipe.image_newline.grad, g["image_newline"]) < GRAD_TOL
-    assert err(pipe.embed_tokens.weight.grad[rows.to(DEV)], g["embed_rows"]) < GRAD_TOL
+            fl = gmax * 1e-2 if name.endswith("k_proj.bias") else floor      # k bias: true gradient is exactly 0
+            assert err(p.grad, g[pref + name], fl) < GRAD_TOL, (pref + name, err(p.grad, g[pref + name], fl))
+    assert err(pipe.image_newline.grad, g["image_newline"], floor) < GRAD_TOL
+    assert err(pipe.embed_tokens.weight.grad[rows.to(DEV)], g["embed_rows"], floor) < GRAD_TOL
     # inference path == training path forward
     with torch.no_grad():
         inf = pipe.memory_forward(zz)
