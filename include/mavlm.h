@@ -111,10 +111,12 @@ MAVLM_API int mavlm_assemble_fwd(void* seq, const void* mem, int64_t n_mem_rows,
 /* General GEMM: C[M,N] (+)= alpha * op(A) op(B).  trans_a = 0: A is [M,K]; 1: A is [K,M].  trans_b = 1: B is [N,K]
  * (nn.Linear weight layout); 0: B is [K,N].  Batched over outer*inner problems; strides (elements) =
  * {a_outer, a_inner, b_outer, b_inner, c_outer, c_inner} or NULL.  dgrad: dX = dY W (trans_b = 0);
- * wgrad: dW (+)= dY^T X (trans_a = 1, trans_b = 0, accumulate over chunks). */
+ * wgrad: dW (+)= dY^T X (trans_a = 1, trans_b = 0, accumulate over chunks).  MAVLM_BF16 runs on the tcgen05
+ * kernel (transposed operands are consumed as MN-major UMMA operands; alpha must be 1; out_dtype may be
+ * MAVLM_F32), MAVLM_F32 on the SIMT tier. */
 MAVLM_API int mavlm_gemm_ex(const void* A, int64_t lda, int trans_a, const void* B, int64_t ldb, int trans_b, void* C,
                             int64_t ldc, int M, int N, int K, float alpha, int accumulate, int outer, int inner,
-                            const int64_t* host_strides, int dtype, void* stream);
+                            const int64_t* host_strides, int dtype, int out_dtype, void* stream);
 /* out[n] (+)= sum_m x[m,n]  (fp32 out): bias / type-embedding / newline gradients. */
 MAVLM_API int mavlm_colsum(const void* x, int64_t ld, float* out, int M, int N, int accumulate, int dtype, void* stream);
 /* LayerNorm backward from the saved fp32 pre-LN sum: dpre (fp32), dgamma/dbeta (fp32, ACCUMULATED into). */

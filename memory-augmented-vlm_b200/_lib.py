@@ -44,7 +44,7 @@ PROTOTYPES = {
     "mavlm_assemble_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mavlm_gemm_ex": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int, c_int,
-                              c_float, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+                              c_float, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "mavlm_colsum": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mavlm_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
                                     c_int, c_void_p]),

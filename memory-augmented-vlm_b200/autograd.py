@@ -33,13 +33,14 @@ def _raw():
 
 
 def gemm_ex(a: torch.Tensor, trans_a: bool, b: torch.Tensor, trans_b: bool, m: int, n: int, k: int, *,
-            out: Optional[torch.Tensor] = None, alpha: float = 1.0, accumulate: bool = False) -> torch.Tensor:
+            out: Optional[torch.Tensor] = None, alpha: float = 1.0, accumulate: bool = False,
+            out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     """C[M,N] (+)= alpha * op(A) op(B) on 2-D row-major operands (see include/mavlm.h: mavlm_gemm_ex)."""
     if out is None:
-        out = torch.empty((m, n), dtype=a.dtype, device=a.device)
+        out = torch.empty((m, n), dtype=out_dtype or a.dtype, device=a.device)
     st = _lib.load().mavlm_gemm_ex(_p(a), a.stride(0), int(trans_a), _p(b), b.stride(0), int(trans_b), _p(out),
                                    out.stride(0), m, n, k, float(alpha), int(accumulate), 1, 1, None, _DT[a.dtype],
-                                   _s())
+                                   _DT[out.dtype], _s())
     _lib.check(st, "gemm_ex")
     return out
 

@@ -9,6 +9,9 @@ namespace mavlm {
 int gemm_ex_fp32(const float* A, long long lda, int trans_a, const float* B, long long ldb, int trans_b, float* C,
                  long long ldc, int M, int N, int K, float alpha, int accumulate, int outer, int inner,
                  const long long* strides, cudaStream_t st);
+int gemm_ex_bf16(const __nv_bfloat16* A, long long lda, int trans_a, const __nv_bfloat16* B, long long ldb, int trans_b,
+                 void* C, long long ldc, int M, int N, int K, int accumulate, int out_f32, int outer, int inner,
+                 const long long* s6, cudaStream_t st);
 
 template <typename T>
 __device__ __forceinline__ float ldf(const T* p);
@@ -199,6 +202,44 @@ __global__ void __launch_bounds__(256) ds_kernel(const float* __restrict__ p, fl
   for (int i = threadIdx.x; i < n; i += blockDim.x) dr[i] = pr[i] * (dr[i] - d) * scale;
 }
 
+// ---- attention backward, bf16 tier: scores / dP stay fp32 in the workspace, P and dS are stored as bf16 GEMM operands
+// p[row, :] = bf16(exp(s[row, :] * scale - lse[row]))
+__global__ void __launch_bounds__(256) probs_bf16_kernel(const float* __restrict__ s, const float* __restrict__ lse,
+                                                         __nv_bfloat16* __restrict__ p, int n, float scale) {
+  const float* r = s + static_cast<long long>(blockIdx.x) * n;
+  __nv_bfloat16* o = p + static_cast<long long>(blockIdx.x) * n;
+  const float l = lse[blockIdx.x];
+  for (int i = threadIdx.x * 2; i < n; i += blockDim.x * 2) {
+    const float2 v = *reinterpret_cast<const float2*>(r + i);
+    *reinterpret_cast<__nv_bfloat162*>(o + i) = __floats2bfloat162_rn(__expf(v.x * scale - l), __expf(v.y * scale - l));
+  }
+}
+// ds[row, :] = bf16(p[row, :] * (dp[row, :] - D[row]) * scale), written over p
+__global__ void __launch_bounds__(256) ds_bf16_kernel(__nv_bfloat16* __restrict__ p, const float* __restrict__ dp,
+                                                      const float* __restrict__ D, int n, float scale) {
+  __nv_bfloat16* pr = p + static_cast<long long>(blockIdx.x) * n;
+  const float* dr = dp + static_cast<long long>(blockIdx.x) * n;
+  const float d = D[blockIdx.x];
+  for (int i = threadIdx.x * 2; i < n; i += blockDim.x * 2) {
+    const float2 pv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(pr + i));
+    const float2 g = *reinterpret_cast<const float2*>(dr + i);
+    *reinterpret_cast<__nv_bfloat162*>(pr + i) = __floats2bfloat162_rn(pv.x * (g.x - d) * scale, pv.y * (g.y - d) * scale);
+  }
+}
+__global__ void __launch_bounds__(128) rowdot_bf16_kernel(const __nv_bfloat16* __restrict__ dO, long long ldd,
+                                                          long long dob, const __nv_bfloat16* __restrict__ O,
+                                                          long long ldo, long long ob, float* __restrict__ D, int heads,
+                                                          int lq, int dh) {
+  __shared__ float red[32];
+  const int q = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const __nv_bfloat16* a = dO + b * dob + static_cast<long long>(q) * ldd + h * dh;
+  const __nv_bfloat16* c = O + b * ob + static_cast<long long>(q) * ldo + h * dh;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < dh; i += blockDim.x) s += __bfloat162float(a[i]) * __bfloat162float(c[i]);
+  s = block_sum_b(s, red);
+  if (threadIdx.x == 0) D[(static_cast<long long>(b) * heads + h) * lq + q] = s;
+}
+
 static int ew_grid(long long n) {
   long long b = (n + 255) / 256;
   const long long cap = static_cast<long long>(sm_count()) * 16;
@@ -213,16 +254,21 @@ extern "C" {
 
 int mavlm_gemm_ex(const void* A, int64_t lda, int trans_a, const void* B, int64_t ldb, int trans_b, void* C, int64_t ldc,
                   int M, int N, int K, float alpha, int accumulate, int outer, int inner, const int64_t* strides,
-                  int dtype, void* stream) {
-  MAVLM_REQUIRE(dtype == MAVLM_F32, MAVLM_E_INVALID,
-                "gemm_ex: only the fp32 tier implements the general (transposed / accumulating) GEMM so far");
+                  int dtype, int out_dtype, void* stream) {
   MAVLM_REQUIRE(M >= 0 && N >= 0 && K > 0, MAVLM_E_INVALID, "gemm_ex: bad shape");
   long long st6[6] = {0, 0, 0, 0, 0, 0};
   if (strides != nullptr)
     for (int i = 0; i < 6; ++i) st6[i] = strides[i];
-  return gemm_ex_fp32(static_cast<const float*>(A), lda, trans_a, static_cast<const float*>(B), ldb, trans_b,
-                      static_cast<float*>(C), ldc, M, N, K, alpha, accumulate, outer, inner, st6,
-                      static_cast<cudaStream_t>(stream));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == MAVLM_F32) {
+    MAVLM_REQUIRE(out_dtype == MAVLM_F32, MAVLM_E_INVALID, "gemm_ex: fp32 inputs require fp32 output");
+    return gemm_ex_fp32(static_cast<const float*>(A), lda, trans_a, static_cast<const float*>(B), ldb, trans_b,
+                        static_cast<float*>(C), ldc, M, N, K, alpha, accumulate, outer, inner, st6, st);
+  }
+  MAVLM_REQUIRE(dtype == MAVLM_BF16, MAVLM_E_INVALID, "gemm_ex: bad dtype %d", dtype);
+  MAVLM_REQUIRE(alpha == 1.f, MAVLM_E_INVALID, "gemm_ex: the tensor-core tier has no alpha scaling (got %f)", alpha);
+  return gemm_ex_bf16(static_cast<const __nv_bfloat16*>(A), lda, trans_a, static_cast<const __nv_bfloat16*>(B), ldb,
+                      trans_b, C, ldc, M, N, K, accumulate, out_dtype == MAVLM_F32, outer, inner, st6, st);
 }
 
 int mavlm_colsum(const void* x, int64_t ld, float* out, int M, int N, int accumulate, int dtype, void* stream) {
@@ -294,8 +340,9 @@ int mavlm_act_bwd(const void* dy, const void* ref, void* dx, int64_t n, int act,
 
 size_t mavlm_xattn_bwd_workspace_bytes(int batch, int heads, int lq, int lk, int head_dim, int dtype) {
   (void)head_dim;
-  (void)dtype;
   const size_t rows = static_cast<size_t>(batch) * heads * lq;
+  if (dtype == MAVLM_BF16)  // S/dP fp32, P/dS bf16, D fp32
+    return rows * static_cast<size_t>(lk) * (sizeof(float) + 2) + rows * sizeof(float);
   return (2 * rows * static_cast<size_t>(lk) + rows) * sizeof(float);  // P, dP/dS, D
 }
 
@@ -304,7 +351,7 @@ int mavlm_xattn_bwd(const void* Q, int64_t ldq, int64_t qb, const void* K, int64
                     int64_t dob, const float* lse, void* dQ, int64_t lddq, int64_t dqb, void* dK, int64_t lddk,
                     int64_t dkb, void* dV, int64_t lddv, int64_t dvb, int batch, int heads, int lq, int lk, int head_dim,
                     float scale, int dtype, void* workspace, size_t workspace_bytes, void* stream) {
-  MAVLM_REQUIRE(dtype == MAVLM_F32, MAVLM_E_INVALID, "xattn_bwd: only the fp32 tier is implemented so far");
+  MAVLM_REQUIRE(dtype == MAVLM_F32 || dtype == MAVLM_BF16, MAVLM_E_INVALID, "xattn_bwd: bad dtype %d", dtype);
   const size_t need = mavlm_xattn_bwd_workspace_bytes(batch, heads, lq, lk, head_dim, dtype);
   MAVLM_REQUIRE(workspace != nullptr && workspace_bytes >= need, MAVLM_E_WORKSPACE,
                 "xattn_bwd: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
@@ -312,6 +359,48 @@ int mavlm_xattn_bwd(const void* Q, int64_t ldq, int64_t qb, const void* K, int64
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long rows = static_cast<long long>(batch) * heads * lq;
   const long long hs = static_cast<long long>(lq) * lk;
+  if (dtype == MAVLM_BF16) {
+    // Unfused tensor-core backward: five batched tcgen05 GEMMs (transposed operands as MN-major UMMA operands)
+    // around three elementwise passes.  Scores and dP are kept in fp32; only P and dS are rounded to bf16.
+    MAVLM_REQUIRE(lk % 8 == 0 && head_dim % 8 == 0, MAVLM_E_INVALID, "xattn_bwd bf16: lk and head_dim must be multiples of 8");
+    float* X = static_cast<float*>(workspace);                                  // S, then dP
+    __nv_bfloat16* Pb = reinterpret_cast<__nv_bfloat16*>(X + rows * lk);        // P, then dS
+    float* Dv = reinterpret_cast<float*>(Pb + rows * lk);
+    const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(Q);
+    const __nv_bfloat16* k = static_cast<const __nv_bfloat16*>(K);
+    const __nv_bfloat16* v = static_cast<const __nv_bfloat16*>(V);
+    const __nv_bfloat16* o = static_cast<const __nv_bfloat16*>(O);
+    const __nv_bfloat16* go = static_cast<const __nv_bfloat16*>(dO);
+    const int dh = head_dim;
+    int rc;
+    {  // S = Q K^T (fp32)
+      const long long s6[6] = {qb, dh, kb, dh, hs * heads, hs};
+      if ((rc = gemm_ex_bf16(q, ldq, 0, k, ldk, 1, X, lk, lq, lk, dh, 0, 1, batch, heads, s6, st))) return rc;
+    }
+    probs_bf16_kernel<<<static_cast<unsigned>(rows), 256, 0, st>>>(X, lse, Pb, lk, scale);
+    MAVLM_LAUNCH_OK();
+    {  // dV = P^T dO
+      const long long s6[6] = {hs * heads, hs, dob, dh, dvb, dh};
+      if ((rc = gemm_ex_bf16(Pb, lk, 1, go, lddo, 0, dV, lddv, lk, dh, lq, 0, 0, batch, heads, s6, st))) return rc;
+    }
+    {  // dP = dO V^T (fp32, over S)
+      const long long s6[6] = {dob, dh, vb, dh, hs * heads, hs};
+      if ((rc = gemm_ex_bf16(go, lddo, 0, v, ldv, 1, X, lk, lq, lk, dh, 0, 1, batch, heads, s6, st))) return rc;
+    }
+    rowdot_bf16_kernel<<<dim3(lq, heads, batch), 128, 0, st>>>(go, lddo, dob, o, ldo, ob, Dv, heads, lq, dh);
+    MAVLM_LAUNCH_OK();
+    ds_bf16_kernel<<<static_cast<unsigned>(rows), 256, 0, st>>>(Pb, X, Dv, lk, scale);
+    MAVLM_LAUNCH_OK();
+    {  // dQ = dS K
+      const long long s6[6] = {hs * heads, hs, kb, dh, dqb, dh};
+      if ((rc = gemm_ex_bf16(Pb, lk, 0, k, ldk, 0, dQ, lddq, lq, dh, lk, 0, 0, batch, heads, s6, st))) return rc;
+    }
+    {  // dK = dS^T Q
+      const long long s6[6] = {hs * heads, hs, qb, dh, dkb, dh};
+      if ((rc = gemm_ex_bf16(Pb, lk, 1, q, ldq, 0, dK, lddk, lk, dh, lq, 0, 0, batch, heads, s6, st))) return rc;
+    }
+    return MAVLM_OK;
+  }
   float* P = static_cast<float*>(workspace);
   float* dP = P + rows * lk;
   float* D = dP + rows * lk;

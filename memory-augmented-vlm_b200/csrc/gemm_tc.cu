@@ -33,6 +33,10 @@ struct GemmTcParams {
   int act;
   int out_f32;
   int m_tiles, n_tiles;
+  // general / batched mode (backward pass): problem index = outer * inner + inner_idx
+  int batches, inner;
+  long long c_outer, c_inner;
+  int accumulate;  // C += result
 };
 
 template <int BN>
@@ -56,7 +60,10 @@ __device__ __forceinline__ void gemm_tile_coords(int tile, int m_tiles, int n_ti
   n_blk = r / gm;
 }
 
-template <int BN>
+// A_MN / B_MN: the operand is stored with its M (resp. N) index contiguous ([K, M] / [K, N] row-major: the
+// transposed operands of dgrad / wgrad / attention backward).  Such a tile is loaded as 64x64 boxes
+// [64 k-rows x 64 m] and consumed as an MN-major UMMA operand (8-k-row atoms of 1 KB, 64-wide M groups 8 KB apart).
+template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmTcParams p) {
   using Cfg = GemmCfg<BN>;
@@ -74,7 +81,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int tiles_per_batch = p.m_tiles * p.n_tiles;
+  const int num_tiles = tiles_per_batch * p.batches;
   const int kblocks = (p.K + GEMM_BK - 1) / GEMM_BK;
 
   if (threadIdx.x == 0) {
@@ -102,20 +110,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int m_blk, n_blk;
-        gemm_tile_coords(tile, p.m_tiles, p.n_tiles, m_blk, n_blk);
+        const int batch = tile / tiles_per_batch;
+        gemm_tile_coords(tile - batch * tiles_per_batch, p.m_tiles, p.n_tiles, m_blk, n_blk);
         const int m0 = m_blk * GEMM_BM, n0 = n_blk * BN;
+        const int bi = batch % p.inner, bo = batch / p.inner;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], kb * GEMM_BK, m0);
-          tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * GEMM_BK, n0);
+          uint8_t* a_dst = sA + stage * Cfg::A_BYTES;
+          uint8_t* b_dst = sB + stage * Cfg::B_BYTES;
+          if (!A_MN) {
+            tma_load_4d(a_dst, &tmA, &full[stage], kb * GEMM_BK, m0, bi, bo);
+          } else {
+#pragma unroll
+            for (int i = 0; i < GEMM_BM / 64; ++i)
+              tma_load_4d(a_dst + i * 8192, &tmA, &full[stage], m0 + 64 * i, kb * GEMM_BK, bi, bo);
+          }
+          if (!B_MN) {
+            tma_load_4d(b_dst, &tmB, &full[stage], kb * GEMM_BK, n0, bi, bo);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_4d(b_dst + i * 8192, &tmB, &full[stage], n0 + 64 * i, kb * GEMM_BK, bi, bo);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, 0, 0);
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -127,11 +151,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint64_t a_desc = umma_desc_kmajor(smem_u32(sA + stage * Cfg::A_BYTES));
-          const uint64_t b_desc = umma_desc_kmajor(smem_u32(sB + stage * Cfg::B_BYTES));
+          const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES), b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
+          const uint64_t a_desc = A_MN ? umma_desc_mnmajor(a_addr, 8192) : umma_desc_kmajor(a_addr);
+          const uint64_t b_desc = B_MN ? umma_desc_mnmajor(b_addr, 8192) : umma_desc_kmajor(b_addr);
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k)  // +32 B per K=16 step inside the 128 B swizzle row
-            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < GEMM_BK / 16; ++k)  // K-major: +32 B inside the 128 B swizzle row; MN-major: +16 k-rows = 2 KB
+            umma_bf16(d_tmem, a_desc + (A_MN ? 128 : 2) * k, b_desc + (B_MN ? 128 : 2) * k, idesc, (kb | k) != 0);
           umma_commit(&empty[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -149,8 +174,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m_blk, n_blk;
-      gemm_tile_coords(tile, p.m_tiles, p.n_tiles, m_blk, n_blk);
+      const int batch = tile / tiles_per_batch;
+      gemm_tile_coords(tile - batch * tiles_per_batch, p.m_tiles, p.n_tiles, m_blk, n_blk);
       const int m0 = m_blk * GEMM_BM, n0 = n_blk * BN;
+      const long long c_off = (batch / p.inner) * p.c_outer + (batch % p.inner) * p.c_inner;
       float* bs = bias_s + acc * BN;
       float* as = addv_s + acc * BN;
       for (int j = et; j < BN; j += 32 * GEMM_EPI_WARPS) {
@@ -205,7 +232,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 32; ++j) v[j] += as[c * 32 + j];
           }
           if (p.out_f32) {
-            float* cp = static_cast<float*>(p.C) + row * p.ldc + nc;
+            float* cp = static_cast<float*>(p.C) + c_off + row * p.ldc + nc;
+            if (p.accumulate) {
+              for (int j = 0; j < 32; ++j)
+                if (nc + j < p.N) v[j] += cp[j];
+            }
             if (full_chunk) {
 #pragma unroll
               for (int g = 0; g < 8; ++g)
@@ -215,7 +246,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (nc + j < p.N) cp[j] = v[j];
             }
           } else {
-            __nv_bfloat16* cp = static_cast<__nv_bfloat16*>(p.C) + row * p.ldc + nc;
+            __nv_bfloat16* cp = static_cast<__nv_bfloat16*>(p.C) + c_off + row * p.ldc + nc;
+            if (p.accumulate) {
+              for (int j = 0; j < 32; ++j)
+                if (nc + j < p.N) v[j] += __bfloat162float(cp[j]);
+            }
             if (full_chunk) {
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
@@ -247,22 +282,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-template <int BN>
+template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmTcParams p, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    MAVLM_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MAVLM_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::SMEM_BYTES));
     configured = true;
   }
   p.m_tiles = ceil_div(p.M, GEMM_BM);
   p.n_tiles = ceil_div(p.N, BN);
-  const int tiles = p.m_tiles * p.n_tiles;
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+  if (p.batches < 1) p.batches = 1;
+  if (p.inner < 1) p.inner = 1;
+  const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles * p.batches;
+  const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
+  gemm_tc_kernel<BN, A_MN, B_MN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
   MAVLM_LAUNCH_OK();
   return MAVLM_OK;
+}
+
+template <bool A_MN, bool B_MN>
+static int dispatch_bn(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcParams& p, cudaStream_t st) {
+  switch (bn) {
+    case 256: return launch_gemm_tc<256, A_MN, B_MN>(tmA, tmB, p, st);
+    case 192: return launch_gemm_tc<192, A_MN, B_MN>(tmA, tmB, p, st);
+    case 128: return launch_gemm_tc<128, A_MN, B_MN>(tmA, tmB, p, st);
+    default:  return launch_gemm_tc<64, A_MN, B_MN>(tmA, tmB, p, st);
+  }
 }
 
 // Pick the N tile: minimise (waves x tile width / tile efficiency); wide tiles re-use A better
@@ -288,44 +335,74 @@ int gemm_tc_pick_bn(int M, int N) {
   return best;
 }
 
+// Operand description for the general entry: `rows` x `cols` is the STORED 2-D shape of one problem's operand
+// (K-major operand: rows = M or N, cols = K; MN-major operand: rows = K, cols = M or N).
+static int make_operand_map(CUtensorMap* tm, const void* base, long long ld, int rows, int cols, bool mn_major,
+                            int tile_rows, int inner, int outer, long long s_inner, long long s_outer) {
+  const uint64_t dims[4] = {static_cast<uint64_t>(cols), static_cast<uint64_t>(rows), static_cast<uint64_t>(inner),
+                            static_cast<uint64_t>(outer)};
+  // unused batch dims keep a valid (16-byte multiple) stride
+  const uint64_t si = inner > 1 ? static_cast<uint64_t>(s_inner) * 2 : static_cast<uint64_t>(ld) * 2;
+  const uint64_t so = outer > 1 ? static_cast<uint64_t>(s_outer) * 2 : static_cast<uint64_t>(ld) * 2;
+  const uint64_t str[3] = {static_cast<uint64_t>(ld) * 2, si, so};
+  const uint32_t box[4] = {64, mn_major ? 64u : static_cast<uint32_t>(tile_rows), 1, 1};
+  return make_tmap_bf16(tm, base, 4, dims, str, box);
+}
+
+// General tensor-core GEMM:  C[M,N] (+)= op(A) op(B) (+ epilogue), batched over outer x inner problems.
+int gemm_tc_general(const __nv_bfloat16* A, long long lda, bool a_mn, const __nv_bfloat16* B, long long ldb, bool b_mn,
+                    GemmTcParams p, int outer, int inner, const long long* s6, cudaStream_t st) {
+  if (p.M == 0 || p.N == 0) return MAVLM_OK;
+  MAVLM_REQUIRE(p.K > 0 && lda % 8 == 0 && ldb % 8 == 0, MAVLM_E_INVALID,
+                "bf16 gemm: lda (%lld) and ldb (%lld) must be multiples of 8", lda, ldb);
+  MAVLM_REQUIRE((a_mn ? p.M : p.K) % 8 == 0 && (b_mn ? p.N : p.K) % 8 == 0, MAVLM_E_INVALID,
+                "bf16 gemm: the contiguous extent of each operand must be a multiple of 8 (M=%d N=%d K=%d)", p.M, p.N,
+                p.K);
+  const int cvec = p.out_f32 ? 4 : 8;
+  MAVLM_REQUIRE(p.ldc % cvec == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0, MAVLM_E_INVALID,
+                "bf16 gemm: C must be 16-byte aligned with ldc %% %d == 0", cvec);
+  if (p.resid != nullptr)
+    MAVLM_REQUIRE(p.ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(p.resid) & 15) == 0, MAVLM_E_INVALID,
+                  "bf16 gemm: resid must be 16-byte aligned with ldr %% 8 == 0");
+  if (outer < 1) outer = 1;
+  if (inner < 1) inner = 1;
+  const long long z6[6] = {0, 0, 0, 0, 0, 0};
+  if (s6 == nullptr) s6 = z6;
+  p.batches = outer * inner;
+  p.inner = inner;
+  p.c_outer = s6[4];
+  p.c_inner = s6[5];
+  const int bn = gemm_tc_pick_bn(p.M * p.batches, p.N);
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = make_operand_map(&tmA, A, lda, a_mn ? p.K : p.M, a_mn ? p.M : p.K, a_mn, GEMM_BM, inner, outer, s6[1],
+                             s6[0])))
+    return rc;
+  if ((rc = make_operand_map(&tmB, B, ldb, b_mn ? p.K : p.N, b_mn ? p.N : p.K, b_mn, bn, inner, outer, s6[3], s6[2])))
+    return rc;
+  if (a_mn) return b_mn ? dispatch_bn<true, true>(bn, tmA, tmB, p, st) : dispatch_bn<true, false>(bn, tmA, tmB, p, st);
+  return b_mn ? dispatch_bn<false, true>(bn, tmA, tmB, p, st) : dispatch_bn<false, false>(bn, tmA, tmB, p, st);
+}
+
 int gemm_bf16_tc(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw,
                  const __nv_bfloat16* bias, const __nv_bfloat16* resid, long long ldr, const __nv_bfloat16* addvec,
                  void* C, long long ldc, int M, int N, int K, int act, int out_f32, cudaStream_t st) {
-  if (M == 0 || N == 0) return MAVLM_OK;
-  MAVLM_REQUIRE(K > 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, MAVLM_E_INVALID,
-                "bf16 gemm: K (%d), lda (%lld), ldw (%lld) must be multiples of 8", K, lda, ldw);
-  const int cvec = out_f32 ? 4 : 8;
-  MAVLM_REQUIRE(ldc % cvec == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0, MAVLM_E_INVALID,
-                "bf16 gemm: C must be 16-byte aligned with ldc %% %d == 0", cvec);
-  if (resid != nullptr)
-    MAVLM_REQUIRE(ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(resid) & 15) == 0, MAVLM_E_INVALID,
-                  "bf16 gemm: resid must be 16-byte aligned with ldr %% 8 == 0");
-  const int bn = gemm_tc_pick_bn(M, N);
-  CUtensorMap tmA, tmB;
-  {
-    const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
-    const uint64_t str[1] = {static_cast<uint64_t>(lda) * 2};
-    const uint32_t box[2] = {GEMM_BK, GEMM_BM};
-    int rc = make_tmap_bf16(&tmA, A, 2, dims, str, box);
-    if (rc) return rc;
-  }
-  {
-    const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
-    const uint64_t str[1] = {static_cast<uint64_t>(ldw) * 2};
-    const uint32_t box[2] = {GEMM_BK, static_cast<uint32_t>(bn)};
-    int rc = make_tmap_bf16(&tmB, W, 2, dims, str, box);
-    if (rc) return rc;
-  }
+  MAVLM_REQUIRE(K > 0 && K % 8 == 0, MAVLM_E_INVALID, "bf16 gemm: K (%d) must be a multiple of 8", K);
   GemmTcParams p{};
   p.M = M; p.N = N; p.K = K;
   p.bias = bias; p.resid = resid; p.ldr = ldr; p.addvec = addvec;
   p.C = C; p.ldc = ldc; p.act = act; p.out_f32 = out_f32;
-  switch (bn) {
-    case 256: return launch_gemm_tc<256>(tmA, tmB, p, st);
-    case 192: return launch_gemm_tc<192>(tmA, tmB, p, st);
-    case 128: return launch_gemm_tc<128>(tmA, tmB, p, st);
-    default:  return launch_gemm_tc<64>(tmA, tmB, p, st);
-  }
+  return gemm_tc_general(A, lda, false, W, ldw, false, p, 1, 1, nullptr, st);
+}
+
+// Backward-pass entry (mavlm_gemm_ex, bf16): trans_a = 1 -> A stored [K,M]; trans_b = 0 -> B stored [K,N].
+int gemm_ex_bf16(const __nv_bfloat16* A, long long lda, int trans_a, const __nv_bfloat16* B, long long ldb, int trans_b,
+                 void* C, long long ldc, int M, int N, int K, int accumulate, int out_f32, int outer, int inner,
+                 const long long* s6, cudaStream_t st) {
+  GemmTcParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.C = C; p.ldc = ldc; p.act = MAVLM_ACT_NONE; p.out_f32 = out_f32; p.accumulate = accumulate;
+  return gemm_tc_general(A, lda, trans_a != 0, B, ldb, trans_b == 0, p, outer, inner, s6, st);
 }
 
 void gemm_tc_force_bn(int bn) { g_force_bn = bn; }

@@ -146,3 +146,82 @@ def test_single_chunk_leaves_evolution_attention_without_gradient():
     assert all(p.grad is None for p in rmt.memory_update_attention.parameters())
     assert all(p.grad is not None for p in rmt.layers.parameters())
     assert rmt.initial_memory.grad is not None and rmt.memory_pos_embed.grad is not None
+
+
+# ------------------------------------------------------------------------------------------------
+# bf16 tensor-core tier
+# ------------------------------------------------------------------------------------------------
+def _nerr(a, b):
+    a, b = a.detach().double(), b.detach().double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def test_gemm_ex_bf16_all_operand_layouts():
+    """tcgen05 GEMM with K-major / MN-major operands (dgrad / wgrad / attention-backward layouts), batched."""
+    from mavlm_b200 import autograd as ag
+    torch.manual_seed(0)
+    m, n, k = 328, 200, 264
+    a = torch.randn(m, k, device=DEV).bfloat16()
+    b = (torch.randn(n, k, device=DEV) / 16).bfloat16()
+    ref = a.double() @ b.double().T
+    for ta in (False, True):
+        for tb in (True, False):
+            aa = a.t().contiguous() if ta else a            # stored [K, M] when trans_a
+            bb = b if tb else b.t().contiguous()            # stored [N, K] when trans_b, else [K, N]
+            out = ag.gemm_ex(aa, ta, bb, tb, m, n, k)
+            assert _nerr(out, ref) < 1e-2, (ta, tb)
+            o32 = ag.gemm_ex(aa, ta, bb, tb, m, n, k, out_dtype=torch.float32)
+            assert _nerr(o32, ref) < 1e-5, (ta, tb)
+            acc = o32.clone()
+            ag.gemm_ex(aa, ta, bb, tb, m, n, k, out=acc, accumulate=True)
+            assert _nerr(acc, 2 * ref) < 1e-5, (ta, tb)
+
+
+def test_op_level_gradients_bf16():
+    torch.manual_seed(0)
+    x = torch.randn(1568, 896, device=DEV).bfloat16().requires_grad_()
+    w = (torch.randn(3584, 896, device=DEV) / 30).bfloat16().requires_grad_()
+    b = torch.randn(3584, device=DEV).bfloat16().requires_grad_()
+    y = ops.linear(x, w, b, act=2)
+    ref = torch.relu(x.float() @ w.float().T + b.float())
+    go = torch.randn_like(ref).bfloat16()
+    got = torch.autograd.grad(y, [x, w, b], go)
+    exp = torch.autograd.grad(ref, [x, w, b], go.float())
+    for a_, e_ in zip(got, exp):
+        assert a_.dtype == torch.bfloat16 and _nerr(a_, e_) < 2e-2
+    for dh in (128, 448):
+        h = 8
+        q = torch.randn(1, 1568, h * dh, device=DEV).bfloat16().requires_grad_()
+        kv = torch.randn(1, 784, 2 * h * dh, device=DEV).bfloat16().requires_grad_()
+        o, _, _ = ops.xattn(q, kv[..., :h * dh], kv[..., h * dh:], h)
+        qh = q.float().view(1, -1, h, dh).transpose(1, 2)
+        kh = kv.float()[..., :h * dh].reshape(1, -1, h, dh).transpose(1, 2)
+        vh = kv.float()[..., h * dh:].reshape(1, -1, h, dh).transpose(1, 2)
+        ref = ((qh @ kh.transpose(-1, -2) / dh ** 0.5).softmax(-1) @ vh).transpose(1, 2).reshape(1, -1, h * dh)
+        go = torch.randn_like(ref).bfloat16()
+        got = torch.autograd.grad(o, [q, kv], go)
+        exp = torch.autograd.grad(ref, [q, kv], go.float())
+        for a_, e_ in zip(got, exp):
+            assert _nerr(a_, e_) < 3e-2, dh
+
+
+def test_bf16_training_step_matches_fp32_tier():
+    """OV-0.5B dims, 2 chunks (BPTT + evolution), loss = mean(sequence^2): bf16 tensor-core gradients against the
+    fp32 tier's (which is pinned to the reference's autograd above)."""
+    grads = {}
+    for dt in (torch.float32, torch.bfloat16):
+        pipe, _ = synthetic.build_pipeline(896, 1152, dtype=dt, chunk_size=4, device=DEV)
+        g = torch.Generator().manual_seed(5)
+        z = torch.randn(1, 8, 196, 896, generator=g).bfloat16().to(DEV).to(dt)
+        out = pipe.memory_forward_train(z)
+        (out["sequence"].float() ** 2).mean().backward()
+        grads[dt] = {n: p.grad.detach().float().clone() for n, p in pipe.named_parameters() if p.grad is not None}
+    assert set(grads[torch.float32]) == set(grads[torch.bfloat16])
+    gmax = max(float(v.abs().max()) for v in grads[torch.float32].values())
+    worst = 0.0
+    for n, g32 in grads[torch.float32].items():
+        g16 = grads[torch.bfloat16][n]
+        e = float((g16 - g32).abs().max() / max(float(g32.abs().max()), 1e-3 * gmax))
+        worst = max(worst, e)
+        assert e < 0.1, (n, e)
+    print("worst bf16-vs-fp32 gradient error", worst)
