@@ -161,14 +161,17 @@ class Attention(nn.Module):
         scale = 1.0 / math.sqrt(self.attention_head_size)
         q = ops.linear(x, p["wq"], p["bq"])
         fp32 = q.dtype == torch.float32
-        ctx, _, cs = ops.xattn(q, kv_projected[..., :hd], kv_projected[..., hd:], h, head_dim=dhp, scale=scale,
-                               want_col_scores=col_scores and fp32)
-        if col_scores and not fp32:
-            # frame scores (MemoryController.py:135) need normalised probabilities, which the fused bf16 kernel
-            # never forms: diagnostics-only second pass through the fp32 tier on the same q / k.
-            qf = ops.cast(q, torch.float32)
-            kf = ops.cast(kv_projected[..., :hd].contiguous(), torch.float32)
-            _, _, cs = ops.xattn(qf, kf, kf, h, head_dim=dhp, scale=scale, want_col_scores=True)
+        k_, v_ = kv_projected[..., :hd], kv_projected[..., hd:]
+        grad = torch.is_grad_enabled() and (q.requires_grad or kv_projected.requires_grad)
+        fused_scores = col_scores and fp32 and not grad
+        ctx, _, cs = ops.xattn(q, k_, v_, h, head_dim=dhp, scale=scale, want_col_scores=fused_scores)
+        if col_scores and not fused_scores:
+            # frame scores (MemoryController.py:135, detached at :157) need normalised probabilities, which neither
+            # the fused bf16 kernel nor the autograd path forms: diagnostics-only extra pass through the fp32 tier.
+            with torch.no_grad():
+                qf = ops.cast(q.detach(), torch.float32)
+                kf = ops.cast(k_.detach().contiguous(), torch.float32)
+                _, _, cs = ops.xattn(qf, kf, kf, h, head_dim=dhp, scale=scale, want_col_scores=True)
         self.last_col_scores = cs
         out = self.residual(ctx, x, weight=p["wo"])
         return out.reshape(hidden_states.shape), None
