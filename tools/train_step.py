@@ -1,0 +1,79 @@
+#!/usr/bin/env python
+"""BASELINE config[3]: OV-7B finetune_short-style forward+backward of the memory module and fuser, bf16,
+batch of videos x 32 frames (one chunk: memory_update_attention gets no gradient) and a
+64-frame case (2 chunks: evolution attention trains too).  Pooled-token input (frame features are detached),
+loss = mean-square of the assembled sequence.  Reports ms per training step (fwd+bwd), frames/s and the
+algorithmic TFLOP/s (backward counted as 2x forward minus the frame-side dgrad that is never needed).
+
+    python tools/train_step.py [--dims 7b|0.5b] [--batch 8] [--frames 32 64] -> gpurun_out/train_step.json
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from mavlm_b200 import synthetic  # noqa: E402
+
+
+def fwd_gflop(frames, chunk, d, lq=1568, p=196, depth=2, cap=10):
+    n_chunks = -(-frames // chunk)
+    fl = 0.0
+    for t in range(n_chunks):
+        c = min(chunk, frames - t * chunk)
+        fl += depth * (4.0 * lq * d * d + 4.0 * c * p * d * d + 4.0 * lq * c * p * d + 16.0 * lq * d * d)
+        if t > 0:
+            fl += 8.0 * lq * d * d + 4.0 * lq * (min(t, cap) * lq) * d
+    fl += 16.0 * min(n_chunks, cap) * lq * d * d
+    return fl / 1e9
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--dims", default="7b")
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--frames", type=int, nargs="+", default=[32, 64])
+    ap.add_argument("--iters", type=int, default=2)
+    args = ap.parse_args()
+    d = synthetic.OV_DIMS[args.dims]
+    pipe, _ = synthetic.build_pipeline(d, 1152, dtype=torch.bfloat16, chunk_size=32, device="cuda:0")
+    out = []
+    for frames in args.frames:
+        g = torch.Generator(device="cuda:0").manual_seed(1234)
+        z = torch.randn(args.batch, frames, 196, d, device="cuda:0", generator=g).bfloat16()
+
+        def step():
+            for p_ in pipe.parameters():
+                p_.grad = None
+            res = pipe.memory_forward_train(z)
+            loss = (res["sequence"].float() ** 2).mean()
+            loss.backward()
+            return float(loss)
+
+        step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.iters):
+            loss = step()
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) / args.iters * 1e3
+        gf = 3.0 * args.batch * fwd_gflop(frames, 32, d)
+        n_grads = sum(p_.grad is not None for p_ in pipe.parameters())
+        rec = {"dims": args.dims, "batch": args.batch, "frames": frames, "ms_per_step": ms,
+               "frames_per_s": args.batch * frames / ms * 1e3, "algorithmic_tflops_fwd_bwd": gf / ms,
+               "params_with_grad": n_grads, "loss": loss,
+               "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+        out.append(rec)
+        print(json.dumps(rec), flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "train_step.json"), "w") as fh:
+        json.dump(out, fh, indent=1)
+
+
+if __name__ == "__main__":
+    main()
