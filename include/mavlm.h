@@ -103,6 +103,12 @@ MAVLM_API int mavlm_assemble_fwd(void* seq, const void* mem, int64_t n_mem_rows,
                        const int64_t* prompt_mem_ids, int n_prompt_mem, const int64_t* prompt_frm_ids,
                        int n_prompt_frm, int dim, int drop_frames, int dtype, void* stream);
 
+/* ---- text / vision splice + padding (llava_arch.py:745-878), the consumer of the assembled sequence: every output
+ * row copies one source row.  row_src (device int64 [n_rows]): >= 0 -> embed_table[row_src] (embed_tokens of a text
+ * token), -1 -> zeros (padding), <= -2 -> feats[-(row_src + 2)] (a row of the video token sequence). */
+MAVLM_API int mavlm_gather_rows_fwd(void* out, int64_t ld_out, const void* embed_table, const void* feats,
+                                    const int64_t* row_src, int64_t n_rows, int dim, int dtype, void* stream);
+
 /* ======================= backward pass (training: BPTT through the memory, fuser) =======================
  * The reference trains this path with PyTorch autograd (train.py:1694-1728 unfreezes recurrent_memory_transformer,
  * memory_fuser, token_type_embedding; frame features are detached, llava_arch.py:302).  These entry points are

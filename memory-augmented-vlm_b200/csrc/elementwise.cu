@@ -307,6 +307,29 @@ __global__ void __launch_bounds__(256) cast_kernel(const TI* __restrict__ x, TO*
   }
 }
 
+// Text / vision splice (llava_arch.py:745-878): every output row copies one source row.
+// src >= 0: embed_table[src];  src == -1: zero (padding);  src <= -2: feats[-(src + 2)].
+template <typename T>
+__global__ void __launch_bounds__(128) gather_rows_kernel(T* __restrict__ out, long long ld_out,
+                                                          const T* __restrict__ table, const T* __restrict__ feats,
+                                                          const int64_t* __restrict__ src, int dim) {
+  constexpr int V = Vec<T>::N;
+  const long long r = blockIdx.x;
+  const int64_t sidx = src[r];
+  const T* sp = sidx >= 0 ? table + sidx * dim : (sidx == -1 ? nullptr : feats + (-(sidx + 2)) * dim);
+  T* dst = out + r * ld_out;
+  for (int i = threadIdx.x * V; i < dim; i += blockDim.x * V) {
+    float v[V];
+    if (sp != nullptr) {
+      Vec<T>::load(sp + i, v);
+    } else {
+#pragma unroll
+      for (int k = 0; k < V; ++k) v[k] = 0.f;
+    }
+    Vec<T>::store(dst + i, v);
+  }
+}
+
 static int grid_for(long long total_threads, int block) {
   long long b = (total_threads + block - 1) / block;
   const long long cap = static_cast<long long>(sm_count()) * 32;  // grid-stride beyond 32 CTAs/SM
@@ -397,6 +420,26 @@ int mavlm_add_pe_fwd(const void* x, void* y, const float* pe_table, const int64_
     add_pe_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x),
                                                        static_cast<__nv_bfloat16*>(y), pe_table, frame_idx, frames,
                                                        tokens, dim);
+  MAVLM_LAUNCH_OK();
+  return MAVLM_OK;
+}
+
+int mavlm_gather_rows_fwd(void* out, int64_t ld_out, const void* embed_table, const void* feats, const int64_t* row_src,
+                          int64_t n_rows, int dim, int dtype, void* stream) {
+  MAVLM_REQUIRE(dtype == MAVLM_F32 || dtype == MAVLM_BF16, MAVLM_E_INVALID, "gather_rows: bad dtype %d", dtype);
+  const int vec = dtype == MAVLM_F32 ? 4 : 8;
+  MAVLM_REQUIRE(dim > 0 && dim % vec == 0 && ld_out % vec == 0, MAVLM_E_INVALID,
+                "gather_rows: dim %d / ld_out must be multiples of %d", dim, vec);
+  if (n_rows == 0) return MAVLM_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == MAVLM_F32)
+    gather_rows_kernel<float><<<static_cast<unsigned>(n_rows), 128, 0, st>>>(
+        static_cast<float*>(out), ld_out, static_cast<const float*>(embed_table), static_cast<const float*>(feats),
+        row_src, dim);
+  else
+    gather_rows_kernel<__nv_bfloat16><<<static_cast<unsigned>(n_rows), 128, 0, st>>>(
+        static_cast<__nv_bfloat16*>(out), ld_out, static_cast<const __nv_bfloat16*>(embed_table),
+        static_cast<const __nv_bfloat16*>(feats), row_src, dim);
   MAVLM_LAUNCH_OK();
   return MAVLM_OK;
 }

@@ -325,6 +325,37 @@ def gen_pool_and_full(ARCH, PB):
     full.update({"w::" + k: v for k, v in w.items()})
     np.savez(os.path.join(OUT, "full_path.npz"), **full)
 
+    # ---- text / vision splice variants (llava_arch.py:745-878) on the same video: labels / mask / position ids,
+    # truncation, left and right padding, a batch of two with the batch-1 IndexError fallback (:799-802)
+    sp = {}
+    full_seq = emb[0][2:-2]                                   # the video token sequence itself
+    sp["video_sequence"] = full_seq.numpy()
+    # (the fork is batch-1 for videos: llava_arch.py:436, :561, :723-731 -- so two single-sample calls)
+    ids2 = torch.tensor([[5, ARCH.IMAGE_TOKEN_INDEX, 9, 11, 0], [7, ARCH.IMAGE_TOKEN_INDEX, 8, 0, 0]])
+    mask2 = torch.tensor([[1, 1, 1, 1, 0], [1, 1, 1, 0, 0]])
+    lab2 = torch.tensor([[1, -100, 2, 3, -100], [5, -100, 6, -100, -100]])
+    pos2 = torch.arange(5)[None].expand(2, 5).contiguous()
+    for tag, side, maxlen, row in (("right", "right", 32768, 0), ("left_trunc", "left", 9000, 1)):
+        h.config.tokenizer_padding_side = side
+        h.config.tokenizer_model_max_length = maxlen
+        with torch.no_grad():
+            r = h.prepare_inputs_labels_for_multimodal(ids2[row:row + 1], pos2[row:row + 1], mask2[row:row + 1], None,
+                                                       lab2[row:row + 1], [video], modalities=["video"])
+        _, p_out, m_out, _, e_out, l_out = r
+        sp[f"{tag}.position_ids"] = p_out.numpy()
+        sp[f"{tag}.attention_mask"] = m_out.numpy()
+        sp[f"{tag}.labels"] = l_out.numpy()
+        sp[f"{tag}.shape"] = np.array(e_out.shape)
+        sp[f"{tag}.rows_head"] = e_out[:, :12].numpy()
+        sp[f"{tag}.rows_tail"] = e_out[:, -12:].numpy()
+        sp[f"{tag}.rows_stride"] = e_out[:, ::97].numpy()
+        sp[f"{tag}.colsum"] = e_out.double().sum(dim=1).numpy()
+    h.config.tokenizer_padding_side = "right"
+    h.config.tokenizer_model_max_length = 32768
+    sp["input_ids"], sp["mask"], sp["labels"], sp["pos"] = ids2.numpy(), mask2.numpy(), lab2.numpy(), pos2.numpy()
+    sp["embed_table"] = w["_emb.weight"]
+    np.savez(os.path.join(OUT, "splice.npz"), **sp)
+
     # short video (< 32 frames): 5 frames, single ragged chunk, 5 fine frames
     torch.manual_seed(34)
     video5 = torch.randn(5, 4, 27, 27)
