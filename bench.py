@@ -287,34 +287,81 @@ def run_ours(args):
     def step_eager():
         pipe(x_dev, idx, return_states=False)
 
-    # ---- instrumented pass: per-launch CUDA-event timing of the dominant kernel (tcgen05 GEMM) ----
+    # ---- instrumented pass: per-launch CUDA-event timing of every op, INSIDE a CUDA graph of the step ----
+    # The step is captured a second time with an external timing event recorded before and after every library
+    # call (event-record nodes on the capture stream), so the intervals are device times of back-to-back
+    # kernels exactly as the timed graph replays run them: no host launch gaps, no allocator stalls.
     recs = []
-    orig_linear = ops.linear
+    other = {}
+    orig = {name: getattr(ops, name) for name in ("linear", "xattn", "layernorm", "pool_pe", "add_pe", "add_rows",
+                                                  "assemble")}
+
+    def _events():
+        return (torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True))
 
     def timed_linear(x, w, b=None, **kw):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if not torch.cuda.is_current_stream_capturing():
+            return orig["linear"](x, w, b, **kw)
+        e0, e1 = _events()
         e0.record()
-        y = orig_linear(x, w, b, **kw)
+        y = orig["linear"](x, w, b, **kw)
         e1.record()
         recs.append((x.numel() // x.shape[-1], w.shape[0], w.shape[1], e0, e1))
         return y
 
+    def timed_other(name):
+        def fn(*a, **kw):
+            if not torch.cuda.is_current_stream_capturing():
+                return orig[name](*a, **kw)
+            e0, e1 = _events()
+            e0.record()
+            y = orig[name](*a, **kw)
+            e1.record()
+            other.setdefault(name, []).append((e0, e1))
+            return y
+        return fn
+
     ops.linear = timed_linear
+    for name in orig:
+        if name != "linear":
+            setattr(ops, name, timed_other(name))
     try:
-        prof_steps = min(steps, 10)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
+        prof_graph = M.GraphedPipeline(pipe, 1, FRAMES)
+    finally:
+        for name, fn in orig.items():
+            setattr(ops, name, fn)
+    prof_graph(x_dev, idx)
+    torch.cuda.synchronize()
+    prof_steps = min(steps, 10)
+    gemm_t = [0.0] * len(recs)
+    other_t = {name: 0.0 for name in other}
+    prof_ms = 0.0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(prof_steps):
         e0.record()
-        for _ in range(prof_steps):
-            step_eager()
+        prof_graph(None, None)
         e1.record()
         torch.cuda.synchronize()
-        prof_ms = e0.elapsed_time(e1)
-    finally:
-        ops.linear = orig_linear
-    gemm_ms = sum(a.elapsed_time(b) for (_, _, _, a, b) in recs)
-    gemm_fl = sum(2.0 * m * n * k for (m, n, k, _, _) in recs)
-    n_gemm = len(recs)
+        prof_ms += e0.elapsed_time(e1)
+        for i, (_, _, _, a, b) in enumerate(recs):
+            gemm_t[i] += a.elapsed_time(b)
+        for name, evs in other.items():
+            other_t[name] += sum(a.elapsed_time(b) for (a, b) in evs)
+    breakdown = {"gemm": sum(gemm_t) / prof_steps}
+    for name in other:
+        breakdown[name] = other_t[name] / prof_steps
+    breakdown = {k: {"ms_per_step": v, "share": v * prof_steps / prof_ms} for k, v in breakdown.items()}
+    by_shape = {}
+    for i, (m, n, k, _, _) in enumerate(recs):
+        t = by_shape.setdefault((m, n, k), [0, 0.0])
+        t[0] += 1
+        t[1] += gemm_t[i] / prof_steps
+    gemm_shapes = {f"{m}x{n}x{k}": {"launches_per_step": c, "us": 1e3 * ms / c,
+                                    "tflops": 2.0 * m * n * k / (ms / c * 1e-3) / 1e12}
+                   for (m, n, k), (c, ms) in by_shape.items()}
+    gemm_ms = sum(gemm_t)
+    gemm_fl = sum(2.0 * m * n * k for (m, n, k, _, _) in recs) * prof_steps
+    n_gemm = len(recs) * prof_steps
     peaks = measured_peaks()
     achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     traffic = None
@@ -360,6 +407,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": out_host.numel() * out_host.element_size(), "ms_per_step": ms_e2e / steps},
             "gpu_launches": int(launches), "launch_mode": "one CUDA graph replay per step (kernels counted from an "
             "eager step)", "roofline": roofline, "cpu_baseline": cpu,
+            "kernel_breakdown": breakdown, "gemm_shapes": gemm_shapes,
             "algorithmic_gflop_per_step": gflop_step,
             "path_tflops": gflop_step * 1e9 / (ms_total / steps * 1e-3) / 1e12,
             "path_frac_of_peak": gflop_step * 1e9 / (ms_total / steps * 1e-3) / 1e12 / peaks["tflops"]}

@@ -57,6 +57,7 @@ PROTOTYPES = {
                                 c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int,
                                 c_int, c_int, c_float, c_int, c_void_p, c_size_t, c_void_p]),
     "mavlm_debug_force_gemm_bn": (c_int, [c_int]),
+    "mavlm_debug_set_flags": (c_int, [c_int]),
     "mavlm_debug_force_attn_groups": (c_int, [c_int]),
 }
 

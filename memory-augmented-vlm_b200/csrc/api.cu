@@ -9,6 +9,7 @@ int gemm_bf16_tc(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, 
                  const __nv_bfloat16* bias, const __nv_bfloat16* resid, long long ldr, const __nv_bfloat16* addvec,
                  void* C, long long ldc, int M, int N, int K, int act, int out_f32, cudaStream_t st);
 void gemm_tc_force_bn(int bn);
+void gemm_tc_set_debug(int flags);
 int xattn_fp32(const float* Q, long long ldq, long long qb, const float* K, long long ldk, long long kb, const float* V,
                long long ldv, long long vb, float* O, long long ldo, long long ob, float* lse, float* col_scores,
                int batch, int heads, int lq, int lk, int dh, float scale, void* ws, size_t ws_bytes, cudaStream_t st);
@@ -71,10 +72,19 @@ int mavlm_xattn_fwd(const void* Q, int64_t ldq, int64_t q_batch_stride, const vo
                        o_batch_stride, lse, batch, heads, lq, lk, head_dim, scale, workspace, workspace_bytes, st);
 }
 
-/* development knob (not part of the reference-facing surface): force the GEMM N tile (0 = heuristic) */
+/* development knob (not part of the reference-facing surface): force the GEMM tile (0 = heuristic).
+   -1 = heuristic over single-CTA tiles only; 64/128/192/256 = single-CTA 128 x BN tiles; 1128/1192/1256 = CTA-pair 256 x BN tiles (K-major operands) */
 MAVLM_API int mavlm_debug_force_gemm_bn(int bn) {
-  MAVLM_REQUIRE(bn == 0 || bn == 64 || bn == 128 || bn == 192 || bn == 256, MAVLM_E_INVALID, "bad BN %d", bn);
+  MAVLM_REQUIRE(bn == -1 || bn == 0 || bn == 64 || bn == 128 || bn == 192 || bn == 256 || bn == 1128 || bn == 1192 || bn == 1256,
+                MAVLM_E_INVALID, "bad BN %d", bn);
   gemm_tc_force_bn(bn);
+  return MAVLM_OK;
+}
+
+/* development knob: kernel experiment flags (bit 0: GEMM epilogue skips its global stores, bit 1: skips the
+   activation) -- for bottleneck attribution on the GPU only; results are garbage while a flag is set */
+MAVLM_API int mavlm_debug_set_flags(int flags) {
+  gemm_tc_set_debug(flags);
   return MAVLM_OK;
 }
 

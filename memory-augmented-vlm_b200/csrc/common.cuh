@@ -45,6 +45,10 @@ int sm_count();  // cached multiProcessorCount of the current device
 // (strides in bytes for dims 1..rank-1), 128B swizzle. Returns 0 / negative error.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box);
+// General form: elem_bytes 2 (bf16) or 4 (fp32); swizzle_bytes 128 or 64 (the box's inner extent in bytes
+// must not exceed it).
+int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int swizzle_bytes, int rank, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box);
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
@@ -139,6 +143,21 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// TMA store: shared memory box -> global (bulk async group of the issuing thread); out-of-range rows /
+// columns of the box are clipped by the hardware.
+__device__ __forceinline__ void tma_store_2d(const void* smem_src, const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {  // at most N groups still reading their shared-memory source
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---- tcgen05 / TMEM ----
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {  // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
@@ -167,6 +186,78 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+
+// ---- CTA pairs (cluster of 2, tcgen05 cta_group::2) ----
+// A pair = the two CTAs of a (2,1,1) cluster on the two SMs of a TPC.  One thread of the rank-0 CTA
+// ("leader") issues M=256 MMAs that read A/B halves from BOTH CTAs' shared memory (same CTA-relative
+// offsets) and write 128 accumulator rows into each CTA's own TMEM.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {  // every thread of every CTA in the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+// Possibly remote arrive.  Default (.release.cta) semantics on purpose: what the waiter consumes is TMEM /
+// shared-memory state ordered by tcgen05 fences, not this thread's global stores -- .release.cluster compiles
+// to MEMBAR.ALL.GPU + ERRBAR, i.e. a wait for every outstanding global store of the epilogue (12 % of the
+// samples of the pair GEMM).
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load issued by either CTA of a pair; the transaction bytes are credited to the mbarrier at
+// `bar_cluster_addr` (the leader's), the data lands in the issuing CTA's own shared memory.
+__device__ __forceinline__ void tma_load_4d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
+                                                 int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
+                                                 int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {  // warp w of BOTH CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {  // warp w of BOTH CTAs
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive (once all MMAs issued so far have completed) on the mbarrier at this CTA-relative offset in
+// every CTA of `cta_mask`.
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
 }
 
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets lane (base_lane + t).
@@ -234,6 +325,25 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// GELU(erf) for the bf16 tensor-core epilogues:  erfc(z) = 2^(-Q(z)),  Q a degree-6 polynomial through the
+// origin fitted (erfc-weighted least squares on [0, 4.2]) to -log2(erfc(z)); written in |x| = sqrt(2) z.
+// |erf error| <= 3.5e-7, GELU abs error <= 7e-7 over all x (fp32 evaluation; tools/fit_gelu.py reproduces the
+// coefficients and the bound) -- 4 orders below the bf16 output's half-ulp.  One MUFU (ex2) + 10 FMA-pipe
+// instructions per element; libdevice erff is ~30 with a branch and the K = 1152 projector GEMM's epilogue
+// (128 x 256 outputs per tile against only 18 k-blocks of MMAs) is bound by instruction issue / MUFU rate.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float ax = fminf(fabsf(x), 5.939697f);   // erfc(4.2) = 2.9e-9: erf == 1 in fp32 beyond
+  float q = fmaf(-1.975574536e-05f, ax, 6.616290625e-04f);
+  q = fmaf(q, ax, -7.758132054e-03f);
+  q = fmaf(q, ax, 5.296287755e-02f);
+  q = fmaf(q, ax, 4.590668649e-01f);
+  q = fmaf(q, ax, 1.151119014e+00f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-q * ax));
+  const float hx = 0.5f * x;
+  return fmaf(fabsf(hx), 1.0f - e, hx);          // 0.5 x (1 + sign(x) erf(|x| / sqrt 2))
+}
 #endif  // __CUDACC__
 
 }  // namespace mavlm

@@ -57,7 +57,15 @@ static EncodeTiledFn get_encode_fn() {
 
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box) {
+  return make_tmap(out, base, 2, 128, rank, dims, strides_bytes, box);
+}
+
+int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int swizzle_bytes, int rank, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
+  MAVLM_REQUIRE((elem_bytes == 2 || elem_bytes == 4) && (swizzle_bytes == 128 || swizzle_bytes == 64) &&
+                    static_cast<int>(box[0]) * elem_bytes <= swizzle_bytes,
+                MAVLM_E_INVALID, "bad TMA element size / swizzle (%d, %d, box %u)", elem_bytes, swizzle_bytes, box[0]);
   MAVLM_REQUIRE(fn != nullptr, MAVLM_E_CUDA, "cuTensorMapEncodeTiled not available from the CUDA driver");
   MAVLM_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, MAVLM_E_INVALID,
                 "TMA source pointer %p is not 16-byte aligned", base);
@@ -75,8 +83,10 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
                     static_cast<unsigned long long>(gstr[i - 1]));
     }
   }
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
-                  gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  CUresult r = fn(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                  static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstr, bdim, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MAVLM_REQUIRE(r == CUDA_SUCCESS, MAVLM_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
   return MAVLM_OK;

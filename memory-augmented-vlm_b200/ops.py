@@ -120,26 +120,34 @@ def cast(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
-              out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+              out_dtype: Optional[torch.dtype] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     if _grad_needed(x, gamma, beta):
+        if out is not None:
+            raise RuntimeError("mavlm.layernorm: out= cannot be combined with autograd")
         from . import autograd as ag
         return ag.LayerNormFn.apply(x, gamma, beta, eps, out_dtype)
-    return _layernorm_raw(x, gamma, beta, eps, out_dtype)
+    return _layernorm_raw(x, gamma, beta, eps, out_dtype, out)
 
 
 def _layernorm_raw(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
-                   out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
-    _need_cuda(x, gamma, beta)
+                   out_dtype: Optional[torch.dtype] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`out`: a contiguous tensor with x's element count (e.g. a ring-buffer slot) that receives the result."""
+    _need_cuda(x, gamma, beta, out)
     d = x.shape[-1]
     x2 = x.reshape(-1, d)
     if not x2.is_contiguous():
         x2 = x2.contiguous()
     odt = out_dtype or gamma.dtype
-    y = torch.empty(x2.shape, dtype=odt, device=x.device)
+    if out is None:
+        y = torch.empty(x2.shape, dtype=odt, device=x.device)
+    else:
+        if not out.is_contiguous() or out.numel() != x2.numel() or out.shape[-1] != d:
+            raise RuntimeError("mavlm.layernorm: out must be contiguous [..., D] with the input's element count")
+        y, odt = out, out.dtype
     st = _lib.load().mavlm_layernorm_fwd(_ptr(x2), _ptr(gamma), _ptr(beta), _ptr(y), x2.shape[0], d, float(eps),
                                          dtype_code(x2), _DTYPES[odt], _stream())
     _lib.check(st, "layernorm_fwd")
-    return y.reshape(x.shape)
+    return y if out is not None else y.reshape(x.shape)
 
 
 def xattn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *, head_dim: Optional[int] = None,

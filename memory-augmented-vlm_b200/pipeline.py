@@ -149,7 +149,9 @@ class VisualMemoryPipeline(nn.Module):
         ring_kv = torch.empty((b, cap * lq, 2 * hd), dtype=dtype, device=dev) if n_chunks > 1 else None
 
         mem = rmt.initial_state(dtype).reshape(1, lq, d).expand(b, lq, d).contiguous()
+        last_layer = len(rmt.layers) - 1
         for t in range(n_chunks):
+            slot = t % cap
             if t > 0:
                 # memory evolution: Q = newest state, K/V = every state still cached (incl. itself)
                 n = min(t, cap)
@@ -167,9 +169,12 @@ class VisualMemoryPipeline(nn.Module):
                                       head_dim=dhp, scale=scale)
                 a = att.residual(ctx, mem, weight=pk["wo"])
                 up = ops.linear(a, layer.mlp[0].weight, layer.mlp[0].bias, act=layer._act)
-                mem = layer.residual(up, a)
-            slot = t % cap
-            ring_states[:, slot].copy_(mem)
+                if li == last_layer and b == 1:                         # the new state is normalised straight into its ring slot
+                    mem = layer.residual(up, a, out=ring_states[:, slot])
+                else:
+                    mem = layer.residual(up, a)
+            if b != 1:
+                ring_states[:, slot].copy_(mem)
             if t + 1 < n_chunks:                                        # project the new state once for later chunks
                 for bi in range(b):
                     ops.linear(mem[bi], evo_p["wkv"], evo_p["bkv"], out=ring_kv[bi, slot * lq:(slot + 1) * lq])
@@ -190,11 +195,22 @@ class VisualMemoryPipeline(nn.Module):
         fz = self.memory_fuser
         hidden = ops.linear(ring_states[:, :n_keep].reshape(b * n_keep * lq, d), fz[0].weight, fz[0].bias,
                             act=ACT_GELU_ERF).reshape(b, n_keep, lq, 4 * d)
+        # reference order is oldest state first: ring slots (first+i) % cap -- at most two contiguous runs of
+        # slots, each ONE GEMM whose rows land in their final position in the sequence (M = run * Lq rows
+        # quantises far better on 148 SMs than per-state GEMMs of 1568 rows)
+        runs, i = [], 0
+        while i < n_keep:
+            s0 = (first + i) % cap
+            ln = min(n_keep - i, cap - s0, n_keep - s0) if s0 < n_keep else 0
+            if ln <= 0:
+                raise RuntimeError("mavlm: inconsistent state ring")    # pragma: no cover
+            runs.append((i, s0, ln))
+            i += ln
         for bi in range(b):
-            for i in range(n_keep):
-                slot = (first + i) % cap
-                dst = seq_out[bi, npm + i * lq: npm + (i + 1) * lq]
-                ops.linear(hidden[bi, slot], fz[2].weight, fz[2].bias, addvec=emb[0], out=dst)
+            for (i0, s0, ln) in runs:
+                dst = seq_out[bi, npm + i0 * lq: npm + (i0 + ln) * lq]
+                ops.linear(hidden[bi, s0:s0 + ln].reshape(ln * lq, 4 * d), fz[2].weight, fz[2].bias, addvec=emb[0],
+                           out=dst)
             ops.assemble(seq_out[bi], None, n_keep * lq, z[bi], fine_idx, p, emb, self.image_newline.detach(),
                          self.embed_tokens.weight.detach(), pm_ids, pf_ids, drop_frames)
         out = {"sequence": seq_out}

@@ -154,10 +154,13 @@ def fam_gemm():
     torch.manual_seed(0)
     _gemm_case(128, 64, 64, 64, identity=True, verbose=True)
     _gemm_case(128, 64, 64, 64, verbose=True)
-    for bn in (64, 128, 192, 256):
-        _gemm_case(128, bn, 64, bn, verbose=True)
-        _gemm_case(128, bn, 256, bn, verbose=True)
-        _gemm_case(384, 2 * bn, 512, bn, verbose=True)
+    for bn in (1128, 1192, 1256, 64, 128, 192, 256):
+        w = bn % 1000
+        _gemm_case(128, w, 64, bn, verbose=True)
+        _gemm_case(256, w, 64, bn, identity=True, verbose=True)
+        _gemm_case(128, w, 256, bn, verbose=True)
+        _gemm_case(384, 2 * w, 512, bn, verbose=True)
+        _gemm_case(2000, 5 * w + 8, 1160, bn, resid=True, verbose=True)
         _gemm_case(1568, 896, 896, bn, act=1, verbose=True)
         _gemm_case(1568, 3584, 3584, bn, act=2, verbose=True)
         _gemm_case(200, 3584, 1152, bn, resid=True, f32out=True, verbose=True)
@@ -320,7 +323,7 @@ def fam_perf():
         b = torch.randn(n, device=dev).bfloat16()
         out = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
         line = f"gemm {m}x{n}x{k}:"
-        for bn in (0, 64, 128, 192, 256):
+        for bn in (0, 128, 192, 256, 1128, 1192, 1256):
             lib.mavlm_debug_force_gemm_bn(bn)
             ms = timeit(lambda: ops.linear(a, w, b, out=out))
             line += f"  BN{bn}: {ms * 1e3:.0f}us {2 * m * n * k / ms / 1e9:.0f}TF"
@@ -362,6 +365,82 @@ def fam_perf():
     print(f"layernorm 1568x3584 f32->bf16: {ms * 1e3:.1f}us {1568 * 3584 * 6 / ms / 1e6:.0f}GB/s")
 
 
+def fam_micro():
+    """Per-kernel device time without host launch overhead: N back-to-back calls captured in one CUDA graph."""
+    import torch
+    from mavlm_b200 import ops
+    dev = "cuda"
+
+    def graph_time(fn, n=20, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            fn()
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(n):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / (n * reps) * 1e3   # us per call
+
+    xl = torch.randn(1568, 3584, device=dev)
+    gm = torch.randn(3584, device=dev).bfloat16()
+    yl = torch.empty(1568, 3584, device=dev, dtype=torch.bfloat16)
+    print(f"layernorm 1568x3584 f32->bf16 (L2-resident input): {graph_time(lambda: ops.layernorm(xl, gm, gm, 1e-12, out=yl)):.1f} us")
+    xs = [torch.randn(1568, 3584, device=dev) for _ in range(12)]    # 270 MB ring: input comes from HBM
+    it = [0]
+
+    def ln_ring():
+        it[0] = (it[0] + 1) % len(xs)
+        ops.layernorm(xs[it[0]], gm, gm, 1e-12, out=yl)
+    print(f"layernorm 1568x3584 f32->bf16 (HBM input): {graph_time(ln_ring, n=24):.1f} us  (ideal 33.7 MB / 6.55 TB/s = 5.1 us)")
+    tiny = torch.randn(8, 196, 64, device=dev).bfloat16()
+    tab = torch.randn(8, 64, device=dev)
+    idx = torch.arange(8, device=dev)
+    print(f"tiny add_pe (launch-to-launch floor): {graph_time(lambda: ops.add_pe(tiny, tab, idx, out=tiny)):.1f} us")
+    for (m, n, k) in ((1568, 3584, 3584), (1568, 14336, 3584), (1568, 3584, 14336)):
+        a = torch.randn(m, k, device=dev).bfloat16()
+        w = torch.randn(n, k, device=dev).bfloat16()
+        b = torch.randn(n, device=dev).bfloat16()
+        out = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
+        us = graph_time(lambda: ops.linear(a, w, b, out=out))
+        print(f"gemm {m}x{n}x{k}: {us:.1f} us {2 * m * n * k / us / 1e6:.0f} TF")
+    from mavlm_b200 import _lib
+    lib = _lib.load()
+    a = torch.randn(46656, 1152, device=dev).bfloat16()
+    w = torch.randn(3584, 1152, device=dev).bfloat16() / 34
+    b = torch.randn(3584, device=dev).bfloat16()
+    out = torch.empty(46656, 3584, device=dev, dtype=torch.bfloat16)
+    for bn in (1256, 256):
+        lib.mavlm_debug_force_gemm_bn(bn)
+        for flags, name in ((0, "full"), (2, "no GELU"), (1, "no stores"), (3, "no GELU, no stores")):
+            lib.mavlm_debug_set_flags(flags)
+            us = graph_time(lambda: ops.linear(a, w, b, act=1, out=out), n=4, reps=3)
+            print(f"projector L1 46656x3584x1152 GELU tile {bn} [{name}]: {us:.1f} us {2 * 46656 * 3584 * 1152 / us / 1e6:.0f} TF")
+    lib.mavlm_debug_set_flags(0)
+    lib.mavlm_debug_force_gemm_bn(0)
+    h, dh = 8, 448
+    for (bsz, lq, lk) in ((1, 1568, 6272), (1, 1568, 1568)):
+        q = torch.randn(bsz, lq, h * dh, device=dev).bfloat16()
+        kk = torch.randn(bsz, lk, h * dh, device=dev).bfloat16()
+        v = torch.randn(bsz, lk, h * dh, device=dev).bfloat16()
+        us = graph_time(lambda: ops.xattn(q, kk, v, h), n=10)
+        print(f"xattn B{bsz} {lq}x{lk} dh{dh} (+merge): {us:.1f} us {4.0 * bsz * h * lq * lk * dh / us / 1e6:.0f} TF")
+    x = torch.randn(64, 729, 3584, device=dev).bfloat16()
+    us = graph_time(lambda: ops.pool_pe(x, side=27), n=5)
+    print(f"pool F64: {us:.1f} us {64 * (729 + 196) * 3584 * 2 / us / 1e3:.0f} GB/s")
+
+
 def fam_ab():
     """A/B of scheduling knobs on the full bench step, alternating within one process (box-to-box and
     thermal variation between separate runs is +-5 %)."""
@@ -383,16 +462,31 @@ def fam_ab():
         return e0.elapsed_time(e1) / n
 
     run(5)
+    g = pipe.graphed(1, 64)
+    g(x, idx)
+
+    def run_graph(n=10):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            g(None, None)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
     for rnd in range(4):
         line = f"round {rnd}:"
-        for g in (8, 0, 10, 11):
-            lib.mavlm_debug_force_attn_groups(g)
-            line += f"  attn_groups={g}: {run():.3f} ms"
+        for bn in (0, -1):
+            lib.mavlm_debug_force_gemm_bn(bn)
+            torch.cuda._sleep(20_000_000)
+            line += f"  gemm_tiles={'pair+single' if bn == 0 else 'single only'}: eager {run():.3f} ms"
+        lib.mavlm_debug_force_gemm_bn(0)
+        line += f"  | graph(pair+single) {run_graph():.3f} ms"
         print(line, flush=True)
-    lib.mavlm_debug_force_attn_groups(0)
 
 
-FAMS = {"ab": fam_ab, "elem": fam_elem, "simt": fam_simt, "gemm": fam_gemm, "attn": fam_attn, "pipe": fam_pipe, "perf": fam_perf}
+FAMS = {"micro": fam_micro, "ab": fam_ab, "elem": fam_elem, "simt": fam_simt, "gemm": fam_gemm, "attn": fam_attn, "pipe": fam_pipe, "perf": fam_perf}
 
 if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[1] == "--child":
