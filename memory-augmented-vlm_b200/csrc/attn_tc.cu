@@ -28,9 +28,18 @@
 // served to the whole group out of L2 (a per-CTA stream-K range destroys exactly this sharing: measured 40 %
 // slower per key block).  Group g owns the contiguous range [g*U/G, (g+1)*U/G) of U = B*H*ngq*J
 // (b, h, q-group, key block) units.  A CTA walks its group's range as segments (item, j0..j1): a segment that
-// covers its whole item writes O / LSE directly, a partial segment writes unnormalised fp32 (O, m, l) to a
-// workspace slot (at most two per CTA) and attn_merge_kernel combines the partials of split items with the
-// usual log-sum-exp weights.
+// covers its whole item writes O / LSE directly.  An item cut across groups is finished INSIDE the kernel: every
+// part that does not start at key block 0 is the FIRST segment of its group -- it writes unnormalised fp32
+// (O, m, l) to its CTA's workspace slot and raises a flag; the part that starts at key block 0 is the LAST
+// segment of its group -- it waits for the flags of the later parts (long set: they were computed first),
+// combines them with its own accumulator using the usual log-sum-exp weights and writes the final rows.
+// (A separate merge kernel cost 20 us per attention call at B = 1: a launch plus a second pass over all partials.)
+//
+// Why the tensor pipe stays near 55 % here (ncu, B = 8): with head_dim 448 the O accumulator takes 448 of the 512
+// TMEM columns, so a score tile can only be 64 keys wide, and an SS-mode MMA with N = 64 runs at half rate
+// (the 4 KB A-operand fetch takes 64 cycles; the N=64 GEMM tile shows the same 0.5x).  QK^T therefore costs twice
+// its math time; a CTA-pair (cta_group::2) version was built and measured at parity, i.e. it is the A fetch and
+// not the K/V bytes that bounds the kernel.
 #include "common.cuh"
 
 namespace mavlm {
@@ -42,6 +51,7 @@ constexpr int ATT_THREADS = 64 + 32 * ATT_SM_WARPS;  // 320
 constexpr int ATT_SLICE_BYTES = ATT_BKV * 64 * 2;    // 8 KB
 constexpr int ATT_SLOT_BYTES = 2 * ATT_SLICE_BYTES;  // 16 KB pair slot
 constexpr int ATT_P_BYTES = ATT_BQ * ATT_BKV * 2;    // 16 KB
+constexpr int MERGE_MAX_PARTS = 14;                  // an item is never cut into more than 1 + 14 parts
 
 struct AttnTcParams {
   int lq, lk, kv_blocks;
@@ -52,7 +62,8 @@ struct AttnTcParams {
   int heads, qtiles, items;
   int gs, ngq, groups;  // CTAs per group (q tiles of one q-group), q-groups per (b,h), number of groups
   long long units;      // batch * heads * ngq * kv_blocks  (group-level units)
-  float* ws;            // partial slots: [grid][2] x { O fp32 [128][DH], m [128], l [128] }
+  float* ws;            // partial slots: [grid] x { O fp32 [DH/32][32][128], m [128], l [128] }
+  unsigned int* flags;  // [grid] "this CTA's partial slot is complete" (zeroed by the host before the launch)
 };
 
 template <int DH>
@@ -345,45 +356,92 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       mbar_wait(&o_done[(n - 1) & 1], ((n - 1) >> 1) & 1);  // PV(n-3) known complete (s_full(n-1)): exact as above
       tc_fence_after();
       const int q = qt * ATT_BQ + row;
-      if (j0 == 0 && j1 == J) {  // the segment covers the whole item: final result
+      if (j0 > 0) {
+        // ---- later part of an item that starts in an earlier group: unnormalised fp32 O + (m, l) into this CTA's
+        // workspace slot, [chunk][column][row] so that both this write and the merging read are coalesced
+        float* wsb = p.ws + static_cast<long long>(blockIdx.x) * attn_slot_floats<DH>();
+#pragma unroll 1
+        for (int c = half * OCH; c < (half + 1) * OCH; ++c) {
+          uint32_t o[32];
+          tmem_ld32(tmem_base + lane_off + c * 32, o);
+          tmem_ld_wait();
+          float* wc = wsb + static_cast<long long>(c) * 32 * ATT_BQ + row;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) wc[i * ATT_BQ] = __uint_as_float(o[i]);
+        }
+        if (half == 0) {
+          wsb[static_cast<long long>(ATT_BQ) * DH + row] = m_used;
+          wsb[static_cast<long long>(ATT_BQ) * DH + ATT_BQ + row] = l;
+        }
+        __threadfence();
+        named_bar_sync(1, 32 * ATT_SM_WARPS);
+        if (warp == 2 && lane == 0) st_release_gpu(p.flags + blockIdx.x, 1u);
+      } else {
+        // ---- the part that starts at key block 0 owns the item's result.  If the item continues in later groups
+        // (j1 < J) their parts were those groups' first segments: wait for them and fold them in.
+        float w_own = 1.f;
+        int np = 0;
+        int g_part[MERGE_MAX_PARTS];
+        float w_part[MERGE_MAX_PARTS];
+        if (j1 < J) {
+          const long long item_end = (static_cast<long long>(item) + 1) * J;
+          float m_all = m_used;
+          for (int g2 = grp + 1; g2 < p.groups && np < MERGE_MAX_PARTS; ++g2) {
+            long long v0, v1;
+            attn_group_range(p, g2, v0, v1);
+            if (v0 >= item_end) break;
+            g_part[np++] = g2;
+          }
+          if (warp == 2 && lane == 0)
+            for (int i = 0; i < np; ++i) wait_flag_gpu(p.flags + static_cast<long long>(g_part[i]) * p.gs + grp_r);
+          named_bar_sync(1, 32 * ATT_SM_WARPS);
+          __threadfence();
+          for (int i = 0; i < np; ++i) {
+            const float* sl = p.ws + (static_cast<long long>(g_part[i]) * p.gs + grp_r) * attn_slot_floats<DH>();
+            w_part[i] = ld_cg_f32(sl + static_cast<long long>(ATT_BQ) * DH + row);  // m of that part
+            m_all = fmaxf(m_all, w_part[i]);
+          }
+          w_own = ex2_approx(m_used - m_all);
+          l *= w_own;
+          for (int i = 0; i < np; ++i) {
+            const float* sl = p.ws + (static_cast<long long>(g_part[i]) * p.gs + grp_r) * attn_slot_floats<DH>();
+            w_part[i] = ex2_approx(w_part[i] - m_all);
+            l += w_part[i] * ld_cg_f32(sl + static_cast<long long>(ATT_BQ) * DH + ATT_BQ + row);
+          }
+          m_used = m_all;
+        }
         const float inv = 1.f / l;
+        const float own_scale = w_own * inv;
         __nv_bfloat16* orow = p.O + b * p.o_batch + static_cast<long long>(q) * p.ldo + h * DH;
 #pragma unroll 1
         for (int c = half * OCH; c < (half + 1) * OCH; ++c) {
           uint32_t o[32];
           tmem_ld32(tmem_base + lane_off + c * 32, o);
           tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(o[i]) * own_scale;
+          for (int k = 0; k < np; ++k) {
+            const float* sl = p.ws + (static_cast<long long>(g_part[k]) * p.gs + grp_r) * attn_slot_floats<DH>() +
+                              static_cast<long long>(c) * 32 * ATT_BQ + row;
+            const float wk = w_part[k] * inv;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaf(wk, ld_cg_f32(sl + i * ATT_BQ), v[i]);
+          }
           if (q < p.lq) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               uint4 t;
-              t.x = pack_bf16x2(__uint_as_float(o[8 * g]) * inv, __uint_as_float(o[8 * g + 1]) * inv);
-              t.y = pack_bf16x2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv);
-              t.z = pack_bf16x2(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv);
-              t.w = pack_bf16x2(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv);
+              t.x = pack_bf16x2(v[8 * g], v[8 * g + 1]);
+              t.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
+              t.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
+              t.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
               reinterpret_cast<uint4*>(orow + c * 32)[g] = t;
             }
           }
         }
         if (half == 0 && p.lse != nullptr && q < p.lq)
           p.lse[(static_cast<long long>(b) * p.heads + h) * p.lq + q] = (m_used + log2f(l)) * 0.69314718055994530942f;
-      } else {  // partial: unnormalised fp32 O + (m, l) into this CTA's workspace slot
-        const int slot = (u == u_begin) ? 0 : 1;
-        float* wsb = p.ws + (static_cast<long long>(blockIdx.x) * 2 + slot) * attn_slot_floats<DH>();
-        float* wrow = wsb + static_cast<long long>(row) * DH;
-#pragma unroll 1
-        for (int c = half * OCH; c < (half + 1) * OCH; ++c) {
-          uint32_t o[32];
-          tmem_ld32(tmem_base + lane_off + c * 32, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int g = 0; g < 8; ++g)
-            reinterpret_cast<uint4*>(wrow + c * 32)[g] = make_uint4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
-        }
-        if (half == 0) {
-          wsb[static_cast<long long>(ATT_BQ) * DH + row] = m_used;
-          wsb[static_cast<long long>(ATT_BQ) * DH + ATT_BQ + row] = l;
-        }
       }
       tc_fence_before();
       __syncwarp();
@@ -395,81 +453,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
-  }
-}
-
-// Combine the partial segments of every item that was split across groups (log-sum-exp weights).
-// grid = (items, ATT_BQ / MERGE_ROWS): one block per 16 query rows of a (b, h, q tile); the slot pointers of
-// the item's parts are resolved once per block.
-constexpr int MERGE_ROWS = 16;
-constexpr int MERGE_MAX_PARTS = 16;
-template <int DH>
-__global__ void __launch_bounds__(256) attn_merge_kernel(AttnTcParams p) {
-  __shared__ const float* parts[MERGE_MAX_PARTS];
-  __shared__ int n_parts;
-  const int item = blockIdx.x;
-  const int qt = item % p.qtiles, h = (item / p.qtiles) % p.heads, b = item / (p.qtiles * p.heads);
-  if (threadIdx.x == 0) {
-    const int J = p.kv_blocks;
-    const int r = qt % p.gs;
-    const long long gi = (static_cast<long long>(b) * p.heads + h) * p.ngq + qt / p.gs;  // group-level item
-    const long long i0 = gi * J, i1 = i0 + J;
-    int g_lo = static_cast<int>(i0 * p.groups / p.units);
-    long long u0, u1;
-    while (g_lo > 0) {
-      attn_group_range(p, g_lo, u0, u1);
-      if (u0 <= i0) break;
-      --g_lo;
-    }
-    for (;;) {
-      attn_group_range(p, g_lo, u0, u1);
-      if (u1 > i0) break;
-      ++g_lo;
-    }
-    int n = 0;
-    attn_group_range(p, g_lo, u0, u1);
-    if (!(u0 <= i0 && u1 >= i1)) {  // else: one group covered the whole item and wrote the final result itself
-      const long long slot_f = attn_slot_floats<DH>();
-      for (int g = g_lo; n < MERGE_MAX_PARTS; ++g) {
-        attn_group_range(p, g, u0, u1);
-        const long long s0 = u0 > i0 ? u0 : i0;
-        parts[n++] = p.ws + ((static_cast<long long>(g) * p.gs + r) * 2 + (s0 == u0 ? 0 : 1)) * slot_f;
-        if (u1 >= i1) break;
-      }
-    }
-    n_parts = n;
-  }
-  __syncthreads();
-  const int np = n_parts;
-  if (np == 0) return;
-  constexpr int CG = DH / 8;
-  const int row0 = blockIdx.y * MERGE_ROWS;
-  for (int idx = threadIdx.x; idx < MERGE_ROWS * CG; idx += blockDim.x) {
-    const int row = row0 + idx / CG, cg = idx % CG;
-    const int q = qt * ATT_BQ + row;
-    if (q >= p.lq) continue;
-    float m = -INFINITY;
-    for (int i = 0; i < np; ++i) m = fmaxf(m, parts[i][static_cast<long long>(ATT_BQ) * DH + row]);
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    float lsum = 0.f;
-    for (int i = 0; i < np; ++i) {
-      const float* sl = parts[i];
-      const float w = ex2_approx(sl[static_cast<long long>(ATT_BQ) * DH + row] - m);
-      lsum += w * sl[static_cast<long long>(ATT_BQ) * DH + ATT_BQ + row];
-      const float4 a = __ldg(reinterpret_cast<const float4*>(sl + static_cast<long long>(row) * DH + cg * 8));
-      const float4 d = __ldg(reinterpret_cast<const float4*>(sl + static_cast<long long>(row) * DH + cg * 8 + 4));
-      acc[0] += w * a.x; acc[1] += w * a.y; acc[2] += w * a.z; acc[3] += w * a.w;
-      acc[4] += w * d.x; acc[5] += w * d.y; acc[6] += w * d.z; acc[7] += w * d.w;
-    }
-    const float inv = 1.f / lsum;
-    uint4 t;
-    t.x = pack_bf16x2(acc[0] * inv, acc[1] * inv);
-    t.y = pack_bf16x2(acc[2] * inv, acc[3] * inv);
-    t.z = pack_bf16x2(acc[4] * inv, acc[5] * inv);
-    t.w = pack_bf16x2(acc[6] * inv, acc[7] * inv);
-    *reinterpret_cast<uint4*>(p.O + b * p.o_batch + static_cast<long long>(q) * p.ldo + h * DH + cg * 8) = t;
-    if (cg == 0 && p.lse != nullptr)
-      p.lse[(static_cast<long long>(b) * p.heads + h) * p.lq + q] = (m + log2f(lsum)) * 0.69314718055994530942f;
   }
 }
 
@@ -490,7 +473,7 @@ static AttnGeom attn_geometry(int batch, int heads, int lq, int lk) {
   if (g_force_groups > 0) groups = g_force_groups;
   // an item (one (b,h,q-group), J units) must not be cut into more than MERGE_MAX_PARTS parts
   const long long bh = static_cast<long long>(batch) * heads * g.ngq;
-  if (groups > bh * (MERGE_MAX_PARTS - 2)) groups = bh * (MERGE_MAX_PARTS - 2);
+  if (groups > bh * (MERGE_MAX_PARTS - 1)) groups = bh * (MERGE_MAX_PARTS - 1);
   if (groups < 1) groups = 1;
   if (groups > g.units) groups = g.units;
   g.groups = static_cast<int>(groups);
@@ -508,19 +491,18 @@ static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUt
                                        Cfg::SMEM_BYTES));
     configured = true;
   }
+  if (p.units % p.groups != 0 || (p.units / p.groups) % p.kv_blocks != 0)  // some item is split across groups
+    MAVLM_CUDA_OK(cudaMemsetAsync(p.flags, 0, static_cast<size_t>(p.groups) * p.gs * sizeof(unsigned int), st));
   attn_tc_kernel<DH><<<p.groups * p.gs, ATT_THREADS, Cfg::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
   MAVLM_LAUNCH_OK();
-  if (p.units % p.groups != 0 || (p.units / p.groups) % p.kv_blocks != 0) {  // some item is split across groups
-    attn_merge_kernel<DH><<<dim3(p.items, ATT_BQ / MERGE_ROWS), 256, 0, st>>>(p);
-    MAVLM_LAUNCH_OK();
-  }
   return MAVLM_OK;
 }
 
 size_t xattn_bf16_workspace_bytes(int batch, int heads, int lq, int lk, int dh) {
   const AttnGeom g = attn_geometry(batch, heads, lq, lk);
   const long long slot = static_cast<long long>(ATT_BQ) * dh + 2 * ATT_BQ;
-  return static_cast<size_t>(g.groups) * g.gs * 2 * slot * sizeof(float);
+  const size_t ctas = static_cast<size_t>(g.groups) * g.gs;
+  return ctas * slot * sizeof(float) + ctas * sizeof(unsigned int);  // one partial slot + one flag per CTA
 }
 
 int xattn_bf16_tc(const __nv_bfloat16* Q, long long ldq, long long qb, const __nv_bfloat16* K, long long ldk,
@@ -560,6 +542,7 @@ int xattn_bf16_tc(const __nv_bfloat16* Q, long long ldq, long long qb, const __n
   p.qtiles = geo.qtiles; p.ngq = geo.ngq; p.gs = geo.gs; p.groups = geo.groups; p.units = geo.units;
   p.items = batch * heads * p.qtiles;
   p.ws = static_cast<float*>(ws);
+  p.flags = reinterpret_cast<unsigned int*>(p.ws + static_cast<long long>(p.groups) * p.gs * (static_cast<long long>(ATT_BQ) * dh + 2 * ATT_BQ));
   return dh == 448 ? launch_attn<448>(tmQ, tmK, tmV, p, st) : launch_attn<128>(tmQ, tmK, tmV, p, st);
 }
 

@@ -315,6 +315,32 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, int a_mn_ma
          (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// ---- inter-CTA hand-off through global memory (in-kernel fix-up of split work) ----
+__device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void wait_flag_gpu(const unsigned int* p) {  // bounded like mbar_wait
+  if (ld_acquire_gpu(p) != 0u) return;
+  const long long t0 = clock64();
+  while (ld_acquire_gpu(p) == 0u) {
+    __nanosleep(64);
+    if (clock64() - t0 > MAVLM_MBAR_TIMEOUT_CYCLES) {
+      printf("mavlm: partial-result flag timeout block %d\n", blockIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ float ld_cg_f32(const float* p) {  // L2 load: data written by another CTA of this grid
+  float v;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -430,12 +430,12 @@ def fam_micro():
     lib.mavlm_debug_set_flags(0)
     lib.mavlm_debug_force_gemm_bn(0)
     h, dh = 8, 448
-    for (bsz, lq, lk) in ((1, 1568, 6272), (1, 1568, 1568)):
+    for (bsz, lq, lk) in ((1, 1568, 6272), (1, 1568, 1568), (8, 1568, 6272), (1, 1568, 15680)):
         q = torch.randn(bsz, lq, h * dh, device=dev).bfloat16()
         kk = torch.randn(bsz, lk, h * dh, device=dev).bfloat16()
         v = torch.randn(bsz, lk, h * dh, device=dev).bfloat16()
         us = graph_time(lambda: ops.xattn(q, kk, v, h), n=10)
-        print(f"xattn B{bsz} {lq}x{lk} dh{dh} (+merge): {us:.1f} us {4.0 * bsz * h * lq * lk * dh / us / 1e6:.0f} TF")
+        print(f"xattn B{bsz} {lq}x{lk} dh{dh}: {us:.1f} us {4.0 * bsz * h * lq * lk * dh / us / 1e6:.0f} TF")
     x = torch.randn(64, 729, 3584, device=dev).bfloat16()
     us = graph_time(lambda: ops.pool_pe(x, side=27), n=5)
     print(f"pool F64: {us:.1f} us {64 * (729 + 196) * 3584 * 2 / us / 1e3:.0f} GB/s")
