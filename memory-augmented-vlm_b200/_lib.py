@@ -78,6 +78,8 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
+    if os.environ.get("MAVLM_DEBUG_FLAGS"):                       # development only (see mavlm_debug_set_flags)
+        lib.mavlm_debug_set_flags(int(os.environ["MAVLM_DEBUG_FLAGS"]))
     _lib = lib
     return lib
 

@@ -85,6 +85,7 @@ MAVLM_API int mavlm_debug_force_gemm_bn(int bn) {
    activation) -- for bottleneck attribution on the GPU only; results are garbage while a flag is set */
 MAVLM_API int mavlm_debug_set_flags(int flags) {
   gemm_tc_set_debug(flags);
+  pdl_force_off((flags & 16) != 0);
   return MAVLM_OK;
 }
 

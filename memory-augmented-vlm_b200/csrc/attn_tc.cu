@@ -152,6 +152,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     if (elect_one()) {
@@ -493,7 +495,9 @@ static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUt
   }
   if (p.units % p.groups != 0 || (p.units / p.groups) % p.kv_blocks != 0)  // some item is split across groups
     MAVLM_CUDA_OK(cudaMemsetAsync(p.flags, 0, static_cast<size_t>(p.groups) * p.gs * sizeof(unsigned int), st));
-  attn_tc_kernel<DH><<<p.groups * p.gs, ATT_THREADS, Cfg::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
+  LaunchCfg lc;  // (after a memset node the PDL attribute is inert: the edge is then a full dependency)
+  make_launch(lc, dim3(p.groups * p.gs), dim3(ATT_THREADS), Cfg::SMEM_BYTES, st, 1, 2);
+  MAVLM_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, attn_tc_kernel<DH>, tmQ, tmK, tmV, p));
   MAVLM_LAUNCH_OK();
   return MAVLM_OK;
 }

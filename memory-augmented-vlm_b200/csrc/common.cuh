@@ -52,12 +52,69 @@ int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int swizzle_by
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Programmatic dependent launch (PDL): the hot-path kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, call griddepcontrol.launch_dependents at their start and
+// griddepcontrol.wait before their first access to global memory.  The next kernel's CTAs then become resident
+// as soon as SMs free up and run their prologue (barrier init, TMEM allocation, descriptor prefetch) under the
+// tail of the previous kernel; the wait returns once the previous grid has completed and flushed.  The
+// recurrence is ~45 dependent launches per 64 frames, so the launch-to-launch gap matters.
+// MAVLM_PDL=0 in the environment (read once) or mavlm_debug_set_flags bit 4 disables it.
+bool pdl_enabled(int family = 0);  // family: 1 gemm, 2 attention, 4 layernorm, 8 pool / pe (MAVLM_PDL_MASK, default all)
+void pdl_force_off(bool off);
+
+struct LaunchCfg {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[2];
+};
+// cluster = 0 / 1: no cluster attribute
+inline void make_launch(LaunchCfg& lc, dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster, int pdl) {
+  lc.cfg = cudaLaunchConfig_t{};
+  lc.cfg.gridDim = grid;
+  lc.cfg.blockDim = block;
+  lc.cfg.dynamicSmemBytes = smem;
+  lc.cfg.stream = st;
+  unsigned n = 0;
+  if (cluster > 1) {
+    lc.attr[n].id = cudaLaunchAttributeClusterDimension;
+    lc.attr[n].val.clusterDim.x = static_cast<unsigned>(cluster);
+    lc.attr[n].val.clusterDim.y = 1;
+    lc.attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl && pdl_enabled(pdl)) {
+    lc.attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    lc.attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  lc.cfg.attrs = lc.attr;
+  lc.cfg.numAttrs = n;
+}
+
 #if defined(__CUDACC__)
 // ---------------------------------------------------------------------------------------
 // device-side PTX wrappers
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// PDL (see make_launch): no-ops in a kernel launched without the attribute
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Loads of data written by the PREVIOUS kernel in a PDL kernel: they must stay behind griddepcontrol.wait.
+// nvcc hoists ld.global.nc (__ldg / const __restrict__) loads above an asm volatile with a "memory" clobber
+// (the LayerNorm kernel read its input before the wait that way), so these are volatile asm themselves:
+// volatile asm statements keep their relative order.
+__device__ __forceinline__ uint4 ld_dep_u4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint2 ld_dep_u2(const void* p) {
+  uint2 v;
+  asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
 }
 
 __device__ __forceinline__ bool elect_one() {

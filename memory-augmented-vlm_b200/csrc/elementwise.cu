@@ -14,9 +14,9 @@ struct Vec<float> {
     float4 t = __ldg(reinterpret_cast<const float4*>(p));
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   }
-  __device__ static void load_plain(const float* p, float (&v)[4]) {
-    float4 t = *reinterpret_cast<const float4*>(p);
-    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  __device__ static void load_plain(const float* p, float (&v)[4]) {  // data of the previous kernel (see ld_dep_u4)
+    const uint4 t = ld_dep_u4(p);
+    v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y); v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
   }
   __device__ static void store(float* p, const float (&v)[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
@@ -35,7 +35,7 @@ struct Vec<__nv_bfloat16> {
     }
   }
   __device__ static void load_plain(const __nv_bfloat16* p, float (&v)[8]) {
-    uint4 t = *reinterpret_cast<const uint4*>(p);
+    uint4 t = ld_dep_u4(p);
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -62,6 +62,8 @@ __global__ void __launch_bounds__(256) pool_pe_kernel(const T* __restrict__ x, T
                                                       const float* __restrict__ pe, const int64_t* __restrict__ fidx,
                                                       int frames, int side, int out_side, int stride, int dim) {
   constexpr int V = Vec<T>::N;
+  pdl_trigger();
+  pdl_wait();
   const int groups = dim / V;
   const long long total = static_cast<long long>(frames) * out_side * out_side * groups;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -82,10 +84,10 @@ __global__ void __launch_bounds__(256) pool_pe_kernel(const T* __restrict__ x, T
       int y1 = y0 + (y0 < side - 1), x1 = x0 + (x0 < side - 1);
       float ly1 = sy - y0, lx1 = sx - x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
       float v00[V], v01[V], v10[V], v11[V];
-      Vec<T>::load(xf + (static_cast<long long>(y0) * side + x0) * dim, v00);
-      Vec<T>::load(xf + (static_cast<long long>(y0) * side + x1) * dim, v01);
-      Vec<T>::load(xf + (static_cast<long long>(y1) * side + x0) * dim, v10);
-      Vec<T>::load(xf + (static_cast<long long>(y1) * side + x1) * dim, v11);
+      Vec<T>::load_plain(xf + (static_cast<long long>(y0) * side + x0) * dim, v00);
+      Vec<T>::load_plain(xf + (static_cast<long long>(y0) * side + x1) * dim, v01);
+      Vec<T>::load_plain(xf + (static_cast<long long>(y1) * side + x0) * dim, v10);
+      Vec<T>::load_plain(xf + (static_cast<long long>(y1) * side + x1) * dim, v11);
 #pragma unroll
       for (int k = 0; k < V; ++k) acc[k] = ly0 * (lx0 * v00[k] + lx1 * v01[k]) + ly1 * (lx0 * v10[k] + lx1 * v11[k]);
     } else {
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(256) pool_pe_kernel(const T* __restrict__ x, T
       for (int dy = 0; dy < stride; ++dy)
         for (int dx = 0; dx < stride; ++dx) {
           float v[V];
-          Vec<T>::load(xf + (static_cast<long long>(oy * stride + dy) * side + (ox * stride + dx)) * dim, v);
+          Vec<T>::load_plain(xf + (static_cast<long long>(oy * stride + dy) * side + (ox * stride + dx)) * dim, v);
 #pragma unroll
           for (int k = 0; k < V; ++k) acc[k] = (MODE == MAVLM_POOL_MAX) ? fmaxf(acc[k], v[k]) : acc[k] + v[k];
         }
@@ -121,6 +123,8 @@ __global__ void __launch_bounds__(256) add_pe_kernel(const T* x, T* y,  // y may
                                                      const float* __restrict__ pe, const int64_t* __restrict__ fidx,
                                                      int frames, int tokens, int dim) {
   constexpr int V = Vec<T>::N;
+  pdl_trigger();
+  pdl_wait();
   const int groups = dim / V;
   const long long total = static_cast<long long>(frames) * tokens * groups;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -167,6 +171,8 @@ __global__ void __launch_bounds__(32 * LN_WARPS, 3) layernorm_kernel(const TI* _
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
   const bool active = row < rows;
+  pdl_trigger();
+  pdl_wait();
   const TI* xr = x + (active ? row : 0) * dim;
   TO* yr = y + (active ? row : 0) * dim;
   float v[CACHE][4];
@@ -176,10 +182,11 @@ __global__ void __launch_bounds__(32 * LN_WARPS, 3) layernorm_kernel(const TI* _
     const int i = (c * 32 + lane) * 4;
     if (active && i < dim) {
       if (sizeof(TI) == 4) {
-        float4 t = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(xr) + i);
-        v[c][0] = t.x; v[c][1] = t.y; v[c][2] = t.z; v[c][3] = t.w;
+        const uint4 t = ld_dep_u4(reinterpret_cast<const float*>(xr) + i);
+        v[c][0] = __uint_as_float(t.x); v[c][1] = __uint_as_float(t.y);
+        v[c][2] = __uint_as_float(t.z); v[c][3] = __uint_as_float(t.w);
       } else {
-        uint2 t = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(xr) + i);
+        uint2 t = ld_dep_u2(reinterpret_cast<const __nv_bfloat16*>(xr) + i);
         float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&t.x));
         float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&t.y));
         v[c][0] = a.x; v[c][1] = a.y; v[c][2] = b.x; v[c][3] = b.y;
@@ -259,6 +266,8 @@ __global__ void __launch_bounds__(128) assemble_kernel(T* __restrict__ seq, cons
                                                        const int64_t* __restrict__ pm_ids, int n_pm,
                                                        const int64_t* __restrict__ pf_ids, int n_pf, int dim) {
   constexpr int V = Vec<T>::N;
+  pdl_trigger();
+  pdl_wait();
   long long r = blockIdx.x;
   const T* src = nullptr;
   const T* add = nullptr;
@@ -283,7 +292,7 @@ __global__ void __launch_bounds__(128) assemble_kernel(T* __restrict__ seq, cons
   T* dst = seq + static_cast<long long>(blockIdx.x) * dim;
   for (int i = threadIdx.x * V; i < dim; i += blockDim.x * V) {
     float v[V];
-    Vec<T>::load(src + i, v);
+    Vec<T>::load_plain(src + i, v);
     if (add != nullptr) {
       float a[V];
       Vec<T>::load(add + i, a);
@@ -364,9 +373,12 @@ static int launch_pool(const void* x, void* y, const float* pe, const int64_t* f
   const int grid = grid_for(total, 256);
   const T* xp = static_cast<const T*>(x);
   T* yp = static_cast<T*>(y);
-  if (mode == MAVLM_POOL_BILINEAR)
-    pool_pe_kernel<T, MAVLM_POOL_BILINEAR><<<grid, 256, 0, st>>>(xp, yp, pe, fidx, frames, side, out_side, stride, dim);
-  else if (mode == MAVLM_POOL_AVERAGE)
+  if (mode == MAVLM_POOL_BILINEAR) {
+    LaunchCfg lc;
+    make_launch(lc, dim3(grid), dim3(256), 0, st, 1, 8);
+    MAVLM_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, pool_pe_kernel<T, MAVLM_POOL_BILINEAR>, xp, yp, pe, fidx, frames, side,
+                                     out_side, stride, dim));
+  } else if (mode == MAVLM_POOL_AVERAGE)
     pool_pe_kernel<T, MAVLM_POOL_AVERAGE><<<grid, 256, 0, st>>>(xp, yp, pe, fidx, frames, side, out_side, stride, dim);
   else
     pool_pe_kernel<T, MAVLM_POOL_MAX><<<grid, 256, 0, st>>>(xp, yp, pe, fidx, frames, side, out_side, stride, dim);
@@ -383,10 +395,14 @@ int layernorm_launch(const void* x, const void* gamma, const void* beta, void* y
   MAVLM_REQUIRE((reinterpret_cast<uintptr_t>(gamma) & 15) == 0 && (reinterpret_cast<uintptr_t>(beta) & 15) == 0,
                 MAVLM_E_INVALID, "layernorm: gamma / beta must be 16-byte aligned");
   if (rows == 0) return MAVLM_OK;
-#define MAVLM_LN(TI, TO, CA)                                                                                  \
-  layernorm_kernel<TI, TO, CA><<<ceil_div(rows, LN_WARPS), 32 * LN_WARPS, 2 * dim * sizeof(TO), st>>>(       \
-      static_cast<const TI*>(x), static_cast<const TO*>(gamma), static_cast<const TO*>(beta), static_cast<TO*>(y), \
-      rows, dim, eps)
+  LaunchCfg lc;
+#define MAVLM_LN(TI, TO, CA)                                                                                       \
+  do {                                                                                                             \
+    make_launch(lc, dim3(ceil_div(rows, LN_WARPS)), dim3(32 * LN_WARPS), 2 * dim * sizeof(TO), st, 1, 4);          \
+    MAVLM_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, layernorm_kernel<TI, TO, CA>, static_cast<const TI*>(x),             \
+                                     static_cast<const TO*>(gamma), static_cast<const TO*>(beta),                 \
+                                     static_cast<TO*>(y), rows, dim, eps));                                       \
+  } while (0)
 #define MAVLM_LN_DT(CA)                                                         \
   do {                                                                          \
     if (dtype == MAVLM_F32) MAVLM_LN(float, float, CA);                         \
@@ -437,13 +453,14 @@ int mavlm_add_pe_fwd(const void* x, void* y, const float* pe_table, const int64_
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long total = static_cast<long long>(frames) * tokens * (dim / vec);
   const int grid = grid_for(total, 256);
+  LaunchCfg lc;
+  make_launch(lc, dim3(grid), dim3(256), 0, st, 1, 8);
   if (dtype == MAVLM_F32)
-    add_pe_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), static_cast<float*>(y), pe_table,
-                                               frame_idx, frames, tokens, dim);
+    MAVLM_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, add_pe_kernel<float>, static_cast<const float*>(x),
+                                     static_cast<float*>(y), pe_table, frame_idx, frames, tokens, dim));
   else
-    add_pe_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x),
-                                                       static_cast<__nv_bfloat16*>(y), pe_table, frame_idx, frames,
-                                                       tokens, dim);
+    MAVLM_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, add_pe_kernel<__nv_bfloat16>, static_cast<const __nv_bfloat16*>(x),
+                                     static_cast<__nv_bfloat16*>(y), pe_table, frame_idx, frames, tokens, dim));
   MAVLM_LAUNCH_OK();
   return MAVLM_OK;
 }

@@ -126,6 +126,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched from here on
 
   if (warp == 0) {
     if (elect_one()) {
@@ -230,11 +232,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        auto add_vec32 = [&](const __nv_bfloat16* src) {  // v += src[0..32) (warp-uniform address: one broadcast load)
+        // v += src[0..32).  `dep`: src was written by the previous kernel (resid) -> ordered load, see ld_dep_u4
+        auto add_vec32 = [&](const __nv_bfloat16* src, bool dep) {
           if (full_chunk) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              const uint4 t = __ldg(reinterpret_cast<const uint4*>(src) + g);
+              const uint4 t = dep ? ld_dep_u4(reinterpret_cast<const uint4*>(src) + g)
+                                  : __ldg(reinterpret_cast<const uint4*>(src) + g);
               const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -248,7 +252,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (nc + j < p.N) v[j] += __bfloat162float(src[j]);
           }
         };
-        if (p.bias != nullptr) add_vec32(p.bias + nc);
+        if (p.bias != nullptr) add_vec32(p.bias + nc, false);
         if (p.act == MAVLM_ACT_GELU_ERF && !(p.dbg & 2)) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
@@ -256,8 +260,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
-        if (p.resid != nullptr && row_ok) add_vec32(p.resid + row * p.ldr + nc);
-        if (p.addvec != nullptr) add_vec32(p.addvec + nc);
+        if (p.resid != nullptr && row_ok) add_vec32(p.resid + row * p.ldr + nc, true);
+        if (p.addvec != nullptr) add_vec32(p.addvec + nc, false);
         if (p.dbg & 1) {  // experiment: no global stores (keep the values live)
           float acc_dbg = 0.f;
 #pragma unroll
@@ -406,23 +410,9 @@ static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles * p.batches;
   const int workers_max = sm_count() / CG;
   const int workers = static_cast<int>(tiles < workers_max ? tiles : workers_max);
-  if (CG == 1) {
-    gemm_tc_kernel<BN, A_MN, B_MN, CG><<<workers, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmC, p);
-  } else {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(workers * CG);
-    cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = CG;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    MAVLM_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, A_MN, B_MN, CG>, tmA, tmB, tmC, p));
-  }
+  LaunchCfg lc;
+  make_launch(lc, dim3(workers * CG), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, st, CG, 1);
+  MAVLM_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, gemm_tc_kernel<BN, A_MN, B_MN, CG>, tmA, tmB, tmC, p));
   MAVLM_LAUNCH_OK();
   return MAVLM_OK;
 }

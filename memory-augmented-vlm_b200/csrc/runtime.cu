@@ -3,6 +3,7 @@
 // library also loads on a CPU-only box for the symbol tests).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -23,6 +24,19 @@ void set_error(const char* fmt, ...) {
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   set_error("CUDA error %d (%s) at %s:%d in `%s`", static_cast<int>(e), cudaGetErrorString(e), file, line, what);
   return MAVLM_E_CUDA;
+}
+
+static bool g_pdl_off = false;
+void pdl_force_off(bool off) { g_pdl_off = off; }
+bool pdl_enabled(int family) {
+  static int env = -1, mask = 0xff;
+  if (env < 0) {
+    const char* e = getenv("MAVLM_PDL");
+    env = (e != nullptr && e[0] == '0') ? 0 : 1;
+    const char* m = getenv("MAVLM_PDL_MASK");
+    if (m != nullptr) mask = atoi(m);
+  }
+  return env == 1 && !g_pdl_off && (family == 0 || (mask & family) != 0);
 }
 
 int sm_count() {

@@ -462,28 +462,30 @@ def fam_ab():
         return e0.elapsed_time(e1) / n
 
     run(5)
-    g = pipe.graphed(1, 64)
-    g(x, idx)
+    from mavlm_b200 import GraphedPipeline
 
-    def run_graph(n=10):
+    def graph_ms(gp, n=10):
+        gp(x, idx)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(n):
-            g(None, None)
+            gp(None, None)
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n
 
-    for rnd in range(4):
-        line = f"round {rnd}:"
-        for bn in (0, -1):
-            lib.mavlm_debug_force_gemm_bn(bn)
-            torch.cuda._sleep(20_000_000)
-            line += f"  gemm_tiles={'pair+single' if bn == 0 else 'single only'}: eager {run():.3f} ms"
-        lib.mavlm_debug_force_gemm_bn(0)
-        line += f"  | graph(pair+single) {run_graph():.3f} ms"
-        print(line, flush=True)
+    variants = {}
+    for name, flags in (("pdl", 0), ("no-pdl", 16)):
+        lib.mavlm_debug_set_flags(flags)
+        variants[name] = GraphedPipeline(pipe, 1, 64)       # the launch attributes are baked in at capture time
+    lib.mavlm_debug_set_flags(0)
+    for rnd in range(5):
+        print(f"round {rnd}:  " + "   ".join(f"{name}: {graph_ms(gp):.3f} ms" for name, gp in variants.items()), flush=True)
+    ref = variants["no-pdl"](x, idx)["sequence"].float().clone()
+    out = variants["pdl"](x, idx)["sequence"].float()
+    torch.cuda.synchronize()
+    print("pdl vs no-pdl max abs diff:", float((out - ref).abs().max()))
 
 
 FAMS = {"micro": fam_micro, "ab": fam_ab, "elem": fam_elem, "simt": fam_simt, "gemm": fam_gemm, "attn": fam_attn, "pipe": fam_pipe, "perf": fam_perf}
