@@ -30,8 +30,8 @@ def test_library_exports_every_declared_symbol():
     assert lib.mavlm_version() == 100
     assert lib.mavlm_launch_count() == 0          # nothing has been launched: no compute on the CPU box
     assert lib.mavlm_xattn_workspace_bytes(1, 8, 1568, 6272, 112, _lib.F32) == 8 * 1568 * 6272 * 4
-    # bf16 tier: two partial-result slots per persistent CTA: 11 groups of 13 q-tile CTAs on 148 SMs
-    assert lib.mavlm_xattn_workspace_bytes(1, 8, 1568, 6272, 448, _lib.BF16) == 11 * 13 * 2 * (128 * 448 + 256) * 4
+    # bf16 tier: one partial-result slot + one completion flag per persistent CTA: 11 groups of 13 q-tile CTAs
+    assert lib.mavlm_xattn_workspace_bytes(1, 8, 1568, 6272, 448, _lib.BF16) == 11 * 13 * ((128 * 448 + 256) * 4 + 4)
 
 
 def test_no_cpu_fallback():
