@@ -279,6 +279,14 @@ def run_ours(args):
     launches = launches_per_step * steps                    # kernels replayed inside the timed region
     clocks = sampler.stop() if sampler else None
 
+    if args.timed_only:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": world * FRAMES * steps / (ms_total * 1e-3), "unit": "frames/s",
+                              "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_total / steps,
+                              "note": "--timed-only (profiling run)"}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     for _ in range(3):
         step_e2e()
     streamer.synchronize()
@@ -423,6 +431,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--timed-only", action="store_true",
+                    help="only the device-timed graph replays (no e2e / breakdown / CPU passes): the short run that is "
+                         "put under `ncu` for the per-launch list in profiles/")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

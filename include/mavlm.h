@@ -109,6 +109,26 @@ MAVLM_API int mavlm_assemble_fwd(void* seq, const void* mem, int64_t n_mem_rows,
 MAVLM_API int mavlm_gather_rows_fwd(void* out, int64_t ld_out, const void* embed_table, const void* feats,
                                     const int64_t* row_src, int64_t n_rows, int dim, int dtype, void* stream);
 
+/* ---- frame pre-processing, the producer side of the path: decoded uint8 frames [F, H, W, 3] (the
+ * `.pt` video tensor of extract_video_frames/video_reader_tmp.py:87, fed at train.py:1239) ->
+ * SigLipImageProcessor.preprocess (siglip_encoder.py:47-67): PIL bicubic resize to `size`, rescale 1/255, normalize,
+ * channels-first -> pixel_values [F, 3, out_h, out_w] (f32, or bf16 = the tower's `.to(dtype)`, siglip_encoder.py:585).
+ * Bit-exact with Pillow's two-pass 22-bit fixed-point resampler (uint8 intermediate, horizontal pass first, a pass
+ * skipped when that dimension already matches) and transformers' rescale / normalize arithmetic.
+ *
+ * mavlm_resize_coeffs (host, no CUDA): Pillow's precompute_coeffs + normalize_coeffs_8bpc for one axis.
+ *   bounds int32 [out, 2] = (first input index, tap count), kk int32 [out, ksize_capacity].  Returns ksize (the
+ *   number of columns needed) when bounds / kk are NULL or on success, negative on error.
+ * mavlm_frames_preprocess_fwd: the tables are DEVICE pointers (NULL for an axis whose size already matches);
+ *   tmp: uint8 [F, in_h, out_w, 3] workspace (needed when the width changes); resized_u8: optional uint8
+ *   [F, out_h, out_w, 3] copy of the resized frames (NULL to skip); mean3 / std3: HOST float[3]. */
+MAVLM_API int mavlm_resize_coeffs(int in_size, int out_size, int32_t* bounds, int32_t* kk, int ksize_capacity);
+MAVLM_API int mavlm_frames_preprocess_fwd(const uint8_t* frames, int n_frames, int in_h, int in_w, uint8_t* tmp,
+                                          uint8_t* resized_u8, void* pixel_values, int out_h, int out_w,
+                                          const int32_t* bounds_h, const int32_t* kk_h, int ksize_h,
+                                          const int32_t* bounds_v, const int32_t* kk_v, int ksize_v, double rescale,
+                                          const float* mean3, const float* std3, int out_dtype, void* stream);
+
 /* ======================= backward pass (training: BPTT through the memory, fuser) =======================
  * The reference trains this path with PyTorch autograd (train.py:1694-1728 unfreezes recurrent_memory_transformer,
  * memory_fuser, token_type_embedding; frame features are detached, llava_arch.py:302).  These entry points are

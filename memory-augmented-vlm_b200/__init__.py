@@ -13,6 +13,8 @@ from .modules import (Attention, Config, MemoryFuser, MemoryFuserMLP, Residual, 
                       TransformerProjector, VisionProjector, build_memory_fuser, build_vision_projector,
                       fine_frame_indices, get_2dPool, sample_frame_indices, uniform_segment_variant)
 from .patch import convert_rmt, patch_llava
+from . import preprocess  # noqa: F401
+from .preprocess import SigLipImageProcessor, frames_preprocess
 from .splice import IGNORE_INDEX, IMAGE_TOKEN_INDEX, splice_text_and_vision
 from .pipeline import (FRAME_PROMPT_IDS, MEMORY_PROMPT_IDS, GraphedPipeline, HostStreamEncoder,
                        VisualMemoryPipeline)
@@ -21,5 +23,5 @@ __all__ = [
     "Attention", "Config", "MemoryFuser", "MemoryFuserMLP", "Residual", "TemporalPositionalEncoding", "TransformerLayer",
     "TransformerProjector", "VisionProjector", "build_memory_fuser", "build_vision_projector", "fine_frame_indices",
     "get_2dPool", "sample_frame_indices", "uniform_segment_variant", "VisualMemoryPipeline", "GraphedPipeline", "HostStreamEncoder", "MEMORY_PROMPT_IDS",
-    "FRAME_PROMPT_IDS", "patch_llava", "convert_rmt", "splice_text_and_vision", "IGNORE_INDEX", "IMAGE_TOKEN_INDEX",
+    "FRAME_PROMPT_IDS", "SigLipImageProcessor", "frames_preprocess", "patch_llava", "convert_rmt", "splice_text_and_vision", "IGNORE_INDEX", "IMAGE_TOKEN_INDEX",
 ]

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_ulonglong, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_ulonglong, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmavlm.so")
@@ -56,6 +56,10 @@ PROTOTYPES = {
                                 c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64,
                                 c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int,
                                 c_int, c_int, c_float, c_int, c_void_p, c_size_t, c_void_p]),
+    "mavlm_resize_coeffs": (c_int, [c_int, c_int, c_void_p, c_void_p, c_int]),
+    "mavlm_frames_preprocess_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                            c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_double, c_void_p,
+                                            c_void_p, c_int, c_void_p]),
     "mavlm_debug_force_gemm_bn": (c_int, [c_int]),
     "mavlm_debug_set_flags": (c_int, [c_int]),
     "mavlm_debug_force_attn_groups": (c_int, [c_int]),

@@ -9,8 +9,8 @@
 //                            bf16 or fp32 rows, 16-byte vector stores); two warps per TMEM lane quadrant,
 //                            each taking half of the tile's columns (the erf epilogue of the K=1152
 //                            projector GEMM was epilogue-bound with four warps: 55 % tensor-active)
-// Tiles are rasterised in groups of 16 M-tiles, m-fastest inside a group and sweeping N, so the ~148
-// tiles in flight share ~16 A row-blocks and ~9 W slabs (L2-resident working set of ~30 MB); plain
+// Tiles are rasterised in groups of M-tiles (sized on the host so that a group's A rows stay in L2), m-fastest
+// inside a group and sweeping N, so the tiles in flight share a few A row-blocks and W slabs; plain
 // m-fastest order re-read A once per N-slab wave (3.2 GB of DRAM reads for the 12544x14336x3584 GEMM).
 #include "common.cuh"
 
@@ -20,7 +20,6 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_EPI_WARPS = 8;                         // two warps per TMEM lane quadrant, splitting the columns
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;   // 320
-constexpr int GEMM_GROUP_M = 16;                         // tile rasterisation: sweep N inside groups of 16 M-tiles
 
 struct GemmTcParams {
   int M, N, K;
@@ -33,6 +32,7 @@ struct GemmTcParams {
   int act;
   int out_f32;
   int m_tiles, n_tiles;
+  int group_m;     // M-tiles per rasterisation group
   // general / batched mode (backward pass): problem index = outer * inner + inner_idx
   int batches, inner;
   long long c_outer, c_inner;
@@ -61,9 +61,12 @@ struct GemmCfg {
       STAGES * STAGE_BYTES + GEMM_EPI_WARPS * OUT_STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 1024;
 };
 
-template <int CG>
-__device__ __forceinline__ void gemm_tile_coords(int tile, int m_tiles, int n_tiles, int& m_blk, int& n_blk) {
-  constexpr int GROUP = GEMM_GROUP_M / CG;
+// Tile rasterisation: N is swept inside groups of `group` M-tiles (m-fastest inside a group), so the tiles in
+// flight share `group` A row-blocks and ~workers/group W slabs out of L2, and W is re-read once per group.
+// The host sizes the group so that a group's A rows stay L2-resident through the sweep (gemm_group_m).
+__device__ __forceinline__ void gemm_tile_coords(int tile, int m_tiles, int n_tiles, int group, int& m_blk,
+                                                 int& n_blk) {
+  const int GROUP = group;
   const int per_group = GROUP * n_tiles;
   const int g = tile / per_group, r = tile - g * per_group;
   const int first_m = g * GROUP;
@@ -136,7 +139,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int tile = worker; tile < num_tiles; tile += workers) {
         int m_blk, n_blk;
         const int batch = tile / tiles_per_batch;
-        gemm_tile_coords<CG>(tile - batch * tiles_per_batch, p.m_tiles, p.n_tiles, m_blk, n_blk);
+        gemm_tile_coords(tile - batch * tiles_per_batch, p.m_tiles, p.n_tiles, p.group_m, m_blk, n_blk);
         const int m0 = m_blk * TILE_M + static_cast<int>(rank) * GEMM_BM;
         const int n0 = n_blk * BN + static_cast<int>(rank) * Cfg::B_ROWS;
         const int bi = batch % p.inner, bo = batch / p.inner;
@@ -216,7 +219,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = worker; tile < num_tiles; tile += workers) {
       int m_blk, n_blk;
       const int batch = tile / tiles_per_batch;
-      gemm_tile_coords<CG>(tile - batch * tiles_per_batch, p.m_tiles, p.n_tiles, m_blk, n_blk);
+      gemm_tile_coords(tile - batch * tiles_per_batch, p.m_tiles, p.n_tiles, p.group_m, m_blk, n_blk);
       const int m0 = m_blk * TILE_M + static_cast<int>(rank) * GEMM_BM, n0 = n_blk * BN;
       const long long c_off = (batch / p.inner) * p.c_outer + (batch % p.inner) * p.c_inner;
       const int row = m0 + row_in_tile;
@@ -392,6 +395,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+int gemm_tc_debug_flags();
 template <int BN, bool A_MN, bool B_MN, int CG>
 static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, GemmTcParams p,
                           cudaStream_t st) {
@@ -405,6 +409,18 @@ static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   }
   p.m_tiles = ceil_div(p.M, GEMM_BM * CG);
   p.n_tiles = ceil_div(p.N, BN);
+  {
+    // a group's A rows (group * TILE_M * K bf16) should stay in L2 (126 MB, shared with the W slabs in flight and
+    // the streaming C writes) while N is swept: ~32 MB.  With the old fixed 16 x 128 rows the 12544 x 14336 x
+    // 3584 K/V projection read 1.06 GB from DRAM for 0.19 GB of operands (W re-read once per group).
+    const long long tile_bytes = static_cast<long long>(GEMM_BM) * CG * p.K * 2;
+    long long g = (32ll << 20) / (tile_bytes > 0 ? tile_bytes : 1);
+    const int dbg_g = (gemm_tc_debug_flags() >> 8) & 0xff;
+    if (dbg_g) g = dbg_g;
+    if (g < 2) g = 2;
+    if (g > p.m_tiles) g = p.m_tiles;
+    p.group_m = static_cast<int>(g);
+  }
   if (p.batches < 1) p.batches = 1;
   if (p.inner < 1) p.inner = 1;
   const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles * p.batches;

@@ -240,8 +240,17 @@ class TransformerProjector(nn.Module):
     def initial_state(self, dtype: torch.dtype) -> torch.Tensor:
         """(initial_memory + memory_pos_embed).to(dtype)   (MemoryController.py:123-124) via the PE-add kernel."""
         im = self.initial_memory
-        table = self.memory_pos_embed.reshape(self.num_memory_tokens, self.hidden_size)
-        return ops.add_rows(im if im.dtype == dtype else im.to(dtype), table)
+        pos = self.memory_pos_embed
+        table = pos.reshape(self.num_memory_tokens, self.hidden_size)
+        if torch.is_grad_enabled() and (im.requires_grad or pos.requires_grad):
+            return ops.add_rows(im if im.dtype == dtype else im.to(dtype), table)   # training: part of the graph
+        # inference: the sum only changes when a parameter does -- cached (it was 4 small launches per video)
+        key = (im.data_ptr(), im._version, pos.data_ptr(), pos._version, dtype, im.device)
+        if getattr(self, "_init_state_key", None) != key:
+            with torch.no_grad():
+                self._init_state = ops.add_rows(im if im.dtype == dtype else im.to(dtype), table)
+            self._init_state_key = key
+        return self._init_state
 
     def _update_memory_tokens_with_cache(self, current_memory: torch.Tensor) -> torch.Tensor:
         """Memory evolution (MemoryController.py:89-115): Q = last state, K/V = all cached states.

@@ -149,3 +149,18 @@ def test_sequence_length_formula():
     assert pipe.sequence_length(2, 32) == 10 + 2 * 1568 + 1 + 9 + 32 * 196 + 1 == 9429   # SURVEY.md §3.1 (+4 text = 9433)
     assert pipe.sequence_length(1, 5) == 10 + 1568 + 1 + 9 + 5 * 196 + 1
     assert pipe.sequence_length(3, 32, drop_frames=True) == 10 + 3 * 1568 + 1
+
+
+def test_resize_coefficient_tables_match_the_oracle():
+    """mavlm_resize_coeffs is host code (no GPU): Pillow's precompute_coeffs + normalize_coeffs_8bpc, bit for bit."""
+    import numpy as np
+    from oracle import preprocess_oracle as po
+    lib = _lib.load()
+    for in_size, out_size in ((640, 384), (1280, 384), (200, 384), (97, 384), (384, 384), (1080, 384), (1, 7), (500, 3)):
+        k = lib.mavlm_resize_coeffs(in_size, out_size, None, None, 0)
+        bounds = np.zeros((out_size, 2), dtype=np.int32)
+        kk = np.zeros((out_size, k), dtype=np.int32)
+        assert lib.mavlm_resize_coeffs(in_size, out_size, bounds.ctypes.data, kk.ctypes.data, k) == k
+        k2, b2, kk2 = po.precompute_coeffs(in_size, out_size)
+        assert k == k2 and np.array_equal(bounds, b2) and np.array_equal(kk, kk2)
+    assert lib.mavlm_resize_coeffs(0, 4, None, None, 0) < 0                     # error code, never an exception

@@ -429,6 +429,18 @@ def fam_micro():
             print(f"projector L1 46656x3584x1152 GELU tile {bn} [{name}]: {us:.1f} us {2 * 46656 * 3584 * 1152 / us / 1e6:.0f} TF")
     lib.mavlm_debug_set_flags(0)
     lib.mavlm_debug_force_gemm_bn(0)
+    for (m, n, k) in ((12544, 14336, 3584), (12544, 3584, 3584), (3136, 3584, 14336), (46656, 3584, 1152)):
+        a = torch.randn(m, k, device=dev).bfloat16()
+        w = torch.randn(n, k, device=dev).bfloat16()
+        b = torch.randn(n, device=dev).bfloat16()
+        out = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
+        line = f"gemm {m}x{n}x{k} raster group (pair tiles of 256 rows):"
+        for g in (0, 2, 4, 8, 16, 32, 64):
+            lib.mavlm_debug_set_flags(g << 8)
+            us = graph_time(lambda: ops.linear(a, w, b, out=out), n=4, reps=3)
+            line += f"  g{g}: {us:.0f}us"
+        lib.mavlm_debug_set_flags(0)
+        print(line, flush=True)
     h, dh = 8, 448
     for (bsz, lq, lk) in ((1, 1568, 6272), (1, 1568, 1568), (8, 1568, 6272), (1, 1568, 15680)):
         q = torch.randn(bsz, lq, h * dh, device=dev).bfloat16()
@@ -436,6 +448,12 @@ def fam_micro():
         v = torch.randn(bsz, lk, h * dh, device=dev).bfloat16()
         us = graph_time(lambda: ops.xattn(q, kk, v, h), n=10)
         print(f"xattn B{bsz} {lq}x{lk} dh{dh}: {us:.1f} us {4.0 * bsz * h * lq * lk * dh / us / 1e6:.0f} TF")
+    import mavlm_b200 as M
+    for (f, hh, ww) in ((64, 720, 1280), (64, 360, 640)):
+        fr = torch.randint(0, 256, (f, hh, ww, 3), dtype=torch.uint8, device=dev)
+        us = graph_time(lambda: M.frames_preprocess(fr, dtype=torch.bfloat16), n=3)
+        by = f * 3 * (hh * ww + 2 * hh * 384) + f * 3 * 384 * 384 * 2
+        print(f"frames_preprocess {f}x{hh}x{ww} u8 -> bf16 pixel_values: {us:.1f} us ({us / f:.2f} us/frame) {by / us / 1e3:.0f} GB/s")
     x = torch.randn(64, 729, 3584, device=dev).bfloat16()
     us = graph_time(lambda: ops.pool_pe(x, side=27), n=5)
     print(f"pool F64: {us:.1f} us {64 * (729 + 196) * 3584 * 2 / us / 1e3:.0f} GB/s")
