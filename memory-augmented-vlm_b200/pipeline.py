@@ -232,36 +232,72 @@ class VisualMemoryPipeline(nn.Module):
         return self.memory_forward(z.reshape(b, f, *z.shape[1:]), **kw)
 
     def memory_forward_train(self, z: torch.Tensor, *, drop_frames: bool = False) -> Dict[str, torch.Tensor]:
-        """Differentiable version of memory_forward for training (BPTT): list-based state cache like the
-        reference (MemoryController.py:152-154), every op an autograd.Function backed by libmavlm.so.
-        z [B, F, P, D] are the (detached) pooled + PE'd frames; gradients reach the recurrent memory
-        transformer, the fuser, token_type_embedding, image_newline and embed_tokens (prompt rows)."""
+        """Differentiable version of memory_forward for training (BPTT), BATCHED over the videos: every GEMM /
+        attention runs on all B videos at once (M = B * 1568 rows instead of B launches of 1568), with the same
+        per-video arithmetic as the reference's loop (MemoryController.py:118-158, llava_arch.py:528-557).  Every
+        op is an autograd.Function backed by libmavlm.so.  z [B, F, P, D] are the (detached) pooled + PE'd frames;
+        gradients reach the recurrent memory transformer, the fuser, token_type_embedding, image_newline and
+        embed_tokens (prompt rows).  The state cache is a Python list like the reference's (cap 10, :152-154); the
+        evolution K/V of a state are projected once and reused by later chunks (autograd sums their gradients)."""
         rmt = self.recurrent_memory_transformer
         b, f, p, d = z.shape
-        dev = z.device
+        dev, dtype = z.device, z.dtype
         z = z.detach()                                                  # llava_arch.py:302,481
+        m_slots, lq = rmt.num_memory_tokens, rmt.num_memory_tokens * p
+        heads = rmt.layers[0].memory_segment_fusion_attention.num_attention_heads
+        scale = 1.0 / math.sqrt(d // heads)
+        cap = rmt.cache_size
         pm_ids, pf_ids = self._const_ids(dev)
         fine_idx = fine_frame_indices(f, self.max_fine_frames).to(dev)
         emb = self.token_type_embedding.weight
         newline = self.image_newline
         fz = self.memory_fuser
         bounds = uniform_segment_variant(f, self.chunk_size)
-        seqs, states = [], []
-        for bi in range(b):
-            rmt.memory_cache = []
-            for i in range(len(bounds) - 1):
-                cache, _ = rmt(z[bi, bounds[i]:bounds[i + 1]])
-            cat = torch.cat(cache, dim=0)                               # [n*M, P, D]   llava_arch.py:545
-            hid = ops.linear(cat.reshape(-1, d), fz[0].weight, fz[0].bias, act=ACT_GELU_ERF)
-            mem = ops.linear(hid, fz[2].weight, fz[2].bias, addvec=emb[0])          # + token_type_embedding[0]
-            parts = [self.embed_tokens(pm_ids), mem, newline[None].to(mem.dtype)]
-            if not drop_frames:
-                fine = ops.add_rows(z[bi][fine_idx].reshape(1, -1, d), emb[1][None])  # + token_type_embedding[1]
-                parts += [self.embed_tokens(pf_ids), fine[0], newline[None].to(mem.dtype)]
-            seqs.append(torch.cat(parts, dim=0))
-            states.append(torch.stack(list(cache), dim=0))
-            rmt.memory_cache = []
-        return {"sequence": torch.stack(seqs, dim=0), "states": torch.stack(states, dim=0)}
+        n_chunks = len(bounds) - 1
+        z2 = z.reshape(b, f * p, d)
+
+        packs = [l.memory_segment_fusion_attention.packed() for l in rmt.layers]       # part of the autograd graph
+        dhp = packs[0]["dhp"]
+        hd = heads * dhp
+        kvf = [ops.linear(z2, pk["wkv"], pk["bkv"]) for pk in packs]                    # frame-side K/V, all chunks
+        evo = rmt.memory_update_attention
+        evo_p = evo.packed() if n_chunks > 1 else None
+
+        states: List[torch.Tensor] = []                                 # [B, Lq, D] each
+        state_kv: List[torch.Tensor] = []                               # evolution (k | v) of states[i], projected once
+        mem = rmt.initial_state(dtype).reshape(1, lq, d).expand(b, lq, d)
+        for t in range(n_chunks):
+            if t > 0:
+                while len(state_kv) < len(states):
+                    state_kv.append(ops.linear(states[len(state_kv)], evo_p["wkv"], evo_p["bkv"]))
+                kv = state_kv[0] if len(state_kv) == 1 else torch.cat(state_kv, dim=1)
+                q = ops.linear(mem, evo_p["wq"], evo_p["bq"])
+                ctx, _, _ = ops.xattn(q, kv[..., :hd], kv[..., hd:], heads, head_dim=dhp, scale=scale)
+                mem = evo.residual(ctx, mem, weight=evo_p["wo"])
+            r0, r1 = bounds[t] * p, bounds[t + 1] * p
+            for li, layer in enumerate(rmt.layers):
+                pk = packs[li]
+                q = ops.linear(mem, pk["wq"], pk["bq"])
+                ctx, _, _ = ops.xattn(q, kvf[li][:, r0:r1, :hd], kvf[li][:, r0:r1, hd:], heads, head_dim=dhp, scale=scale)
+                a = layer.memory_segment_fusion_attention.residual(ctx, mem, weight=pk["wo"])
+                up = ops.linear(a, layer.mlp[0].weight, layer.mlp[0].bias, act=layer._act)
+                mem = layer.residual(up, a)
+            states.append(mem)
+            if len(states) > cap:                                       # MemoryController.py:153-154
+                states = states[-cap:]
+                state_kv = state_kv[-(cap - 1):] if cap > 1 else []
+        cat = states[0] if len(states) == 1 else torch.cat(states, dim=1)               # [B, n*Lq, D]  llava_arch.py:545
+        hid = ops.linear(cat, fz[0].weight, fz[0].bias, act=ACT_GELU_ERF)
+        memtok = ops.linear(hid, fz[2].weight, fz[2].bias, addvec=emb[0])              # + token_type_embedding[0]
+        nl = newline[None, None].to(memtok.dtype).expand(b, 1, d)
+        parts = [self.embed_tokens(pm_ids)[None].expand(b, -1, d), memtok, nl]
+        if not drop_frames:
+            fine = z[:, fine_idx].reshape(b, -1, d)
+            fine = ops.add_rows(fine, emb[1][None].expand(b, d))                         # + token_type_embedding[1]
+            parts += [self.embed_tokens(pf_ids)[None].expand(b, -1, d), fine, nl]
+        n = len(states)
+        return {"sequence": torch.cat(parts, dim=1),
+                "states": torch.stack([s_.reshape(b, m_slots, p, d) for s_ in states], dim=1)}
 
     def graphed(self, batch: int, frames: int, *, return_states: bool = False) -> "GraphedPipeline":
         """CUDA-graph replay of forward() for a fixed (batch, frames): the ~45 dependent launches of a step

@@ -408,7 +408,8 @@ def fam_micro():
     tab = torch.randn(8, 64, device=dev)
     idx = torch.arange(8, device=dev)
     print(f"tiny add_pe (launch-to-launch floor): {graph_time(lambda: ops.add_pe(tiny, tab, idx, out=tiny)):.1f} us")
-    for (m, n, k) in ((1568, 3584, 3584), (1568, 14336, 3584), (1568, 3584, 14336)):
+    from mavlm_b200 import _lib as _l
+    for (m, n, k) in ((1568, 3584, 3584), (1568, 14336, 3584), (1568, 3584, 14336), (1568, 7168, 3584), (3136, 3584, 14336)):
         a = torch.randn(m, k, device=dev).bfloat16()
         w = torch.randn(n, k, device=dev).bfloat16()
         b = torch.randn(n, device=dev).bfloat16()
