@@ -16,7 +16,9 @@
  *   - return value: 0 on success, negative MAVLM_E_* otherwise; mavlm_last_error_string() gives
  *     the message for the calling thread.
  *   - dtype: MAVLM_F32 runs the exact fp32 SIMT tier (parity <= 1e-5 vs the fp64 oracle),
- *     MAVLM_BF16 runs the TMA + tcgen05/TMEM tier (bf16 operands, fp32 accumulate/softmax/LN).
+ *     MAVLM_BF16 runs the TMA + tcgen05/TMEM tier (bf16 operands, fp32 accumulate/softmax/LN);
+ *     MAVLM_F16 (the reference inference loader's default dtype, builder.py:27) runs the same tier with fp16
+ *     operands / outputs (forward entry points only).
  *   - there is no CPU fallback and no other-architecture path: a non-sm_100 device is an error.
  */
 #ifndef MAVLM_H_
@@ -32,7 +34,7 @@ extern "C" {
 #define MAVLM_VERSION 100 /* 0.1.0 */
 #define MAVLM_API __attribute__((visibility("default")))
 
-enum { MAVLM_F32 = 0, MAVLM_BF16 = 1 };
+enum { MAVLM_F32 = 0, MAVLM_BF16 = 1, MAVLM_F16 = 2 };
 enum { MAVLM_ACT_NONE = 0, MAVLM_ACT_GELU_ERF = 1, MAVLM_ACT_RELU = 2 };
 enum { MAVLM_POOL_BILINEAR = 0, MAVLM_POOL_AVERAGE = 1, MAVLM_POOL_MAX = 2 };
 enum {

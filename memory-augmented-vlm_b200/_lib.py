@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_ulon
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmavlm.so")
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
 ACT_NONE, ACT_GELU_ERF, ACT_RELU = 0, 1, 2
 POOL_BILINEAR, POOL_AVERAGE, POOL_MAX = 0, 1, 2
 E_INVALID, E_CUDA, E_ARCH, E_INDEX, E_WORKSPACE = -1, -2, -3, -4, -5

@@ -7,7 +7,7 @@ int gemm_fp32(const float* A, long long lda, const float* W, long long ldw, cons
               cudaStream_t st);
 int gemm_bf16_tc(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw,
                  const __nv_bfloat16* bias, const __nv_bfloat16* resid, long long ldr, const __nv_bfloat16* addvec,
-                 void* C, long long ldc, int M, int N, int K, int act, int out_f32, cudaStream_t st);
+                 void* C, long long ldc, int M, int N, int K, int act, int out_f32, cudaStream_t st, int half = 0);
 void gemm_tc_force_bn(int bn);
 void gemm_tc_set_debug(int flags);
 int xattn_fp32(const float* Q, long long ldq, long long qb, const float* K, long long ldk, long long kb, const float* V,
@@ -16,7 +16,7 @@ int xattn_fp32(const float* Q, long long ldq, long long qb, const float* K, long
 int xattn_bf16_tc(const __nv_bfloat16* Q, long long ldq, long long qb, const __nv_bfloat16* K, long long ldk,
                   long long kb, const __nv_bfloat16* V, long long ldv, long long vb, __nv_bfloat16* O, long long ldo,
                   long long ob, float* lse, int batch, int heads, int lq, int lk, int dh, float scale, void* ws,
-                  size_t ws_bytes, cudaStream_t st);
+                  size_t ws_bytes, cudaStream_t st, int half = 0);
 size_t xattn_bf16_workspace_bytes(int batch, int heads, int lq, int lk, int dh);
 void attn_force_groups(int n);
 }  // namespace mavlm
@@ -38,12 +38,12 @@ int mavlm_gemm_bias_act_fwd(const void* A, int64_t lda, const void* W, int64_t l
                      static_cast<const float*>(bias), static_cast<const float*>(resid), ldr,
                      static_cast<const float*>(addvec), static_cast<float*>(C), ldc, M, N, K, act, st);
   }
-  MAVLM_REQUIRE(dtype == MAVLM_BF16, MAVLM_E_INVALID, "gemm: bad dtype %d", dtype);
-  MAVLM_REQUIRE(out_dtype == MAVLM_BF16 || out_dtype == MAVLM_F32, MAVLM_E_INVALID, "gemm: bad out_dtype %d",
-                out_dtype);
+  MAVLM_REQUIRE(dtype == MAVLM_BF16 || dtype == MAVLM_F16, MAVLM_E_INVALID, "gemm: bad dtype %d", dtype);
+  MAVLM_REQUIRE(out_dtype == dtype || out_dtype == MAVLM_F32, MAVLM_E_INVALID, "gemm: bad out_dtype %d", out_dtype);
   return gemm_bf16_tc(static_cast<const __nv_bfloat16*>(A), lda, static_cast<const __nv_bfloat16*>(W), ldw,
                       static_cast<const __nv_bfloat16*>(bias), static_cast<const __nv_bfloat16*>(resid), ldr,
-                      static_cast<const __nv_bfloat16*>(addvec), C, ldc, M, N, K, act, out_dtype == MAVLM_F32, st);
+                      static_cast<const __nv_bfloat16*>(addvec), C, ldc, M, N, K, act, out_dtype == MAVLM_F32, st,
+                      dtype == MAVLM_F16 ? 1 : 0);
 }
 
 size_t mavlm_xattn_workspace_bytes(int batch, int heads, int lq, int lk, int head_dim, int dtype) {
@@ -63,13 +63,14 @@ int mavlm_xattn_fwd(const void* Q, int64_t ldq, int64_t q_batch_stride, const vo
                       k_batch_stride, static_cast<const float*>(V), ldv, v_batch_stride, static_cast<float*>(O), ldo,
                       o_batch_stride, lse, col_scores, batch, heads, lq, lk, head_dim, scale, workspace,
                       workspace_bytes, st);
-  MAVLM_REQUIRE(dtype == MAVLM_BF16, MAVLM_E_INVALID, "xattn: bad dtype %d", dtype);
+  MAVLM_REQUIRE(dtype == MAVLM_BF16 || dtype == MAVLM_F16, MAVLM_E_INVALID, "xattn: bad dtype %d", dtype);
   MAVLM_REQUIRE(col_scores == nullptr, MAVLM_E_INVALID,
                 "xattn: col_scores (frame scores, MemoryController.py:135) is produced by the fp32 tier only");
   return xattn_bf16_tc(static_cast<const __nv_bfloat16*>(Q), ldq, q_batch_stride,
                        static_cast<const __nv_bfloat16*>(K), ldk, k_batch_stride,
                        static_cast<const __nv_bfloat16*>(V), ldv, v_batch_stride, static_cast<__nv_bfloat16*>(O), ldo,
-                       o_batch_stride, lse, batch, heads, lq, lk, head_dim, scale, workspace, workspace_bytes, st);
+                       o_batch_stride, lse, batch, heads, lq, lk, head_dim, scale, workspace, workspace_bytes, st,
+                       dtype == MAVLM_F16 ? 1 : 0);
 }
 
 /* development knob (not part of the reference-facing surface): force the GEMM tile (0 = heuristic).

@@ -56,7 +56,7 @@ constexpr int MERGE_MAX_PARTS = 14;                  // an item is never cut int
 struct AttnTcParams {
   int lq, lk, kv_blocks;
   float scale_log2;
-  __nv_bfloat16* O;
+  void* O;  // 16-bit storage type T of the kernel (bf16 or fp16)
   long long ldo, o_batch;
   float* lse;
   int heads, qtiles, items;
@@ -94,7 +94,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-template <int DH>
+template <int DH, typename T = __nv_bfloat16>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, AttnTcParams p) {
@@ -193,9 +193,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BQ, ATT_BKV, 0, 0);
-      constexpr uint32_t idesc_pv128 = umma_idesc_bf16(ATT_BQ, 128, 0, 1);  // B = two V slices, MN-major
-      constexpr uint32_t idesc_pv64 = umma_idesc_bf16(ATT_BQ, 64, 0, 1);
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BQ, ATT_BKV, 0, 0, Elem16<T>::kUmmaFormat);
+      constexpr uint32_t idesc_pv128 = umma_idesc_bf16(ATT_BQ, 128, 0, 1, Elem16<T>::kUmmaFormat);  // B = two V slices, MN-major
+      constexpr uint32_t idesc_pv64 = umma_idesc_bf16(ATT_BQ, 64, 0, 1, Elem16<T>::kUmmaFormat);
       const uint32_t s_tmem = tmem_base + Cfg::S_COL;
       int stage = 0;
       uint32_t phase = 0;
@@ -338,10 +338,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint4 t;
-          t.x = pack_bf16x2(s[8 * c], s[8 * c + 1]);
-          t.y = pack_bf16x2(s[8 * c + 2], s[8 * c + 3]);
-          t.z = pack_bf16x2(s[8 * c + 4], s[8 * c + 5]);
-          t.w = pack_bf16x2(s[8 * c + 6], s[8 * c + 7]);
+          t.x = Elem16<T>::pack2(s[8 * c], s[8 * c + 1]);
+          t.y = Elem16<T>::pack2(s[8 * c + 2], s[8 * c + 3]);
+          t.z = Elem16<T>::pack2(s[8 * c + 4], s[8 * c + 5]);
+          t.w = Elem16<T>::pack2(s[8 * c + 6], s[8 * c + 7]);
           *reinterpret_cast<uint4*>(prow + (((4 * half + c) ^ (row & 7)) << 4)) = t;  // 128B swizzle (K-major A)
         }
         fence_proxy_async_smem();
@@ -414,7 +414,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
         const float inv = 1.f / l;
         const float own_scale = w_own * inv;
-        __nv_bfloat16* orow = p.O + b * p.o_batch + static_cast<long long>(q) * p.ldo + h * DH;
+        T* orow = static_cast<T*>(p.O) + b * p.o_batch + static_cast<long long>(q) * p.ldo + h * DH;
 #pragma unroll 1
         for (int c = half * OCH; c < (half + 1) * OCH; ++c) {
           uint32_t o[32];
@@ -434,10 +434,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               uint4 t;
-              t.x = pack_bf16x2(v[8 * g], v[8 * g + 1]);
-              t.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
-              t.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
-              t.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
+              t.x = Elem16<T>::pack2(v[8 * g], v[8 * g + 1]);
+              t.y = Elem16<T>::pack2(v[8 * g + 2], v[8 * g + 3]);
+              t.z = Elem16<T>::pack2(v[8 * g + 4], v[8 * g + 5]);
+              t.w = Elem16<T>::pack2(v[8 * g + 6], v[8 * g + 7]);
               reinterpret_cast<uint4*>(orow + c * 32)[g] = t;
             }
           }
@@ -482,14 +482,14 @@ static AttnGeom attn_geometry(int batch, int heads, int lq, int lk) {
   return g;
 }
 
-template <int DH>
+template <int DH, typename T = __nv_bfloat16>
 static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnTcParams& p,
                        cudaStream_t st) {
   using Cfg = AttnCfg<DH>;
   static_assert(Cfg::SMEM_BYTES <= 232448, "attention smem budget exceeded");
   static bool configured = false;
   if (!configured) {
-    MAVLM_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MAVLM_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<DH, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::SMEM_BYTES));
     configured = true;
   }
@@ -497,7 +497,7 @@ static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUt
     MAVLM_CUDA_OK(cudaMemsetAsync(p.flags, 0, static_cast<size_t>(p.groups) * p.gs * sizeof(unsigned int), st));
   LaunchCfg lc;  // (after a memset node the PDL attribute is inert: the edge is then a full dependency)
   make_launch(lc, dim3(p.groups * p.gs), dim3(ATT_THREADS), Cfg::SMEM_BYTES, st, 1, 2);
-  MAVLM_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, attn_tc_kernel<DH>, tmQ, tmK, tmV, p));
+  MAVLM_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, attn_tc_kernel<DH, T>, tmQ, tmK, tmV, p));
   MAVLM_LAUNCH_OK();
   return MAVLM_OK;
 }
@@ -512,7 +512,7 @@ size_t xattn_bf16_workspace_bytes(int batch, int heads, int lq, int lk, int dh) 
 int xattn_bf16_tc(const __nv_bfloat16* Q, long long ldq, long long qb, const __nv_bfloat16* K, long long ldk,
                   long long kb, const __nv_bfloat16* V, long long ldv, long long vb, __nv_bfloat16* O, long long ldo,
                   long long ob, float* lse, int batch, int heads, int lq, int lk, int dh, float scale, void* ws,
-                  size_t ws_bytes, cudaStream_t st) {
+                  size_t ws_bytes, cudaStream_t st, int half) {
   if (batch == 0 || lq == 0) return MAVLM_OK;
   MAVLM_REQUIRE(dh == 128 || dh == 448, MAVLM_E_INVALID,
                 "bf16 xattn: head_dim %d not supported by the tcgen05 kernel (128 or 448; 112 is padded to 128 by "
@@ -547,6 +547,8 @@ int xattn_bf16_tc(const __nv_bfloat16* Q, long long ldq, long long qb, const __n
   p.items = batch * heads * p.qtiles;
   p.ws = static_cast<float*>(ws);
   p.flags = reinterpret_cast<unsigned int*>(p.ws + static_cast<long long>(p.groups) * p.gs * (static_cast<long long>(ATT_BQ) * dh + 2 * ATT_BQ));
+  if (half)
+    return dh == 448 ? launch_attn<448, __half>(tmQ, tmK, tmV, p, st) : launch_attn<128, __half>(tmQ, tmK, tmV, p, st);
   return dh == 448 ? launch_attn<448>(tmQ, tmK, tmV, p, st) : launch_attn<128>(tmQ, tmK, tmV, p, st);
 }
 

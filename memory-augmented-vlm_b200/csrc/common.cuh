@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -364,10 +365,11 @@ __device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t smem_addr, uint32
   return umma_smem_desc(smem_addr, mn_group_stride_bytes, 1024);
 }
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32, M x N tile.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, int a_mn_major, int b_mn_major) {
+// `fmt`: operand format of A and B, 1 = BF16 (default), 0 = F16 (Elem16<T>::kUmmaFormat).
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, int a_mn_major, int b_mn_major, uint32_t fmt = 1) {
   return (1u << 4)                                  // D format: F32
-         | (1u << 7)                                // A format: BF16
-         | (1u << 10)                               // B format: BF16
+         | (fmt << 7)                               // A format
+         | (fmt << 10)                              // B format
          | (static_cast<uint32_t>(a_mn_major) << 15) | (static_cast<uint32_t>(b_mn_major) << 16) |
          (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
@@ -401,6 +403,36 @@ __device__ __forceinline__ float ld_cg_f32(const float* p) {  // L2 load: data w
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+
+// 16-bit storage types of the tensor-core tier: conversions and the UMMA operand-format code
+template <typename T>
+struct Elem16;
+template <>
+struct Elem16<__nv_bfloat16> {
+  static constexpr uint32_t kUmmaFormat = 1;  // kind::f16 A/B format BF16
+  __device__ static __forceinline__ float2 unpack2(uint32_t v) {
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
+  }
+  __device__ static __forceinline__ uint32_t pack2(float lo, float hi) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&t);
+  }
+  __device__ static __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+  __device__ static __forceinline__ __nv_bfloat16 from_float(float v) { return __float2bfloat16(v); }
+};
+template <>
+struct Elem16<__half> {
+  static constexpr uint32_t kUmmaFormat = 0;  // F16
+  __device__ static __forceinline__ float2 unpack2(uint32_t v) {
+    return __half22float2(*reinterpret_cast<const __half2*>(&v));
+  }
+  __device__ static __forceinline__ uint32_t pack2(float lo, float hi) {
+    __half2 t = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&t);
+  }
+  __device__ static __forceinline__ float to_float(__half v) { return __half2float(v); }
+  __device__ static __forceinline__ __half from_float(float v) { return __float2half(v); }
+};
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

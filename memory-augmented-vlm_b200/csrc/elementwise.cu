@@ -51,6 +51,27 @@ struct Vec<__nv_bfloat16> {
   }
 };
 
+template <>
+struct Vec<__half> {
+  static constexpr int N = 8;
+  __device__ static void unpack(const uint4& t, float (&v)[8]) {
+    const __half2* h = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __half22float2(h[i]);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+  __device__ static void load(const __half* p, float (&v)[8]) { unpack(__ldg(reinterpret_cast<const uint4*>(p)), v); }
+  __device__ static void load_plain(const __half* p, float (&v)[8]) { unpack(ld_dep_u4(p), v); }
+  __device__ static void store(__half* p, const float (&v)[8]) {
+    uint4 t;
+    t.x = Elem16<__half>::pack2(v[0], v[1]); t.y = Elem16<__half>::pack2(v[2], v[3]);
+    t.z = Elem16<__half>::pack2(v[4], v[5]); t.w = Elem16<__half>::pack2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+};
+
 // ---------------------------------------------------------------------------------------
 // K2 + K3: channels-last spatial pool (+ PE).  One thread per (frame, out token, 16-byte
 // channel group); the 4 bilinear taps are 4 independent 16-byte loads.
@@ -181,14 +202,14 @@ __global__ void __launch_bounds__(32 * LN_WARPS, 3) layernorm_kernel(const TI* _
   for (int c = 0; c < CACHE; ++c) {
     const int i = (c * 32 + lane) * 4;
     if (active && i < dim) {
-      if (sizeof(TI) == 4) {
+      if constexpr (sizeof(TI) == 4) {
         const uint4 t = ld_dep_u4(reinterpret_cast<const float*>(xr) + i);
         v[c][0] = __uint_as_float(t.x); v[c][1] = __uint_as_float(t.y);
         v[c][2] = __uint_as_float(t.z); v[c][3] = __uint_as_float(t.w);
       } else {
-        uint2 t = ld_dep_u2(reinterpret_cast<const __nv_bfloat16*>(xr) + i);
-        float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&t.x));
-        float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&t.y));
+        uint2 t = ld_dep_u2(reinterpret_cast<const uint16_t*>(xr) + i);
+        float2 a = Elem16<TO>::unpack2(t.x);   // a 16-bit input has the output's type
+        float2 b = Elem16<TO>::unpack2(t.y);
         v[c][0] = a.x; v[c][1] = a.y; v[c][2] = b.x; v[c][3] = b.y;
       }
       s += (v[c][0] + v[c][1]) + (v[c][2] + v[c][3]);
@@ -225,30 +246,30 @@ __global__ void __launch_bounds__(32 * LN_WARPS, 3) layernorm_kernel(const TI* _
     const int i = (c * 32 + lane) * 4;
     if (i < dim) {
       float g[4], b[4], o[4];
-      if (sizeof(TO) == 4) {
+      if constexpr (sizeof(TO) == 4) {
         const float4 tg = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sg) + i);
         const float4 tb = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sb) + i);
         g[0] = tg.x; g[1] = tg.y; g[2] = tg.z; g[3] = tg.w;
         b[0] = tb.x; b[1] = tb.y; b[2] = tb.z; b[3] = tb.w;
       } else {
-        const uint2 tg = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(sg) + i);
-        const uint2 tb = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(sb) + i);
-        const float2 g0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&tg.x));
-        const float2 g1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&tg.y));
-        const float2 b0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&tb.x));
-        const float2 b1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&tb.y));
+        const uint2 tg = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(sg) + i);
+        const uint2 tb = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(sb) + i);
+        const float2 g0 = Elem16<TO>::unpack2(tg.x);
+        const float2 g1 = Elem16<TO>::unpack2(tg.y);
+        const float2 b0 = Elem16<TO>::unpack2(tb.x);
+        const float2 b1 = Elem16<TO>::unpack2(tb.y);
         g[0] = g0.x; g[1] = g0.y; g[2] = g1.x; g[3] = g1.y;
         b[0] = b0.x; b[1] = b0.y; b[2] = b1.x; b[3] = b1.y;
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) o[k] = (v[c][k] - mean) * rstd * g[k] + b[k];
-      if (sizeof(TO) == 4) {
+      if constexpr (sizeof(TO) == 4) {
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(yr) + i) = make_float4(o[0], o[1], o[2], o[3]);
       } else {
         uint2 t;
-        t.x = pack_bf16x2(o[0], o[1]);
-        t.y = pack_bf16x2(o[2], o[3]);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(yr) + i) = t;
+        t.x = Elem16<TO>::pack2(o[0], o[1]);
+        t.y = Elem16<TO>::pack2(o[2], o[3]);
+        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(yr) + i) = t;
       }
     }
   }
@@ -303,33 +324,34 @@ __global__ void __launch_bounds__(128) assemble_kernel(T* __restrict__ seq, cons
   }
 }
 
-// dtype conversion (fp32 <-> bf16), 8 elements per thread
+// dtype conversion (fp32 <-> bf16 / fp16), 8 elements per thread
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long n) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 8;
   for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 8; i < n; i += stride) {
     if (i + 8 <= n) {
       float v[8];
-      if (sizeof(TI) == 4) {
+      if constexpr (sizeof(TI) == 4) {
         const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + i);
         const float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + i + 4);
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
       } else {
-        Vec<__nv_bfloat16>::load(reinterpret_cast<const __nv_bfloat16*>(x) + i, v);
+        Vec<TI>::load(x + i, v);
       }
-      if (sizeof(TO) == 4) {
+      if constexpr (sizeof(TO) == 4) {
         float* o = reinterpret_cast<float*>(y) + i;
         *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
         *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
       } else {
-        Vec<__nv_bfloat16>::store(reinterpret_cast<__nv_bfloat16*>(y) + i, v);
+        Vec<TO>::store(y + i, v);
       }
     } else {
       for (long long k = i; k < n; ++k) {
-        float f = sizeof(TI) == 4 ? reinterpret_cast<const float*>(x)[k]
-                                  : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[k]);
-        if (sizeof(TO) == 4) reinterpret_cast<float*>(y)[k] = f;
-        else reinterpret_cast<__nv_bfloat16*>(y)[k] = __float2bfloat16(f);
+        float f;
+        if constexpr (sizeof(TI) == 4) f = reinterpret_cast<const float*>(x)[k];
+        else f = Elem16<TI>::to_float(x[k]);
+        if constexpr (sizeof(TO) == 4) reinterpret_cast<float*>(y)[k] = f;
+        else y[k] = Elem16<TO>::from_float(f);
       }
     }
   }
@@ -357,6 +379,15 @@ __global__ void __launch_bounds__(128) gather_rows_kernel(T* __restrict__ out, l
     Vec<T>::store(dst + i, v);
   }
 }
+
+// run `expr` with T bound to the storage type of `dtype`
+#define MAVLM_DISPATCH_DTYPE(dtype, ...)                         \
+  do {                                                           \
+    if ((dtype) == MAVLM_F32) { using T = float; __VA_ARGS__; }  \
+    else if ((dtype) == MAVLM_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+    else { using T = __half; __VA_ARGS__; }                      \
+  } while (0)
+static inline bool dtype_ok(int dtype) { return dtype == MAVLM_F32 || dtype == MAVLM_BF16 || dtype == MAVLM_F16; }
 
 static int grid_for(long long total_threads, int block) {
   long long b = (total_threads + block - 1) / block;
@@ -391,7 +422,7 @@ int layernorm_launch(const void* x, const void* gamma, const void* beta, void* y
   MAVLM_REQUIRE(dim % 4 == 0 && dim > 0 && dim <= 128 * 32, MAVLM_E_INVALID,
                 "layernorm: dim %d must be a multiple of 4 and <= 4096", dim);
   MAVLM_REQUIRE(x_dtype == MAVLM_F32 || x_dtype == dtype, MAVLM_E_INVALID, "layernorm: x_dtype must be f32 or dtype");
-  MAVLM_REQUIRE(dtype == MAVLM_F32 || dim % 8 == 0, MAVLM_E_INVALID, "layernorm: bf16 dim %d must be a multiple of 8", dim);
+  MAVLM_REQUIRE(dtype == MAVLM_F32 || dim % 8 == 0, MAVLM_E_INVALID, "layernorm: 16-bit dim %d must be a multiple of 8", dim);
   MAVLM_REQUIRE((reinterpret_cast<uintptr_t>(gamma) & 15) == 0 && (reinterpret_cast<uintptr_t>(beta) & 15) == 0,
                 MAVLM_E_INVALID, "layernorm: gamma / beta must be 16-byte aligned");
   if (rows == 0) return MAVLM_OK;
@@ -406,8 +437,10 @@ int layernorm_launch(const void* x, const void* gamma, const void* beta, void* y
 #define MAVLM_LN_DT(CA)                                                         \
   do {                                                                          \
     if (dtype == MAVLM_F32) MAVLM_LN(float, float, CA);                         \
-    else if (x_dtype == MAVLM_F32) MAVLM_LN(float, __nv_bfloat16, CA);          \
-    else MAVLM_LN(__nv_bfloat16, __nv_bfloat16, CA);                            \
+    else if (dtype == MAVLM_BF16 && x_dtype == MAVLM_F32) MAVLM_LN(float, __nv_bfloat16, CA); \
+    else if (dtype == MAVLM_BF16) MAVLM_LN(__nv_bfloat16, __nv_bfloat16, CA);   \
+    else if (x_dtype == MAVLM_F32) MAVLM_LN(float, __half, CA);                 \
+    else MAVLM_LN(__half, __half, CA);                                          \
   } while (0)
   if (dim <= 128 * 8) MAVLM_LN_DT(8);
   else if (dim <= 128 * 28) MAVLM_LN_DT(28);
@@ -426,7 +459,7 @@ extern "C" {
 
 int mavlm_pool_pe_fwd(const void* x, void* y, const float* pe_table, const int64_t* frame_idx, int frames, int side,
                       int out_side, int stride, int dim, int mode, int dtype, void* stream) {
-  MAVLM_REQUIRE(dtype == MAVLM_F32 || dtype == MAVLM_BF16, MAVLM_E_INVALID, "pool_pe: bad dtype %d", dtype);
+  MAVLM_REQUIRE(dtype_ok(dtype), MAVLM_E_INVALID, "pool_pe: bad dtype %d", dtype);
   MAVLM_REQUIRE(mode >= MAVLM_POOL_BILINEAR && mode <= MAVLM_POOL_MAX, MAVLM_E_INVALID,
                 "Unexpected mm_spatial_pool_mode: %d", mode);
   const int vec = dtype == MAVLM_F32 ? 4 : 8;
@@ -438,14 +471,12 @@ int mavlm_pool_pe_fwd(const void* x, void* y, const float* pe_table, const int64
     MAVLM_REQUIRE(out_side * stride <= side, MAVLM_E_INVALID, "pool_pe: window exceeds the input");
   if (frames == 0) return MAVLM_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return dtype == MAVLM_F32
-             ? launch_pool<float>(x, y, pe_table, frame_idx, frames, side, out_side, stride, dim, mode, st)
-             : launch_pool<__nv_bfloat16>(x, y, pe_table, frame_idx, frames, side, out_side, stride, dim, mode, st);
+  MAVLM_DISPATCH_DTYPE(dtype, return launch_pool<T>(x, y, pe_table, frame_idx, frames, side, out_side, stride, dim, mode, st));
 }
 
 int mavlm_add_pe_fwd(const void* x, void* y, const float* pe_table, const int64_t* frame_idx, int frames, int tokens,
                      int dim, int dtype, void* stream) {
-  MAVLM_REQUIRE(dtype == MAVLM_F32 || dtype == MAVLM_BF16, MAVLM_E_INVALID, "add_pe: bad dtype %d", dtype);
+  MAVLM_REQUIRE(dtype_ok(dtype), MAVLM_E_INVALID, "add_pe: bad dtype %d", dtype);
   const int vec = dtype == MAVLM_F32 ? 4 : 8;
   MAVLM_REQUIRE(dim > 0 && dim % vec == 0, MAVLM_E_INVALID, "add_pe: dim %d must be a multiple of %d", dim, vec);
   MAVLM_REQUIRE(pe_table != nullptr && frame_idx != nullptr, MAVLM_E_INVALID, "add_pe: NULL table / indices");
@@ -455,57 +486,56 @@ int mavlm_add_pe_fwd(const void* x, void* y, const float* pe_table, const int64_
   const int grid = grid_for(total, 256);
   LaunchCfg lc;
   make_launch(lc, dim3(grid), dim3(256), 0, st, 1, 8);
-  if (dtype == MAVLM_F32)
-    MAVLM_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, add_pe_kernel<float>, static_cast<const float*>(x),
-                                     static_cast<float*>(y), pe_table, frame_idx, frames, tokens, dim));
-  else
-    MAVLM_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, add_pe_kernel<__nv_bfloat16>, static_cast<const __nv_bfloat16*>(x),
-                                     static_cast<__nv_bfloat16*>(y), pe_table, frame_idx, frames, tokens, dim));
+  MAVLM_DISPATCH_DTYPE(dtype, MAVLM_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, add_pe_kernel<T>, static_cast<const T*>(x),
+                                                              static_cast<T*>(y), pe_table, frame_idx, frames, tokens,
+                                                              dim)));
   MAVLM_LAUNCH_OK();
   return MAVLM_OK;
 }
 
 int mavlm_gather_rows_fwd(void* out, int64_t ld_out, const void* embed_table, const void* feats, const int64_t* row_src,
                           int64_t n_rows, int dim, int dtype, void* stream) {
-  MAVLM_REQUIRE(dtype == MAVLM_F32 || dtype == MAVLM_BF16, MAVLM_E_INVALID, "gather_rows: bad dtype %d", dtype);
+  MAVLM_REQUIRE(dtype_ok(dtype), MAVLM_E_INVALID, "gather_rows: bad dtype %d", dtype);
   const int vec = dtype == MAVLM_F32 ? 4 : 8;
   MAVLM_REQUIRE(dim > 0 && dim % vec == 0 && ld_out % vec == 0, MAVLM_E_INVALID,
                 "gather_rows: dim %d / ld_out must be multiples of %d", dim, vec);
   if (n_rows == 0) return MAVLM_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == MAVLM_F32)
-    gather_rows_kernel<float><<<static_cast<unsigned>(n_rows), 128, 0, st>>>(
-        static_cast<float*>(out), ld_out, static_cast<const float*>(embed_table), static_cast<const float*>(feats),
-        row_src, dim);
-  else
-    gather_rows_kernel<__nv_bfloat16><<<static_cast<unsigned>(n_rows), 128, 0, st>>>(
-        static_cast<__nv_bfloat16*>(out), ld_out, static_cast<const __nv_bfloat16*>(embed_table),
-        static_cast<const __nv_bfloat16*>(feats), row_src, dim);
+  MAVLM_DISPATCH_DTYPE(dtype, (gather_rows_kernel<T><<<static_cast<unsigned>(n_rows), 128, 0, st>>>(
+                                  static_cast<T*>(out), ld_out, static_cast<const T*>(embed_table),
+                                  static_cast<const T*>(feats), row_src, dim)));
   MAVLM_LAUNCH_OK();
   return MAVLM_OK;
 }
 
 int mavlm_cast_fwd(const void* x, void* y, int64_t n, int src_dtype, int dst_dtype, void* stream) {
-  MAVLM_REQUIRE((src_dtype == MAVLM_F32 || src_dtype == MAVLM_BF16) && (dst_dtype == MAVLM_F32 || dst_dtype == MAVLM_BF16) &&
-                    src_dtype != dst_dtype, MAVLM_E_INVALID, "cast: dtypes must be f32 <-> bf16");
+  MAVLM_REQUIRE(dtype_ok(src_dtype) && dtype_ok(dst_dtype) && src_dtype != dst_dtype &&
+                    (src_dtype == MAVLM_F32 || dst_dtype == MAVLM_F32),
+                MAVLM_E_INVALID, "cast: dtypes must be f32 <-> bf16 / f16");
   MAVLM_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
                 MAVLM_E_INVALID, "cast: pointers must be 16-byte aligned");
   if (n == 0) return MAVLM_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = grid_for((n + 7) / 8, 256);
-  if (src_dtype == MAVLM_F32)
-    cast_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const float*>(x),
-                                                             static_cast<__nv_bfloat16*>(y), n);
-  else
+  if (src_dtype == MAVLM_F32) {
+    if (dst_dtype == MAVLM_BF16)
+      cast_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const float*>(x),
+                                                               static_cast<__nv_bfloat16*>(y), n);
+    else
+      cast_kernel<float, __half><<<grid, 256, 0, st>>>(static_cast<const float*>(x), static_cast<__half*>(y), n);
+  } else if (src_dtype == MAVLM_BF16) {
     cast_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x),
                                                              static_cast<float*>(y), n);
+  } else {
+    cast_kernel<__half, float><<<grid, 256, 0, st>>>(static_cast<const __half*>(x), static_cast<float*>(y), n);
+  }
   MAVLM_LAUNCH_OK();
   return MAVLM_OK;
 }
 
 int mavlm_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, int rows, int dim, float eps,
                         int x_dtype, int dtype, void* stream) {
-  MAVLM_REQUIRE(dtype == MAVLM_F32 || dtype == MAVLM_BF16, MAVLM_E_INVALID, "layernorm: bad dtype %d", dtype);
+  MAVLM_REQUIRE(dtype_ok(dtype), MAVLM_E_INVALID, "layernorm: bad dtype %d", dtype);
   return layernorm_launch(x, gamma, beta, y, rows, dim, eps, x_dtype, dtype, static_cast<cudaStream_t>(stream));
 }
 
@@ -513,24 +543,18 @@ int mavlm_assemble_fwd(void* seq, const void* mem, int64_t n_mem_rows, const voi
                        int n_fine, int tokens, const void* type_emb, const void* newline, const void* embed_table,
                        const int64_t* prompt_mem_ids, int n_prompt_mem, const int64_t* prompt_frm_ids,
                        int n_prompt_frm, int dim, int drop_frames, int dtype, void* stream) {
-  MAVLM_REQUIRE(dtype == MAVLM_F32 || dtype == MAVLM_BF16, MAVLM_E_INVALID, "assemble: bad dtype %d", dtype);
+  MAVLM_REQUIRE(dtype_ok(dtype), MAVLM_E_INVALID, "assemble: bad dtype %d", dtype);
   const int vec = dtype == MAVLM_F32 ? 4 : 8;
   MAVLM_REQUIRE(dim > 0 && dim % vec == 0, MAVLM_E_INVALID, "assemble: dim %d must be a multiple of %d", dim, vec);
   long long rows = n_prompt_mem + n_mem_rows + 1;
   if (!drop_frames) rows += n_prompt_frm + static_cast<long long>(n_fine) * tokens + 1;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == MAVLM_F32)
-    assemble_kernel<float><<<static_cast<unsigned>(rows), 128, 0, st>>>(
-        static_cast<float*>(seq), static_cast<const float*>(mem), n_mem_rows, static_cast<const float*>(frames),
-        fine_idx, n_fine, tokens, static_cast<const float*>(type_emb), static_cast<const float*>(newline),
-        static_cast<const float*>(embed_table), prompt_mem_ids, n_prompt_mem, prompt_frm_ids, n_prompt_frm, dim);
-  else
-    assemble_kernel<__nv_bfloat16><<<static_cast<unsigned>(rows), 128, 0, st>>>(
-        static_cast<__nv_bfloat16*>(seq), static_cast<const __nv_bfloat16*>(mem), n_mem_rows,
-        static_cast<const __nv_bfloat16*>(frames), fine_idx, n_fine, tokens,
-        static_cast<const __nv_bfloat16*>(type_emb), static_cast<const __nv_bfloat16*>(newline),
-        static_cast<const __nv_bfloat16*>(embed_table), prompt_mem_ids, n_prompt_mem, prompt_frm_ids, n_prompt_frm,
-        dim);
+  MAVLM_DISPATCH_DTYPE(dtype, (assemble_kernel<T><<<static_cast<unsigned>(rows), 128, 0, st>>>(
+                                  static_cast<T*>(seq), static_cast<const T*>(mem), n_mem_rows,
+                                  static_cast<const T*>(frames), fine_idx, n_fine, tokens,
+                                  static_cast<const T*>(type_emb), static_cast<const T*>(newline),
+                                  static_cast<const T*>(embed_table), prompt_mem_ids, n_prompt_mem, prompt_frm_ids,
+                                  n_prompt_frm, dim)));
   MAVLM_LAUNCH_OK();
   return MAVLM_OK;
 }

@@ -23,10 +23,11 @@ constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;   // 320
 
 struct GemmTcParams {
   int M, N, K;
-  const __nv_bfloat16* bias;
-  const __nv_bfloat16* resid;
+  const void* bias;      // bias / resid / addvec: 16-bit storage type T of the kernel (bf16 or fp16)
+  const void* resid;
   long long ldr;
-  const __nv_bfloat16* addvec;
+  const void* addvec;
+  int half;        // 1: operands / outputs are fp16 (kernels instantiated with T = __half)
   void* C;
   long long ldc;
   int act;
@@ -78,7 +79,7 @@ __device__ __forceinline__ void gemm_tile_coords(int tile, int m_tiles, int n_ti
 // A_MN / B_MN: the operand is stored with its M (resp. N) index contiguous ([K, M] / [K, N] row-major: the
 // transposed operands of dgrad / wgrad / attention backward).  Such a tile is loaded as 64x64 boxes
 // [64 k-rows x 64 m] and consumed as an MN-major UMMA operand (8-k-row atoms of 1 KB, 64-wide M groups 8 KB apart).
-template <int BN, bool A_MN, bool B_MN, int CG>
+template <int BN, bool A_MN, bool B_MN, int CG, typename T = __nv_bfloat16>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, GemmTcParams p) {
@@ -176,7 +177,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     if (rank == 0 && elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN, A_MN ? 1 : 0, B_MN ? 1 : 0, Elem16<T>::kUmmaFormat);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -236,26 +237,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         // v += src[0..32).  `dep`: src was written by the previous kernel (resid) -> ordered load, see ld_dep_u4
-        auto add_vec32 = [&](const __nv_bfloat16* src, bool dep) {
+        auto add_vec32 = [&](const T* src, bool dep) {
           if (full_chunk) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               const uint4 t = dep ? ld_dep_u4(reinterpret_cast<const uint4*>(src) + g)
                                   : __ldg(reinterpret_cast<const uint4*>(src) + g);
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+              const uint32_t* h = reinterpret_cast<const uint32_t*>(&t);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float2 f = __bfloat1622float2(h[e]);
+                const float2 f = Elem16<T>::unpack2(h[e]);
                 v[g * 8 + 2 * e] += f.x;
                 v[g * 8 + 2 * e + 1] += f.y;
               }
             }
           } else {
             for (int j = 0; j < 32; ++j)
-              if (nc + j < p.N) v[j] += __bfloat162float(src[j]);
+              if (nc + j < p.N) v[j] += Elem16<T>::to_float(src[j]);
           }
         };
-        if (p.bias != nullptr) add_vec32(p.bias + nc, false);
+        if (p.bias != nullptr) add_vec32(static_cast<const T*>(p.bias) + nc, false);
         if (p.act == MAVLM_ACT_GELU_ERF && !(p.dbg & 2)) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
@@ -263,8 +264,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
-        if (p.resid != nullptr && row_ok) add_vec32(p.resid + row * p.ldr + nc, true);
-        if (p.addvec != nullptr) add_vec32(p.addvec + nc, false);
+        if (p.resid != nullptr && row_ok) add_vec32(static_cast<const T*>(p.resid) + row * p.ldr + nc, true);
+        if (p.addvec != nullptr) add_vec32(static_cast<const T*>(p.addvec) + nc, false);
         if (p.dbg & 1) {  // experiment: no global stores (keep the values live)
           float acc_dbg = 0.f;
 #pragma unroll
@@ -298,10 +299,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               uint4 t;
-              t.x = pack_bf16x2(v[8 * g], v[8 * g + 1]);
-              t.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
-              t.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
-              t.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
+              t.x = Elem16<T>::pack2(v[8 * g], v[8 * g + 1]);
+              t.y = Elem16<T>::pack2(v[8 * g + 2], v[8 * g + 3]);
+              t.z = Elem16<T>::pack2(v[8 * g + 4], v[8 * g + 5]);
+              t.w = Elem16<T>::pack2(v[8 * g + 6], v[8 * g + 7]);
               *reinterpret_cast<uint4*>(dst + ((g ^ ((lane >> 1) & 3)) << 4)) = t;  // 64B swizzle
             }
             fence_proxy_async_smem();
@@ -328,24 +329,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (nc + j < p.N) cp[j] = v[j];
           }
         } else {
-          __nv_bfloat16* cp = static_cast<__nv_bfloat16*>(p.C) + c_off + row * p.ldc + nc;
+          T* cp = static_cast<T*>(p.C) + c_off + row * p.ldc + nc;
           if (p.accumulate) {
             for (int j = 0; j < 32; ++j)
-              if (nc + j < p.N) v[j] += __bfloat162float(cp[j]);
+              if (nc + j < p.N) v[j] += Elem16<T>::to_float(cp[j]);
           }
           if (full_chunk) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               uint4 t;
-              t.x = pack_bf16x2(v[8 * g], v[8 * g + 1]);
-              t.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
-              t.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
-              t.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
+              t.x = Elem16<T>::pack2(v[8 * g], v[8 * g + 1]);
+              t.y = Elem16<T>::pack2(v[8 * g + 2], v[8 * g + 3]);
+              t.z = Elem16<T>::pack2(v[8 * g + 4], v[8 * g + 5]);
+              t.w = Elem16<T>::pack2(v[8 * g + 6], v[8 * g + 7]);
               reinterpret_cast<uint4*>(cp)[g] = t;
             }
           } else {
             for (int j = 0; j < 32; ++j)
-              if (nc + j < p.N) cp[j] = __float2bfloat16(v[j]);
+              if (nc + j < p.N) cp[j] = Elem16<T>::from_float(v[j]);
           }
         }
       };
@@ -396,15 +397,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 int gemm_tc_debug_flags();
-template <int BN, bool A_MN, bool B_MN, int CG>
+template <int BN, bool A_MN, bool B_MN, int CG, typename T = __nv_bfloat16>
 static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, GemmTcParams p,
                           cudaStream_t st) {
   using Cfg = GemmCfg<BN, CG>;
   static_assert(Cfg::SMEM_BYTES <= 232448, "gemm smem budget exceeded");
   static bool configured = false;
   if (!configured) {
-    MAVLM_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::SMEM_BYTES));
+    MAVLM_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN, CG, T>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
   p.m_tiles = ceil_div(p.M, GEMM_BM * CG);
@@ -428,7 +429,7 @@ static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   const int workers = static_cast<int>(tiles < workers_max ? tiles : workers_max);
   LaunchCfg lc;
   make_launch(lc, dim3(workers * CG), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, st, CG, 1);
-  MAVLM_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, gemm_tc_kernel<BN, A_MN, B_MN, CG>, tmA, tmB, tmC, p));
+  MAVLM_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, gemm_tc_kernel<BN, A_MN, B_MN, CG, T>, tmA, tmB, tmC, p));
   MAVLM_LAUNCH_OK();
   return MAVLM_OK;
 }
@@ -437,6 +438,21 @@ template <bool A_MN, bool B_MN>
 static int dispatch_bn(int bn, int cg, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                        const GemmTcParams& p, cudaStream_t st) {
   if constexpr (!A_MN && !B_MN) {
+    if (p.half) {  // fp16 operands: forward (K-major) GEMMs only
+      if (cg == 2) {
+        switch (bn) {
+          case 256: return launch_gemm_tc<256, false, false, 2, __half>(tmA, tmB, tmC, p, st);
+          case 192: return launch_gemm_tc<192, false, false, 2, __half>(tmA, tmB, tmC, p, st);
+          default:  return launch_gemm_tc<128, false, false, 2, __half>(tmA, tmB, tmC, p, st);
+        }
+      }
+      switch (bn) {
+        case 256: return launch_gemm_tc<256, false, false, 1, __half>(tmA, tmB, tmC, p, st);
+        case 192: return launch_gemm_tc<192, false, false, 1, __half>(tmA, tmB, tmC, p, st);
+        case 128: return launch_gemm_tc<128, false, false, 1, __half>(tmA, tmB, tmC, p, st);
+        default:  return launch_gemm_tc<64, false, false, 1, __half>(tmA, tmB, tmC, p, st);
+      }
+    }
     if (cg == 2) {
       switch (bn) {
         case 256: return launch_gemm_tc<256, false, false, 2>(tmA, tmB, tmC, p, st);
@@ -554,9 +570,10 @@ int gemm_tc_general(const __nv_bfloat16* A, long long lda, bool a_mn, const __nv
 
 int gemm_bf16_tc(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw,
                  const __nv_bfloat16* bias, const __nv_bfloat16* resid, long long ldr, const __nv_bfloat16* addvec,
-                 void* C, long long ldc, int M, int N, int K, int act, int out_f32, cudaStream_t st) {
+                 void* C, long long ldc, int M, int N, int K, int act, int out_f32, cudaStream_t st, int half) {
   MAVLM_REQUIRE(K > 0 && K % 8 == 0, MAVLM_E_INVALID, "bf16 gemm: K (%d) must be a multiple of 8", K);
   GemmTcParams p{};
+  p.half = half;
   p.M = M; p.N = N; p.K = K;
   p.bias = bias; p.resid = resid; p.ldr = ldr; p.addvec = addvec;
   p.C = C; p.ldc = ldc; p.act = act; p.out_f32 = out_f32;

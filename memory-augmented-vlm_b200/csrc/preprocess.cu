@@ -229,8 +229,8 @@ int mavlm_frames_preprocess_fwd(const uint8_t* frames, int n_frames, int in_h, i
                                 const int32_t* bounds_h, const int32_t* kk_h, int ksize_h, const int32_t* bounds_v,
                                 const int32_t* kk_v, int ksize_v, double rescale, const float* mean3,
                                 const float* std3, int out_dtype, void* stream) {
-  MAVLM_REQUIRE(out_dtype == MAVLM_F32 || out_dtype == MAVLM_BF16, MAVLM_E_INVALID, "preprocess: bad dtype %d",
-                out_dtype);
+  MAVLM_REQUIRE(out_dtype == MAVLM_F32 || out_dtype == MAVLM_BF16 || out_dtype == MAVLM_F16, MAVLM_E_INVALID,
+                "preprocess: bad dtype %d", out_dtype);
   MAVLM_REQUIRE(n_frames >= 0 && in_h > 0 && in_w > 0 && out_h > 0 && out_w > 0, MAVLM_E_INVALID,
                 "preprocess: bad geometry");
   MAVLM_REQUIRE(mean3 != nullptr && std3 != nullptr, MAVLM_E_INVALID, "preprocess: NULL mean / std");
@@ -260,6 +260,10 @@ int mavlm_frames_preprocess_fwd(const uint8_t* frames, int n_frames, int in_h, i
     resize_v_norm_kernel<float><<<rs_grid(total), 256, 0, st>>>(vin, resized_u8, static_cast<float*>(pixel_values),
                                                                 bounds_v, kk_v, kv, n_frames, in_h, out_h, out_w, rescale,
                                                                 mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2]);
+  else if (out_dtype == MAVLM_F16)
+    resize_v_norm_kernel<__half><<<rs_grid(total), 256, 0, st>>>(
+        vin, resized_u8, static_cast<__half*>(pixel_values), bounds_v, kk_v, kv, n_frames, in_h, out_h, out_w, rescale,
+        mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2]);
   else
     resize_v_norm_kernel<__nv_bfloat16><<<rs_grid(total), 256, 0, st>>>(
         vin, resized_u8, static_cast<__nv_bfloat16*>(pixel_values), bounds_v, kk_v, kv, n_frames, in_h, out_h, out_w,

@@ -47,10 +47,9 @@ class Config:
 
 
 def _param_dtype(config) -> torch.dtype:
-    # the reference creates fp16 parameters and relies on from_pretrained(torch_dtype=...) to cast;
-    # this path computes in fp32 or bf16 only (fp16 inference is §8f "next"), so fp16 is created as bf16.
-    dt = getattr(config, "mm_dtype", torch.float32)
-    return torch.bfloat16 if dt == torch.float16 else dt
+    # the reference creates fp16 parameters (MemoryController.py:17) and relies on from_pretrained(torch_dtype=...)
+    # to cast; fp16 runs the tensor-core tier like bf16 (inference only), fp32 the exact SIMT tier.
+    return getattr(config, "mm_dtype", torch.float32)
 
 
 class Residual(nn.Module):
@@ -382,7 +381,7 @@ class MemoryFuser(nn.Module):
         h = self.num_heads
         dh = d // h
         dt = x.dtype
-        tc = dt == torch.bfloat16 and dh in (128, 448)          # head dims the fused tensor-core kernel handles
+        tc = dt in (torch.bfloat16, torch.float16) and dh in (128, 448)   # head dims the fused tensor-core kernel handles
         for layer in self.transformer_encoder.layers:
             sa = layer.self_attn
             if tc or dt == torch.float32:

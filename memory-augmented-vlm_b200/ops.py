@@ -10,9 +10,9 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import ACT_GELU_ERF, ACT_NONE, ACT_RELU, BF16, F32
+from ._lib import ACT_GELU_ERF, ACT_NONE, ACT_RELU, BF16, F16, F32
 
-_DTYPES = {torch.float32: F32, torch.bfloat16: BF16}
+_DTYPES = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 _device_checked = set()
 
 
@@ -20,7 +20,7 @@ def dtype_code(t: torch.Tensor) -> int:
     try:
         return _DTYPES[t.dtype]
     except KeyError:
-        raise TypeError(f"mavlm supports float32 and bfloat16 tensors, got {t.dtype}") from None
+        raise TypeError(f"mavlm supports float32, bfloat16 and float16 tensors, got {t.dtype}") from None
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -51,7 +51,11 @@ def _rowmajor2d(t: torch.Tensor, name: str) -> torch.Tensor:
 
 
 def _grad_needed(*ts: Optional[torch.Tensor]) -> bool:
-    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts)
+    need = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts)
+    if need and any(t is not None and t.dtype == torch.float16 for t in ts):
+        raise RuntimeError("mavlm: float16 is an inference dtype on this path (the reference trains in bfloat16, "
+                           "finetune_short.sh:71); use torch.no_grad() or bfloat16 / float32 parameters")
+    return need
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: int = ACT_NONE,
@@ -108,7 +112,7 @@ def _linear_raw(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tens
 
 
 def cast(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
-    """x.to(dtype) for fp32 <-> bf16 (the hand-off between the tensor-core tier and the fp32 tier)."""
+    """x.to(dtype) for fp32 <-> bf16 / fp16 (the hand-off between the tensor-core tier and the fp32 tier)."""
     if x.dtype == dtype:
         return x
     _need_cuda(x)

@@ -58,8 +58,8 @@ def convert_rmt(ref_rmt: nn.Module) -> TransformerProjector:
 def patch_llava(model: nn.Module, *, chunk_size: int = 32) -> nn.Module:
     inner = model.get_model()
     dtype = next(inner.mm_projector.parameters()).dtype
-    if dtype not in (torch.float32, torch.bfloat16):
-        raise TypeError(f"mavlm: {dtype} is not supported on this path (fp32 and bf16 only)")
+    if dtype not in (torch.float32, torch.bfloat16, torch.float16):
+        raise TypeError(f"mavlm: {dtype} is not supported on this path (fp32, bf16 and fp16 only)")
     proj = VisionProjector(*[m for m in inner.mm_projector])
     fuser = MemoryFuserMLP(*[m for m in inner.memory_fuser])
     rmt = convert_rmt(inner.recurrent_memory_transformer)

@@ -409,3 +409,51 @@ def test_frame_scores_bf16_tier():
     assert err(scores[0], ref_score) < BF16_TOL
     rmt.memory_cache = []
     assert rmt.frame_attn_scores == []
+
+
+# ---- fp16: the reference inference loader's default dtype (builder.py:27), SURVEY.md §8f-2 ----
+FP16_TOL = 5e-3      # fp16 carries 3 more mantissa bits than bf16: measured ~1e-3
+
+
+def test_fp16_gemm_attention_layernorm_ops():
+    torch.manual_seed(3)
+    a = (torch.randn(300, 1160, device=DEV)).half()
+    w = (torch.randn(520, 1160, device=DEV) / 34).half()
+    b = torch.randn(520, device=DEV).half()
+    r = torch.randn(300, 520, device=DEV).half()
+    for act in (0, 1, 2):
+        y = ops.linear(a, w, b, act=act, resid=r if act == 0 else None)
+        ref = a.double() @ w.double().T + b.double()
+        ref = torch.nn.functional.gelu(ref) if act == 1 else (torch.relu(ref) if act == 2 else ref + r.double())
+        assert y.dtype == torch.float16 and err(y, ref.cpu().numpy()) < FP16_TOL, act
+    y32 = ops.linear(a, w, b, out_dtype=torch.float32)
+    assert y32.dtype == torch.float32 and err(y32, (a.double() @ w.double().T + b.double()).cpu().numpy()) < 1e-3
+    for dh in (128, 448):
+        h = 2
+        q = torch.randn(2, 300, h * dh, device=DEV).half()
+        k = torch.randn(2, 700, h * dh, device=DEV).half()
+        v = torch.randn(2, 700, h * dh, device=DEV).half()
+        o, lse, _ = ops.xattn(q, k, v, h, want_lse=True)
+        qh, kh, vh = (t.double().view(2, -1, h, dh).transpose(1, 2) for t in (q, k, v))
+        s = qh @ kh.transpose(-1, -2) / dh ** 0.5
+        ref = (s.softmax(-1) @ vh).transpose(1, 2).reshape(2, 300, h * dh)
+        assert o.dtype == torch.float16 and err(o, ref.cpu().numpy()) < FP16_TOL, dh
+        assert err(lse, torch.logsumexp(s, -1).cpu().numpy()) < 1e-4
+    x = torch.randn(77, 3584, device=DEV) * 3 + 1
+    g, be = torch.randn(3584, device=DEV).half(), torch.randn(3584, device=DEV).half()
+    ref = torch.nn.functional.layer_norm(x.double(), (3584,), g.double(), be.double(), 1e-12)
+    assert err(ops.layernorm(x, g, be, 1e-12, out_dtype=torch.float16), ref.cpu().numpy()) < FP16_TOL
+
+
+def test_fp16_whole_path_against_the_oracle():
+    """OV-0.5B and OV-7B dims, fp16 parameters and activations, 2 chunks: assembled tokens and final memory."""
+    for hidden, frames, chunk in ((896, 8, 4), (3584, 64, 32)):
+        (e_seq, e_mem), = _run_vs_oracle(hidden, 1152, torch.float16, frames, chunk)
+        assert e_seq < FP16_TOL and e_mem < FP16_TOL, (hidden, e_seq, e_mem)
+
+
+def test_fp16_is_inference_only():
+    pipe, _ = synthetic.build_pipeline(64, 16, dtype=torch.float16, chunk_size=2, device=DEV)
+    z = torch.randn(1, 4, 196, 64, device=DEV).half()
+    with pytest.raises(RuntimeError, match="inference dtype"):
+        pipe.memory_forward_train(z)

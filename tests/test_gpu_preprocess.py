@@ -33,6 +33,8 @@ def test_processor_interface_and_bf16():
     assert torch.equal(out.cpu(), ref)
     lst = proc.preprocess([f for f in frames])["pixel_values"]                                   # list of frames
     assert torch.equal(lst, out)
+    half = M.SigLipImageProcessor(dtype=torch.float16).preprocess(frames)["pixel_values"]        # fp16 tower (builder.py:27)
+    assert half.dtype == torch.float16 and torch.equal(half.cpu(), torch.from_numpy(po.preprocess(frames)).half())
     with pytest.raises(ValueError):
         M.preprocess.frames_preprocess(torch.zeros(2, 8, 8, 3, device="cuda"))                 # not uint8
 

@@ -71,10 +71,12 @@ def test_patch_keeps_state_dict_and_shares_parameters():
         m.get_2dPool(torch.zeros(1, 729, 32))
 
 
-def test_patch_rejects_fp16():
-    m = _Model().half()
+def test_patch_accepts_fp16_and_rejects_other_dtypes():
+    m = _Model().half()                                      # the reference inference loader's default (builder.py:27)
+    M.patch_llava(m)
+    assert next(m.get_model().recurrent_memory_transformer.parameters()).dtype == torch.float16
     with pytest.raises(TypeError):
-        M.patch_llava(m)
+        M.patch_llava(_Model().double())
 
 
 @pytest.mark.gpu
