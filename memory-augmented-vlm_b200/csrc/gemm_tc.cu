@@ -415,7 +415,8 @@ static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     // the streaming C writes) while N is swept: ~32 MB.  With the old fixed 16 x 128 rows the 12544 x 14336 x
     // 3584 K/V projection read 1.06 GB from DRAM for 0.19 GB of operands (W re-read once per group).
     const long long tile_bytes = static_cast<long long>(GEMM_BM) * CG * p.K * 2;
-    long long g = (32ll << 20) / (tile_bytes > 0 ? tile_bytes : 1);
+    long long g = (40ll << 20) / (tile_bytes > 0 ? tile_bytes : 1);
+    if (tile_bytes * p.m_tiles <= (64ll << 20)) g = p.m_tiles;  // all of A fits: one group, W is read exactly once
     const int dbg_g = (gemm_tc_debug_flags() >> 8) & 0xff;
     if (dbg_g) g = dbg_g;
     if (g < 2) g = 2;
