@@ -487,7 +487,10 @@ static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUt
                        cudaStream_t st) {
   using Cfg = AttnCfg<DH>;
   static_assert(Cfg::SMEM_BYTES <= 232448, "attention smem budget exceeded");
-  static bool configured = false;
+  static bool configured_dev[64] = {};  // the attribute is per device (one process may drive several GPUs)
+  int dev_id = 0;
+  MAVLM_CUDA_OK(cudaGetDevice(&dev_id));
+  bool& configured = configured_dev[dev_id & 63];
   if (!configured) {
     MAVLM_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<DH, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::SMEM_BYTES));

@@ -402,7 +402,10 @@ static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
                           cudaStream_t st) {
   using Cfg = GemmCfg<BN, CG>;
   static_assert(Cfg::SMEM_BYTES <= 232448, "gemm smem budget exceeded");
-  static bool configured = false;
+  static bool configured_dev[64] = {};  // the attribute is per device (one process may drive several GPUs)
+  int dev_id = 0;
+  MAVLM_CUDA_OK(cudaGetDevice(&dev_id));
+  bool& configured = configured_dev[dev_id & 63];
   if (!configured) {
     MAVLM_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN, CG, T>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));

@@ -54,6 +54,20 @@ def max_over_ranks(value: float, device=None) -> float:
     return float(t.item())
 
 
+def synced_dropout_decision(prob: float = 0.5, device=None) -> bool:
+    """One coin flip shared by all ranks (LlavaMetaForCausalLM.get_synced_dropout_decision, llava_arch.py:378-386):
+    rank 0 draws, everybody receives the broadcast.  With `dropout_frames` (stage-1 training, finetune_short.sh:101)
+    a True decision drops the fine-frame half of the video sequence (llava_arch.py:719-725); every rank must take
+    the same branch or the sequence lengths -- and the collectives of the LLM step -- diverge."""
+    if not dist.is_initialized():
+        return bool(torch.rand(1).item() < prob)
+    t = torch.zeros(1, device=device)
+    if dist.get_rank() == 0:
+        t.fill_(1.0 if torch.rand(1).item() < prob else 0.0)
+    dist.broadcast(t, src=0)
+    return bool(t.item())
+
+
 @torch.no_grad()
 def encode_videos_sharded(pipe, tower_tokens: torch.Tensor, frame_idx: torch.Tensor, *, gather: bool = True):
     """tower_tokens [V, F, 729, Dv] (same on every rank, or only the local shard is touched):

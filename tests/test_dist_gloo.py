@@ -40,7 +40,13 @@ def _worker(rank, world, port, q):
         loc = torch.ones((len(mine1), 2))
         full3 = D.all_gather_rows(loc, [len(D.shard_range(1, r, world)) for r in range(world)])
         ok4 = full3.shape == (1, 2)
-        q.put((rank, ok1 and ok2 and ok3 and ok4))
+        # the dropout_frames coin (llava_arch.py:378-386): different local RNG states, one shared decision per draw
+        torch.manual_seed(100 + 17 * rank)
+        draws = [D.synced_dropout_decision(0.5) for _ in range(16)]
+        gathered = [None, None]
+        dist.all_gather_object(gathered, draws)
+        ok5 = gathered[0] == gathered[1] and any(draws) and not all(draws)
+        q.put((rank, ok1 and ok2 and ok3 and ok4 and ok5))
     finally:
         dist.destroy_process_group()
 
