@@ -186,6 +186,44 @@ class XAttnFn(torch.autograd.Function):
         return dq, dk, dv, None, None, None
 
 
+class XAttnKVFn(torch.autograd.Function):
+    """XAttnFn on a fused (k | v) projection buffer [B, Lk, 2*H*dh]: the backward writes dK and dV straight into
+    the two column halves of ONE gradient buffer (column-slice views of `kv` would each get a zero-filled full-size
+    gradient from autograd's SliceBackward: 720 MB of fills and copies per layer at OV-7B, batch 8)."""
+
+    @staticmethod
+    def forward(ctx, q, kv, heads, head_dim, scale):
+        hd = heads * head_dim
+        o, lse, _ = _raw()._xattn_raw(q, kv[..., :hd], kv[..., hd:], heads, head_dim=head_dim, scale=scale, want_lse=True)
+        ctx.save_for_backward(q, kv, o, lse)
+        ctx.cfg = (heads, head_dim, scale)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, kv, o, lse = ctx.saved_tensors
+        heads, dh, scale = ctx.cfg
+        hd = heads * dh
+        k, v = kv[..., :hd], kv[..., hd:]
+        b, lq, _ = q.shape
+        lk = kv.shape[1]
+        do = do.contiguous()
+        dq = torch.empty(q.shape, dtype=q.dtype, device=q.device)
+        dkv = torch.empty(kv.shape, dtype=kv.dtype, device=kv.device)
+        dk, dv = dkv[..., :hd], dkv[..., hd:]
+        lib = _lib.load()
+        code = _DT[q.dtype]
+        nbytes = lib.mavlm_xattn_bwd_workspace_bytes(b, heads, lq, lk, dh, code)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=q.device)
+        st = lib.mavlm_xattn_bwd(_p(q), q.stride(1), q.stride(0), _p(k), k.stride(1), k.stride(0), _p(v), v.stride(1),
+                                 v.stride(0), _p(o), o.stride(1), o.stride(0), _p(do), do.stride(1), do.stride(0),
+                                 _p(lse), _p(dq), dq.stride(1), dq.stride(0), _p(dk), dk.stride(1), dk.stride(0), _p(dv),
+                                 dv.stride(1), dv.stride(0), b, heads, lq, lk, dh, float(scale), code, _p(ws), nbytes,
+                                 _s())
+        _lib.check(st, "xattn_bwd")
+        return dq, dkv, None, None, None
+
+
 class AddRowsFn(torch.autograd.Function):
     """y[t, n, :] = x[t, n, :] + table[t, :]   (initial_memory + memory_pos_embed; x + type embedding with T = 1)."""
 

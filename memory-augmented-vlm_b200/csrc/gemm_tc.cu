@@ -83,7 +83,8 @@ template <int BN, bool A_MN, bool B_MN, int CG, typename T = __nv_bfloat16>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, GemmTcParams p) {
-  static_assert(CG == 1 || (CG == 2 && !A_MN && !B_MN), "CTA-pair tiles are implemented for K-major operands");
+  static_assert(CG == 1 || CG == 2, "one CTA or a CTA pair per tile");
+  static_assert(CG == 1 || !B_MN || (BN / CG) % 64 == 0, "an MN-major W half must be whole 64-column boxes");
   using Cfg = GemmCfg<BN, CG>;
   constexpr int TILE_M = GEMM_BM * CG;
   constexpr int STAGES = Cfg::STAGES;
@@ -152,8 +153,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // both CTAs' boxes are credited to the leader's barrier, which expects the pair's bytes
             if (rank == 0) mbar_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
             const uint32_t bar = mapa_u32(smem_u32(&full[stage]), 0);
-            tma_load_4d_pair(a_dst, &tmA, bar, kb * GEMM_BK, m0, bi, bo);
-            tma_load_4d_pair(b_dst, &tmB, bar, kb * GEMM_BK, n0, bi, bo);
+            if (!A_MN) {
+              tma_load_4d_pair(a_dst, &tmA, bar, kb * GEMM_BK, m0, bi, bo);
+            } else {
+#pragma unroll
+              for (int i = 0; i < GEMM_BM / 64; ++i)
+                tma_load_4d_pair(a_dst + i * 8192, &tmA, bar, m0 + 64 * i, kb * GEMM_BK, bi, bo);
+            }
+            if (!B_MN) {
+              tma_load_4d_pair(b_dst, &tmB, bar, kb * GEMM_BK, n0, bi, bo);
+            } else {
+#pragma unroll
+              for (int i = 0; i < Cfg::B_ROWS / 64; ++i)
+                tma_load_4d_pair(b_dst + i * 8192, &tmB, bar, n0 + 64 * i, kb * GEMM_BK, bi, bo);
+            }
           } else {
             mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
             if (!A_MN) {
@@ -195,7 +208,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {  // K-major: +32 B inside the 128 B swizzle row; MN-major: +16 k-rows = 2 KB
             if (CG == 2)
-              umma_bf16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+              umma_bf16_pair(d_tmem, a_desc + (A_MN ? 128 : 2) * k, b_desc + (B_MN ? 128 : 2) * k, idesc, (kb | k) != 0);
             else
               umma_bf16(d_tmem, a_desc + (A_MN ? 128 : 2) * k, b_desc + (B_MN ? 128 : 2) * k, idesc, (kb | k) != 0);
           }
@@ -465,6 +478,12 @@ static int dispatch_bn(int bn, int cg, const CUtensorMap& tmA, const CUtensorMap
       }
     }
   }
+  if constexpr (A_MN || B_MN) {
+    if (cg == 2) {  // transposed operands (dgrad / wgrad): CTA-pair tiles of 256 x 256 or 256 x 128
+      if (bn >= 192) return launch_gemm_tc<256, A_MN, B_MN, 2>(tmA, tmB, tmC, p, st);
+      return launch_gemm_tc<128, A_MN, B_MN, 2>(tmA, tmB, tmC, p, st);
+    }
+  }
   switch (bn) {
     case 256: return launch_gemm_tc<256, A_MN, B_MN, 1>(tmA, tmB, tmC, p, st);
     case 192: return launch_gemm_tc<192, A_MN, B_MN, 1>(tmA, tmB, tmC, p, st);
@@ -544,7 +563,7 @@ int gemm_tc_general(const __nv_bfloat16* A, long long lda, bool a_mn, const __nv
   p.dbg = gemm_tc_debug_flags();
   p.c_outer = s6[4];
   p.c_inner = s6[5];
-  const bool pair_ok = !a_mn && !b_mn && p.batches == 1;
+  const bool pair_ok = p.batches == 1;
   const int choice = gemm_tc_pick_tile(p.M, p.N, p.batches, pair_ok);
   const int cg = choice >= 1000 ? 2 : 1, bn = choice % 1000;
   CUtensorMap tmA, tmB;

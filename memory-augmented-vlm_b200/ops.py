@@ -170,6 +170,19 @@ def xattn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *, head
                       want_col_scores=want_col_scores)
 
 
+def xattn_kv(q: torch.Tensor, kv: torch.Tensor, heads: int, *, head_dim: int, scale: Optional[float] = None) -> torch.Tensor:
+    """xattn on a fused projection buffer kv = [B, Lk, 2*H*dh] (k | v column halves).  Same forward as
+    xattn(q, kv[..., :hd], kv[..., hd:]); under autograd the gradient comes back as one dkv buffer."""
+    hd = heads * head_dim
+    if kv.stride(2) != 1 or kv.shape[-1] != 2 * hd:
+        raise RuntimeError("mavlm.xattn_kv: kv must be [B, Lk, 2*H*dh] with a contiguous last dim")
+    sc = scale if scale is not None else 1.0 / math.sqrt(head_dim)
+    if _grad_needed(q, kv):
+        from . import autograd as ag
+        return ag.XAttnKVFn.apply(q, kv, heads, head_dim, sc)
+    return _xattn_raw(q, kv[..., :hd], kv[..., hd:], heads, head_dim=head_dim, scale=sc)[0]
+
+
 def _xattn_raw(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *, head_dim: Optional[int] = None,
                scale: Optional[float] = None, want_lse: bool = False,
                want_col_scores: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:

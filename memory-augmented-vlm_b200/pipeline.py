@@ -259,7 +259,8 @@ class VisualMemoryPipeline(nn.Module):
         packs = [l.memory_segment_fusion_attention.packed() for l in rmt.layers]       # part of the autograd graph
         dhp = packs[0]["dhp"]
         hd = heads * dhp
-        kvf = [ops.linear(z2, pk["wkv"], pk["bkv"]) for pk in packs]                    # frame-side K/V, all chunks
+        # frame-side K/V per chunk and layer (one GEMM of B*C*P rows each; the weight gradient accumulates over the
+        # chunks in autograd -- row slices of a whole-video projection would cost a zero-filled full-size gradient each)
         evo = rmt.memory_update_attention
         evo_p = evo.packed() if n_chunks > 1 else None
 
@@ -272,13 +273,15 @@ class VisualMemoryPipeline(nn.Module):
                     state_kv.append(ops.linear(states[len(state_kv)], evo_p["wkv"], evo_p["bkv"]))
                 kv = state_kv[0] if len(state_kv) == 1 else torch.cat(state_kv, dim=1)
                 q = ops.linear(mem, evo_p["wq"], evo_p["bq"])
-                ctx, _, _ = ops.xattn(q, kv[..., :hd], kv[..., hd:], heads, head_dim=dhp, scale=scale)
+                ctx = ops.xattn_kv(q, kv, heads, head_dim=dhp, scale=scale)
                 mem = evo.residual(ctx, mem, weight=evo_p["wo"])
             r0, r1 = bounds[t] * p, bounds[t + 1] * p
+            zc = z2[:, r0:r1] if n_chunks == 1 else z2[:, r0:r1].contiguous()   # one copy per chunk, shared by the layers
             for li, layer in enumerate(rmt.layers):
                 pk = packs[li]
                 q = ops.linear(mem, pk["wq"], pk["bq"])
-                ctx, _, _ = ops.xattn(q, kvf[li][:, r0:r1, :hd], kvf[li][:, r0:r1, hd:], heads, head_dim=dhp, scale=scale)
+                kvf = ops.linear(zc, pk["wkv"], pk["bkv"])
+                ctx = ops.xattn_kv(q, kvf, heads, head_dim=dhp, scale=scale)
                 a = layer.memory_segment_fusion_attention.residual(ctx, mem, weight=pk["wo"])
                 up = ops.linear(a, layer.mlp[0].weight, layer.mlp[0].bias, act=layer._act)
                 mem = layer.residual(up, a)
