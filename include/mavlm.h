@@ -62,6 +62,13 @@ MAVLM_API int mavlm_check_device(int device);
 MAVLM_API int mavlm_pool_pe_fwd(const void* x, void* y, const float* pe_table, const int64_t* frame_idx, int frames, int side,
                       int out_side, int stride, int dim, int mode, int dtype, void* stream);
 
+/* ---- a1 (second projector layer) + a3 fused: C = A W^T + bias + pe_table[frame_idx[row / tokens_per_frame]]
+ * (builder.py:47 followed by position_encoding.py:57-64 when the spatial pool runs before W2): the PE add rides in
+ * the GEMM epilogue instead of a separate read-modify-write pass over [F, 196, D].  bf16 / fp16 tier. */
+MAVLM_API int mavlm_gemm_bias_pe_fwd(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias,
+                                     const float* pe_table, const int64_t* frame_idx, int tokens_per_frame, void* C,
+                                     int64_t ldc, int M, int N, int K, int dtype, void* stream);
+
 /* ---- a3 alone: x [T, N, C] + pe_table[frame_idx[t]] cast to dtype (position_encoding.py:57-64). */
 MAVLM_API int mavlm_add_pe_fwd(const void* x, void* y, const float* pe_table, const int64_t* frame_idx, int frames, int tokens,
                      int dim, int dtype, void* stream);

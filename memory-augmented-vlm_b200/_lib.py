@@ -34,6 +34,8 @@ PROTOTYPES = {
     "mavlm_add_pe_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mavlm_gemm_bias_act_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
                                         c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mavlm_gemm_bias_pe_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                       c_int64, c_int, c_int, c_int, c_int, c_void_p]),
     "mavlm_gather_rows_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "mavlm_cast_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "mavlm_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_int,

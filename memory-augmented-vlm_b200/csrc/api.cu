@@ -7,7 +7,8 @@ int gemm_fp32(const float* A, long long lda, const float* W, long long ldw, cons
               cudaStream_t st);
 int gemm_bf16_tc(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw,
                  const __nv_bfloat16* bias, const __nv_bfloat16* resid, long long ldr, const __nv_bfloat16* addvec,
-                 void* C, long long ldc, int M, int N, int K, int act, int out_f32, cudaStream_t st, int half = 0);
+                 void* C, long long ldc, int M, int N, int K, int act, int out_f32, cudaStream_t st, int half = 0,
+                 const float* pe_table = nullptr, const long long* pe_idx = nullptr, int pe_tokens = 0);
 void gemm_tc_force_bn(int bn);
 void gemm_tc_set_debug(int flags);
 int xattn_fp32(const float* Q, long long ldq, long long qb, const float* K, long long ldk, long long kb, const float* V,
@@ -44,6 +45,21 @@ int mavlm_gemm_bias_act_fwd(const void* A, int64_t lda, const void* W, int64_t l
                       static_cast<const __nv_bfloat16*>(bias), static_cast<const __nv_bfloat16*>(resid), ldr,
                       static_cast<const __nv_bfloat16*>(addvec), C, ldc, M, N, K, act, out_dtype == MAVLM_F32, st,
                       dtype == MAVLM_F16 ? 1 : 0);
+}
+
+int mavlm_gemm_bias_pe_fwd(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const float* pe_table,
+                           const int64_t* frame_idx, int tokens_per_frame, void* C, int64_t ldc, int M, int N, int K,
+                           int dtype, void* stream) {
+  MAVLM_REQUIRE(M >= 0 && N >= 0 && K > 0, MAVLM_E_INVALID, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
+  MAVLM_REQUIRE(A != nullptr && W != nullptr && C != nullptr && pe_table != nullptr && frame_idx != nullptr,
+                MAVLM_E_INVALID, "gemm + PE: NULL operand");
+  MAVLM_REQUIRE(dtype == MAVLM_BF16 || dtype == MAVLM_F16, MAVLM_E_INVALID,
+                "gemm + PE is a tensor-core tier fusion (bf16 / fp16); fp32 uses gemm_bias_act_fwd + add_pe_fwd");
+  static_assert(sizeof(long long) == sizeof(int64_t), "index type");
+  return gemm_bf16_tc(static_cast<const __nv_bfloat16*>(A), lda, static_cast<const __nv_bfloat16*>(W), ldw,
+                      static_cast<const __nv_bfloat16*>(bias), nullptr, 0, nullptr, C, ldc, M, N, K, MAVLM_ACT_NONE, 0,
+                      static_cast<cudaStream_t>(stream), dtype == MAVLM_F16 ? 1 : 0, pe_table,
+                      reinterpret_cast<const long long*>(frame_idx), tokens_per_frame);
 }
 
 size_t mavlm_xattn_workspace_bytes(int batch, int heads, int lq, int lk, int head_dim, int dtype) {

@@ -27,6 +27,10 @@ struct GemmTcParams {
   const void* resid;
   long long ldr;
   const void* addvec;
+  // fused temporal PE (position_encoding.py:57-64): C[row] += pe_table[frame_idx[row / pe_tokens]] (fp32 table)
+  const float* pe_table;
+  const long long* pe_idx;
+  int pe_tokens;
   int half;        // 1: operands / outputs are fp16 (kernels instantiated with T = __half)
   void* C;
   long long ldc;
@@ -279,6 +283,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (p.resid != nullptr && row_ok) add_vec32(static_cast<const T*>(p.resid) + row * p.ldr + nc, true);
         if (p.addvec != nullptr) add_vec32(static_cast<const T*>(p.addvec) + nc, false);
+        if (p.pe_table != nullptr && row_ok) {  // the frame's PE row (fp32, L2-resident: 196 rows share it)
+          const float* pe = p.pe_table + __ldg(p.pe_idx + row / p.pe_tokens) * p.N + nc;
+          if (full_chunk) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(pe) + g);
+              v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (nc + j < p.N) v[j] += pe[j];
+          }
+        }
         if (p.dbg & 1) {  // experiment: no global stores (keep the values live)
           float acc_dbg = 0.f;
 #pragma unroll
@@ -593,10 +610,16 @@ int gemm_tc_general(const __nv_bfloat16* A, long long lda, bool a_mn, const __nv
 
 int gemm_bf16_tc(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw,
                  const __nv_bfloat16* bias, const __nv_bfloat16* resid, long long ldr, const __nv_bfloat16* addvec,
-                 void* C, long long ldc, int M, int N, int K, int act, int out_f32, cudaStream_t st, int half) {
+                 void* C, long long ldc, int M, int N, int K, int act, int out_f32, cudaStream_t st, int half,
+                 const float* pe_table, const long long* pe_idx, int pe_tokens) {
   MAVLM_REQUIRE(K > 0 && K % 8 == 0, MAVLM_E_INVALID, "bf16 gemm: K (%d) must be a multiple of 8", K);
   GemmTcParams p{};
   p.half = half;
+  if (pe_table != nullptr) {
+    MAVLM_REQUIRE(pe_idx != nullptr && pe_tokens > 0 && N % 4 == 0 && (reinterpret_cast<uintptr_t>(pe_table) & 15) == 0,
+                  MAVLM_E_INVALID, "gemm + PE: needs frame indices, tokens per frame > 0, N %% 4 == 0, aligned table");
+    p.pe_table = pe_table; p.pe_idx = pe_idx; p.pe_tokens = pe_tokens;
+  }
   p.M = M; p.N = N; p.K = K;
   p.bias = bias; p.resid = resid; p.ldr = ldr; p.addvec = addvec;
   p.C = C; p.ldc = ldc; p.act = act; p.out_f32 = out_f32;

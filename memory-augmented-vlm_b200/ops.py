@@ -111,6 +111,30 @@ def _linear_raw(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tens
     return out2.reshape(*lead, n)
 
 
+def linear_pe(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, pe_table: torch.Tensor,
+              frame_idx: torch.Tensor) -> torch.Tensor:
+    """x [T, N, K] -> x @ weight.T + bias + pe_table[frame_idx][:, None, :] in one launch (bf16 / fp16 tier):
+    the projector's second layer with the temporal PE added in the GEMM epilogue."""
+    _need_cuda(x, weight, bias, pe_table, frame_idx)
+    t, n_tok, k = x.shape
+    n = weight.shape[0]
+    if x.dtype == torch.float32:
+        return add_pe(linear(x, weight, bias), pe_table, frame_idx)
+    x2 = x.reshape(t * n_tok, k)
+    if x2.stride(1) != 1 or not x2.is_contiguous():
+        x2 = x2.contiguous()
+    _rowmajor2d(weight, "weight")
+    if pe_table.dtype != torch.float32 or not pe_table.is_contiguous() or pe_table.shape[1] != n:
+        raise RuntimeError("mavlm.linear_pe: pe_table must be contiguous fp32 [max_frames, N]")
+    frame_idx = frame_idx.to(device=x.device, dtype=torch.int64).contiguous()
+    out = torch.empty((t, n_tok, n), dtype=x.dtype, device=x.device)
+    st = _lib.load().mavlm_gemm_bias_pe_fwd(_ptr(x2), x2.stride(0), _ptr(weight), weight.stride(0), _ptr(bias),
+                                            _ptr(pe_table), _ptr(frame_idx), n_tok, _ptr(out), n, t * n_tok, n, k,
+                                            dtype_code(x), _stream())
+    _lib.check(st, "gemm_bias_pe_fwd")
+    return out
+
+
 def cast(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     """x.to(dtype) for fp32 <-> bf16 / fp16 (the hand-off between the tensor-core tier and the fp32 tier)."""
     if x.dtype == dtype:

@@ -111,8 +111,7 @@ class VisualMemoryPipeline(nn.Module):
             if self.pool_before_w2 and self.pool_mode == "bilinear":
                 h = ops.linear(x, mp[0].weight, mp[0].bias, act=ACT_GELU_ERF)
                 hp = ops.pool_pe(h, side=self.side, stride=self.pool_stride, mode="bilinear")
-                y = ops.linear(hp, mp[2].weight, mp[2].bias)
-                outs.append(ops.add_pe(y, table, frame_idx[i:i + step], out=y))
+                outs.append(ops.linear_pe(hp, mp[2].weight, mp[2].bias, table, frame_idx[i:i + step]))
             else:
                 y = mp(x)
                 outs.append(ops.pool_pe(y, side=self.side, stride=self.pool_stride, mode=self.pool_mode,
