@@ -145,7 +145,17 @@ class VisualMemoryPipeline(nn.Module):
         evo = rmt.memory_update_attention
         evo_p = evo.packed()
         ring_states = torch.empty((b, cap, lq, d), dtype=dtype, device=dev)
-        ring_kv = torch.empty((b, cap * lq, 2 * hd), dtype=dtype, device=dev) if n_chunks > 1 else None
+        # evolution attention: a new state is projected ONCE, by one GEMM with [Wq; Wk; Wv] (N = 3*H*dh: 294 pair
+        # tiles = 3.97 waves on 74 CTA pairs, where q and k|v separately cost 2 + 3 waves) into its ring slot
+        # (q | k | v columns); q is read by the next chunk, k | v by every later chunk that still caches the state
+        ring_qkv = torch.empty((b, cap * lq, 3 * hd), dtype=dtype, device=dev) if n_chunks > 1 else None
+        if n_chunks > 1:
+            ekey = (id(evo_p["wq"]), id(evo_p["wkv"]))
+            c = self._consts.get("evo_qkv")
+            if c is None or c[0] != ekey:
+                self._consts["evo_qkv"] = (ekey, torch.cat([evo_p["wq"], evo_p["wkv"]], dim=0).contiguous(),
+                                           torch.cat([evo_p["bq"], evo_p["bkv"]], dim=0).contiguous())
+            w_evo, b_evo = self._consts["evo_qkv"][1], self._consts["evo_qkv"][2]
 
         mem = rmt.initial_state(dtype).reshape(1, lq, d).expand(b, lq, d).contiguous()
         last_layer = len(rmt.layers) - 1
@@ -154,9 +164,10 @@ class VisualMemoryPipeline(nn.Module):
             if t > 0:
                 # memory evolution: Q = newest state, K/V = every state still cached (incl. itself)
                 n = min(t, cap)
-                q = ops.linear(mem, evo_p["wq"], evo_p["bq"])
-                kv = ring_kv[:, : n * lq]
-                ctx, _, _ = ops.xattn(q, kv[..., :hd], kv[..., hd:], heads, head_dim=dhp, scale=scale)
+                prev = (t - 1) % cap
+                q = ring_qkv[:, prev * lq:(prev + 1) * lq, :hd]
+                kv = ring_qkv[:, : n * lq]
+                ctx, _, _ = ops.xattn(q, kv[..., hd:2 * hd], kv[..., 2 * hd:], heads, head_dim=dhp, scale=scale)
                 mem = evo.residual(ctx, mem, weight=evo_p["wo"])
             r0, r1 = bounds[t] * p, bounds[t + 1] * p
             for li, layer in enumerate(rmt.layers):
@@ -176,7 +187,7 @@ class VisualMemoryPipeline(nn.Module):
                 ring_states[:, slot].copy_(mem)
             if t + 1 < n_chunks:                                        # project the new state once for later chunks
                 for bi in range(b):
-                    ops.linear(mem[bi], evo_p["wkv"], evo_p["bkv"], out=ring_kv[bi, slot * lq:(slot + 1) * lq])
+                    ops.linear(mem[bi], w_evo, b_evo, out=ring_qkv[bi, slot * lq:(slot + 1) * lq])
 
         # fuser + assembly: state written at chunk t sits in slot t % cap; reference order is oldest first
         first = n_chunks - n_keep
