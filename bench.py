@@ -222,6 +222,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+    numa = M.dist.bind_to_gpu_numa_node(local) if world > 1 else None      # before any pinned buffer is allocated
 
     pipe, weights = synthetic.build_pipeline(HIDDEN, VISION, dtype=torch.bfloat16, chunk_size=CHUNK, device=dev)
     x_host = synthetic.synthetic_tower_tokens(1, FRAMES, seed=1234 + rank, pin=True)
@@ -427,7 +428,7 @@ def run_ours(args):
             "dtype": "bf16", "data": "synthetic", "config": workload_config(world), "clocks": clocks,
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": x_host.numel() * x_host.element_size(),
                     "d2h_bytes_per_step": out_host.numel() * out_host.element_size(), "ms_per_step": ms_e2e / steps},
-            "gpu_launches": int(launches), "launch_mode": "one CUDA graph replay per step (kernels counted from an "
+            "host_numa_node_rank0": numa, "gpu_launches": int(launches), "launch_mode": "one CUDA graph replay per step (kernels counted from an "
             "eager step)", "roofline": roofline, "cpu_baseline": cpu,
             "kernel_breakdown": breakdown, "gemm_shapes": gemm_shapes,
             "algorithmic_gflop_per_step": gflop_step,

@@ -54,6 +54,42 @@ def max_over_ranks(value: float, device=None) -> float:
     return float(t.item())
 
 
+def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (sysfs, via the GPU's PCI bus id), so that the
+    pinned host buffers it allocates afterwards are first-touched on that node.  With 8 ranks streaming 175 MB per
+    step over PCIe each, buffers that all land on one socket make the host memory controller the bottleneck.
+    Returns the node, or None when the topology cannot be read (then nothing is changed)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:                      # nvml prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        base = f"/sys/bus/pci/devices/{bus}"
+        with open(f"{base}/numa_node") as fh:
+            node = int(fh.read().strip())
+        with open(f"{base}/local_cpulist") as fh:
+            spec = fh.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = cpus & os.sched_getaffinity(0)
+        if node < 0 or not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:                                        # no nvml / sysfs (containers): keep the default placement
+        return None
+
+
 def synced_dropout_decision(prob: float = 0.5, device=None) -> bool:
     """One coin flip shared by all ranks (LlavaMetaForCausalLM.get_synced_dropout_decision, llava_arch.py:378-386):
     rank 0 draws, everybody receives the broadcast.  With `dropout_frames` (stage-1 training, finetune_short.sh:101)
