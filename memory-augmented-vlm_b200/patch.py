@@ -18,9 +18,10 @@ import types
 import torch
 from torch import nn
 
-from .modules import (Config, MemoryFuserMLP, TemporalPositionalEncoding, TransformerProjector, VisionProjector,
+from .modules import (sample_frame_indices, Config, MemoryFuserMLP, TemporalPositionalEncoding, TransformerProjector, VisionProjector,
                       get_2dPool)
 from .pipeline import VisualMemoryPipeline
+from .splice import splice_text_and_vision
 
 
 def _adopt(dst: nn.Module, src: nn.Module) -> None:
@@ -55,7 +56,46 @@ def convert_rmt(ref_rmt: nn.Module) -> TransformerProjector:
     return new
 
 
-def patch_llava(model: nn.Module, *, chunk_size: int = 32) -> nn.Module:
+def _fused_prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attention_mask, past_key_values, labels,
+                                                images, modalities=["image"], image_sizes=None):
+    """Whole-function replacement of LlavaMetaForCausalLM.prepare_inputs_labels_for_multimodal (llava_arch.py:388-878)
+    for what the fork actually runs -- video samples at inference (Appendix E of SURVEY.md: non-video entries are
+    dropped by the fork itself): frame sampling (:437-457) -> the reference's own vision tower -> the fused
+    visual-memory pipeline (projector, pool, PE, recurrent memory, fuser, token assembly; one CUDA library) ->
+    text / vision splice, truncation, padding (:745-878, one gather kernel).  Same signature, same 6-tuple.
+    Training (autograd, dropout_frames coin) and non-video inputs go to the reference's method, which by then runs on
+    the patched modules."""
+    vision_tower = self.get_vision_tower()
+    if vision_tower is None or images is None or input_ids.shape[1] == 1:                     # :392-394
+        return input_ids, position_ids, attention_mask, past_key_values, None, labels
+    if isinstance(modalities, str):
+        modalities = [modalities]
+    is_list = type(images) is list
+    if not (is_list or images.ndim == 5) or self.training or any(m != "video" for m in modalities):
+        return self._mavlm_reference_prepare(input_ids, position_ids, attention_mask, past_key_values, labels, images,
+                                             modalities, image_sizes)
+    pipe = self.mavlm_pipeline
+    wdtype = pipe.mm_projector[0].weight.dtype
+    dev = pipe.mm_projector[0].weight.device
+    feats = []
+    for image in images:
+        if image.ndim == 3:
+            image = image.unsqueeze(0)
+        idx = sample_frame_indices(image.shape[0])                                            # :437-451
+        tokens = vision_tower(image[idx.to(image.device)])                                    # [F', side^2, Dv]
+        seq = pipe(tokens.to(device=dev, dtype=wdtype)[None], idx[None])["sequence"][0]
+        feats.append(seq)
+    cfg = self.config
+    pos, mask, embeds, new_labels = splice_text_and_vision(
+        input_ids, position_ids, attention_mask, labels, feats, self.get_model().embed_tokens.weight.detach(),
+        tokenizer_model_max_length=getattr(cfg, "tokenizer_model_max_length", None),
+        padding_side=getattr(cfg, "tokenizer_padding_side", "right"),
+        use_pos_skipping=getattr(cfg, "use_pos_skipping", False),
+        pos_skipping_range=getattr(cfg, "pos_skipping_range", 0), training=False)
+    return None, pos, mask, past_key_values, embeds, new_labels                             # :878
+
+
+def patch_llava(model: nn.Module, *, chunk_size: int = 32, fused: bool = False) -> nn.Module:
     inner = model.get_model()
     dtype = next(inner.mm_projector.parameters()).dtype
     if dtype not in (torch.float32, torch.bfloat16, torch.float16):
@@ -81,4 +121,9 @@ def patch_llava(model: nn.Module, *, chunk_size: int = 32) -> nn.Module:
         mm_projector=proj, recurrent_memory_transformer=rmt, memory_fuser=fuser, positional_encoding=pe,
         token_type_embedding=inner.token_type_embedding, image_newline=inner.image_newline,
         embed_tokens=inner.embed_tokens, chunk_size=chunk_size, num_patches_per_side=side)
+    if fused:   # replace the whole method; the reference's own stays reachable for training / non-video inputs
+        ref = getattr(type(model), "prepare_inputs_labels_for_multimodal", None)
+        if ref is not None:
+            model._mavlm_reference_prepare = types.MethodType(ref, model)
+        model.prepare_inputs_labels_for_multimodal = types.MethodType(_fused_prepare_inputs_labels_for_multimodal, model)
     return model
