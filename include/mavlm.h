@@ -138,6 +138,59 @@ MAVLM_API int mavlm_frames_preprocess_fwd(const uint8_t* frames, int n_frames, i
                                           const int32_t* bounds_v, const int32_t* kk_v, int ksize_v, double rescale,
                                           const float* mean3, const float* std3, int out_dtype, void* stream);
 
+/* ======================= legacy memories and scene segmentation =======================
+ * The Flash-VStream-style memories (memory_module/compress_functions.py, memory_builder.py:41-190) and the scene
+ * segmentation (memory_module/segment.py) that sit beside the recurrent memory in the reference tree. */
+
+/* Streaming compression of a video x [n_frames, row_elems = P*D] to `keep` frames:
+ *   mode 0 drop_feature   (compress_functions.py:20-56)    coins: 1 = drop the right member of the most similar pair
+ *   mode 1 merge_feature  (:59-91)
+ *   mode 2 k_drop_feature (:176-218)                       coins: 1 = drop the row index of the flat argmax
+ *   mode 3 k_merge_feature(:221-264)
+ * One launch per streamed frame, all decisions on the device.  coins: DEVICE uint8 [n_frames - keep] (the host
+ * draws them like the reference: one random.randint(0, 1) per frame; NULL for the merge modes).
+ * out [keep, row_elems]; out_sim fp32: [keep - 1] adjacent similarities (modes 0, 1) or [keep, keep] (modes 2, 3),
+ * may be NULL; decisions int32 [n_frames - keep, 2]: (idx, idx) / (idx, idx + 1) / (left, right) per frame, from
+ * which the host rebuilds the reference's step_indices.  Needs n_frames > keep (the reference returns shorter
+ * videos unchanged), 1 <= keep <= 64. */
+MAVLM_API size_t mavlm_stream_compress_workspace_bytes(int64_t row_elems, int keep, int mode, int dtype);
+MAVLM_API int mavlm_stream_compress_fwd(const void* x, int64_t n_frames, int64_t row_elems, int keep, int mode,
+                                        const uint8_t* coins, void* out, float* out_sim, int32_t* decisions,
+                                        void* workspace, size_t workspace_bytes, int dtype, void* stream);
+/* out[t, :] = mean over the tokens of frame t: the `features.mean(dim=1)` feeding segment() (segment.py:266) and the
+ * scheduler (llava_arch.py:528).  x [frames, tokens, dim]. */
+MAVLM_API int mavlm_frame_mean_fwd(const void* x, void* out, int frames, int tokens, int dim, int dtype, void* stream);
+/* sim[t] = torch.cosine_similarity(x[t], x[t + 1], eps) for t < rows - 1 (segment.py:30, 69, 228;
+ * compress_functions.py:30), rounded through the storage dtype.  Rows of row_elems elements, ld apart. */
+MAVLM_API size_t mavlm_adjacent_cosine_workspace_bytes(int64_t rows, int64_t row_elems, int dtype);
+MAVLM_API int mavlm_adjacent_cosine_fwd(const void* x, int64_t rows, int64_t row_elems, int64_t ld, float eps, float* sim,
+                                        void* workspace, size_t workspace_bytes, int dtype, void* stream);
+/* cal_depth_score (segment.py:3-25) / cal_left_depth_score (:210-223) on fp32 similarities; bit-exact. */
+MAVLM_API int mavlm_depth_scores_fwd(const float* sim, float* depth, int n, int left_only, void* stream);
+/* compress_spatial_features (memory_builder.py:72-99): avg_pool2d with window = stride on [frames, side*side, dim]
+ * channels-last tokens -> [frames, o*o, dim], o = (side - window) / window + 1 (floor mode). */
+MAVLM_API int mavlm_avg_pool_fwd(const void* x, void* out, int frames, int side, int window, int dim, int dtype,
+                                 void* stream);
+/* One iteration of (weighted_)kmeans_feature (compress_functions.py:94-173) over whole frames: labels (first
+ * nearest centroid) and per-cluster weight sums against `cent`, new centroids for the non-empty clusters,
+ * diff[k] = |cent_k - new_k| (0 for an empty cluster, which the caller re-seeds like the reference and measures
+ * with mavlm_row_distance_fwd).  weights: fp32 [n_frames] or NULL (plain k-means); dist: optional fp32
+ * [n_frames, clusters]; new_cent NULL: distances / labels / weight sums only (the key-frame search,
+ * memory_builder.py:157-158). */
+MAVLM_API size_t mavlm_kmeans_workspace_bytes(int64_t n_frames, int64_t row_elems, int clusters, int dtype);
+MAVLM_API int mavlm_kmeans_iter_fwd(const void* x, const float* weights, const void* cent, void* new_cent,
+                                    int32_t* labels, float* wsum, float* diff, float* dist, int64_t n_frames,
+                                    int64_t row_elems, int clusters, void* workspace, size_t workspace_bytes, int dtype,
+                                    void* stream);
+MAVLM_API int mavlm_row_distance_fwd(const void* a, const void* b, float* dist, int rows, int64_t row_elems,
+                                     void* workspace, size_t workspace_bytes, int dtype, void* stream);
+/* Turing-memory update (memory_builder.py:52-64): w = ratio * softmax(scores * scale) over the n new tokens of each
+ * row (columns [n, n_pad) are zero-filled so that w can feed the tensor-core GEMM), and, when mem is given,
+ * mem_scaled = mem * (1 - sum_j w_ij); the caller accumulates w @ new onto it with mavlm_gemm_ex. */
+MAVLM_API int mavlm_ntm_softmax_fwd(const float* scores, int64_t ld_scores, int64_t rows, int n, float scale,
+                                    float ratio, void* w, int64_t ld_w, int n_pad, const void* mem, void* mem_scaled,
+                                    int dim, int dtype, void* stream);
+
 /* ======================= backward pass (training: BPTT through the memory, fuser) =======================
  * The reference trains this path with PyTorch autograd (train.py:1694-1728 unfreezes recurrent_memory_transformer,
  * memory_fuser, token_type_embedding; frame features are detached, llava_arch.py:302).  These entry points are

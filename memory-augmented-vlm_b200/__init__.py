@@ -6,7 +6,8 @@ Directory name `memory-augmented-vlm_b200` is not a valid Python identifier; imp
 Only what the hot path needs lives here: `csrc/` (CUDA kernels + C ABI -> libmavlm.so), `_lib.py`
 (ctypes binding), `ops.py` (tensor-level wrappers), `modules.py` (mirror of the reference's module
 interface), `pipeline.py` (chunk scheduler + fused path), `patch.py` (drop-in for a LLaVA model),
-`dist.py` (video sharding over ranks).
+`dist.py` (video sharding over ranks), `legacy.py` (the reference's older memory builders and scene
+segmentation).
 """
 from . import _lib  # noqa: F401
 from .modules import (Attention, Config, MemoryFuser, MemoryFuserMLP, Residual, TemporalPositionalEncoding, TransformerLayer,
@@ -14,6 +15,7 @@ from .modules import (Attention, Config, MemoryFuser, MemoryFuserMLP, Residual, 
                       fine_frame_indices, get_2dPool, sample_frame_indices, uniform_segment_variant)
 from .patch import convert_rmt, patch_llava
 from . import preprocess  # noqa: F401
+from . import legacy  # noqa: F401  (Flash-VStream-style memories, scene segmentation)
 from .preprocess import SigLipImageProcessor, frames_preprocess
 from .splice import IGNORE_INDEX, IMAGE_TOKEN_INDEX, splice_text_and_vision
 from .pipeline import (FRAME_PROMPT_IDS, MEMORY_PROMPT_IDS, GraphedPipeline, HostStreamEncoder,

@@ -62,6 +62,21 @@ PROTOTYPES = {
     "mavlm_frames_preprocess_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                             c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_double, c_void_p,
                                             c_void_p, c_int, c_void_p]),
+    "mavlm_stream_compress_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int]),
+    "mavlm_stream_compress_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_size_t, c_int, c_void_p]),
+    "mavlm_frame_mean_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mavlm_adjacent_cosine_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
+    "mavlm_adjacent_cosine_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p, c_void_p, c_size_t, c_int,
+                                          c_void_p]),
+    "mavlm_depth_scores_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "mavlm_avg_pool_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mavlm_kmeans_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int]),
+    "mavlm_kmeans_iter_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                      c_int64, c_int, c_void_p, c_size_t, c_int, c_void_p]),
+    "mavlm_row_distance_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_size_t, c_int, c_void_p]),
+    "mavlm_ntm_softmax_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int, c_float, c_float, c_void_p, c_int64, c_int, c_void_p,
+                                      c_void_p, c_int, c_int, c_void_p]),
     "mavlm_debug_force_gemm_bn": (c_int, [c_int]),
     "mavlm_debug_set_flags": (c_int, [c_int]),
     "mavlm_debug_force_attn_groups": (c_int, [c_int]),
