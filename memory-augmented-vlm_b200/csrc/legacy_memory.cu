@@ -14,6 +14,7 @@
 // compression, the k-means distance / centroid kernels and the row softmax of the Turing-memory update (whose
 // contractions run on the tcgen05 GEMM through mavlm_gemm_ex).
 #include <algorithm>
+#include <type_traits>
 
 #include "vec.cuh"
 
@@ -67,25 +68,31 @@ __device__ __forceinline__ void block_sum(float (&v)[N], float* red /* [N][8] */
 // ---------------------------------------------------------------------------------------------------------------
 // streaming compression (drop / merge / k_drop / k_merge)
 // ---------------------------------------------------------------------------------------------------------------
-struct LmState {
+// Small part of the state: the deciding CTA works on a shared-memory copy (one parallel round trip in, one out)
+// instead of chasing dependent global loads from a single thread.
+struct LmSmall {
   int mode, keep, n_in;
   int n_fix, n_new;                       // jobs [0, n_fix): refresh similarities of the last decision; then n_new
                                           // jobs pairing the kept rows with the incoming frame
   int avg_a, avg_b, avg_dst;              // planned average (row handles), avg_dst < 0: none
-  int jobs[LM_MAX_JOBS][2];
-  int fix_target[2 * LM_CAP + 4];
   int fix_pos;
+  int free_pos;
+  int n_free;
+  unsigned ticket;
+  int fix_target[2 * LM_CAP + 4];
   // drop / merge: handles and adjacent similarities in temporal order
   int order[LM_CAP + 2];
   float sim[LM_CAP + 2];
-  // k_drop / k_merge: LM_CAP + 1 physical positions, a logical (temporal) order over them, all-pairs matrix
+  // k_drop / k_merge: LM_CAP + 1 physical positions and a logical (temporal) order over them
   int lorder[LM_CAP + 2];
   int handle[LM_CAP + 2];
-  int free_pos;
-  float S[(LM_CAP + 1) * (LM_CAP + 1)];
   int free_slots[LM_CAP + 4];
-  int n_free;
-  unsigned ticket;
+};
+constexpr int LM_SMALL_WORDS = sizeof(LmSmall) / 4;
+struct LmState {
+  LmSmall sm;
+  float S[(LM_CAP + 1) * (LM_CAP + 1)];   // all-pairs similarities by physical position (k modes)
+  int jobs[LM_MAX_JOBS][2];
 };
 
 template <typename T>
@@ -101,30 +108,30 @@ __device__ __forceinline__ float lm_cos(float ab, float aa, float bb, float eps)
   return ab / (fmaxf(sqrtf(aa), eps) * fmaxf(sqrtf(bb), eps));
 }
 
-__device__ void lm_plan_new(LmState* s, int next) {
-  const int base = s->n_fix;
-  if (next >= s->n_in) { s->n_new = 0; return; }
-  if (s->mode == LM_DROP || s->mode == LM_MERGE) {
-    s->jobs[base][0] = s->order[s->keep - 1];
-    s->jobs[base][1] = next;
-    s->n_new = 1;
+__device__ void lm_plan_new(LmSmall* m, int (*jobs)[2], int next) {
+  const int base = m->n_fix;
+  if (next >= m->n_in) { m->n_new = 0; return; }
+  if (m->mode == LM_DROP || m->mode == LM_MERGE) {
+    jobs[base][0] = m->order[m->keep - 1];
+    jobs[base][1] = next;
+    m->n_new = 1;
   } else {
-    for (int j = 0; j < s->keep; ++j) {
-      s->jobs[base + j][0] = s->handle[s->lorder[j]];
-      s->jobs[base + j][1] = next;
+    for (int j = 0; j < m->keep; ++j) {
+      jobs[base + j][0] = m->handle[m->lorder[j]];
+      jobs[base + j][1] = next;
     }
-    s->n_new = s->keep;
+    m->n_new = m->keep;
   }
 }
 
 // first maximum of S over the logical (row-major) order of the keep + 1 live positions
-__device__ void lm_argmax_pairs(const LmState* s, int n, int* out_left, int* out_right, float* sv, int* si) {
+__device__ void lm_argmax_pairs(const LmSmall* m, const float* S, int n, int* out_left, int* out_right, float* sv, int* si) {
   float best = -3.0e38f;
   int bi = 0x7fffffff;
   const int stride = LM_CAP + 1;
   for (int f = threadIdx.x; f < n * n; f += LM_THREADS) {
     const int l = f / n, r = f - l * n;
-    const float v = s->S[s->lorder[l] * stride + s->lorder[r]];
+    const float v = S[m->lorder[l] * stride + m->lorder[r]];
     if (v > best) { best = v; bi = f; }      // f ascending per thread: keeps the first maximum
   }
   sv[threadIdx.x] = best;
@@ -143,10 +150,11 @@ __device__ void lm_argmax_pairs(const LmState* s, int n, int* out_left, int* out
   __syncthreads();
 }
 
+// m, S: shared-memory copies of the state; jobs: the job list in global memory (write only here)
 template <typename T>
-__device__ void lm_decide(LmState* s, const float* dots /* [jobs][3] */, int phase, int step, const uint8_t* coins,
-                          int* decisions, float* sv, int* si) {
-  const int keep = s->keep, mode = s->mode;
+__device__ void lm_decide(LmSmall* m, float* S, int (*jobs)[2], const float* dots /* [jobs][3] */, int phase, int step,
+                          int coin, int* decisions, float* sv, int* si) {
+  const int keep = m->keep, mode = m->mode;
   const bool adjacent = mode == LM_DROP || mode == LM_MERGE;
   const float eps = adjacent ? 1e-8f : 1e-12f;
   const int stride = LM_CAP + 1;
@@ -155,122 +163,123 @@ __device__ void lm_decide(LmState* s, const float* dots /* [jobs][3] */, int pha
   if (phase == LM_PHASE_INIT) {
     if (threadIdx.x == 0) {
       if (adjacent) {
-        for (int j = 0; j + 1 < keep; ++j) s->sim[j] = cosj(j);
+        for (int j = 0; j + 1 < keep; ++j) m->sim[j] = cosj(j);
       } else {
         int j = 0;
         for (int a = 0; a < keep; ++a)
-          for (int b = a + 1; b < keep; ++b, ++j) s->S[a * stride + b] = s->S[b * stride + a] = cosj(j);
+          for (int b = a + 1; b < keep; ++b, ++j) S[a * stride + b] = S[b * stride + a] = cosj(j);
       }
-      s->n_fix = 0;
-      lm_plan_new(s, keep);
+      m->n_fix = 0;
+      lm_plan_new(m, jobs, keep);
     }
     return;
   }
   // similarities left over from the previous decision
   if (threadIdx.x == 0) {
-    for (int j = 0; j < s->n_fix; ++j) {
-      const int t = s->fix_target[j];
+    for (int j = 0; j < m->n_fix; ++j) {
+      const int t = m->fix_target[j];
       if (t < 0) continue;
-      if (adjacent) s->sim[t] = cosj(j);
-      else s->S[s->fix_pos * stride + t] = s->S[t * stride + s->fix_pos] = cosj(j);
+      if (adjacent) m->sim[t] = cosj(j);
+      else S[m->fix_pos * stride + t] = S[t * stride + m->fix_pos] = cosj(j);
     }
-    s->avg_dst = -1;
+    m->avg_dst = -1;
   }
   __syncthreads();
-  if (phase == LM_PHASE_FLUSH || s->n_new == 0) {
-    if (threadIdx.x == 0) { s->n_fix = 0; s->n_new = 0; }
+  if (phase == LM_PHASE_FLUSH || m->n_new == 0) {
+    __syncthreads();
+    if (threadIdx.x == 0) { m->n_fix = 0; m->n_new = 0; }
     return;
   }
-  const int nf = s->n_fix;   // new-frame jobs start here
+  const int nf = m->n_fix;   // new-frame jobs start here
   const int d = step - keep; // decision slot
   if (adjacent) {
     if (threadIdx.x != 0) return;
     // temporal list of keep + 1 rows with keep adjacent similarities
-    s->order[keep] = step;
-    s->sim[keep - 1] = cosj(nf);
+    m->order[keep] = step;
+    m->sim[keep - 1] = cosj(nf);
     int idx = 0;
     for (int j = 1; j < keep; ++j)
-      if (s->sim[j] > s->sim[idx]) idx = j;
+      if (m->sim[j] > m->sim[idx]) idx = j;
     if (mode == LM_DROP) {
-      if (coins[d]) ++idx;
+      if (coin) ++idx;
       decisions[2 * d] = idx;
       decisions[2 * d + 1] = idx;
-      s->n_fix = 0;
+      m->n_fix = 0;
       if (idx < keep) {
-        for (int j = idx; j < keep; ++j) s->order[j] = s->order[j + 1];
+        for (int j = idx; j < keep; ++j) m->order[j] = m->order[j + 1];
         if (idx == 0) {
-          for (int j = 0; j + 1 < keep; ++j) s->sim[j] = s->sim[j + 1];
+          for (int j = 0; j + 1 < keep; ++j) m->sim[j] = m->sim[j + 1];
         } else {
-          for (int j = idx; j + 1 < keep; ++j) s->sim[j] = s->sim[j + 1];
-          s->jobs[0][0] = s->order[idx - 1];
-          s->jobs[0][1] = s->order[idx];
-          s->fix_target[0] = idx - 1;
-          s->n_fix = 1;
+          for (int j = idx; j + 1 < keep; ++j) m->sim[j] = m->sim[j + 1];
+          jobs[0][0] = m->order[idx - 1];
+          jobs[0][1] = m->order[idx];
+          m->fix_target[0] = idx - 1;
+          m->n_fix = 1;
         }
       }
     } else {
       decisions[2 * d] = idx;
       decisions[2 * d + 1] = idx + 1;
-      const int ha = s->order[idx], hb = s->order[idx + 1];
-      const int dst = s->free_slots[--s->n_free];
-      if (ha >= s->n_in) s->free_slots[s->n_free++] = ha;
-      if (hb >= s->n_in) s->free_slots[s->n_free++] = hb;
-      s->avg_a = ha; s->avg_b = hb; s->avg_dst = dst;
-      s->order[idx + 1] = dst;
-      for (int j = idx; j < keep; ++j) s->order[j] = s->order[j + 1];
-      for (int j = idx; j + 1 < keep; ++j) s->sim[j] = s->sim[j + 1];
+      const int ha = m->order[idx], hb = m->order[idx + 1];
+      const int dst = m->free_slots[--m->n_free];
+      if (ha >= m->n_in) m->free_slots[m->n_free++] = ha;
+      if (hb >= m->n_in) m->free_slots[m->n_free++] = hb;
+      m->avg_a = ha; m->avg_b = hb; m->avg_dst = dst;
+      m->order[idx + 1] = dst;
+      for (int j = idx; j < keep; ++j) m->order[j] = m->order[j + 1];
+      for (int j = idx; j + 1 < keep; ++j) m->sim[j] = m->sim[j + 1];
       int n = 0;
-      s->jobs[n][0] = dst; s->jobs[n][1] = dst; s->fix_target[n++] = -1;
-      if (idx > 0) { s->jobs[n][0] = dst; s->jobs[n][1] = s->order[idx - 1]; s->fix_target[n++] = idx - 1; }
-      if (idx + 1 < keep) { s->jobs[n][0] = dst; s->jobs[n][1] = s->order[idx + 1]; s->fix_target[n++] = idx; }
-      s->n_fix = n;
+      jobs[n][0] = dst; jobs[n][1] = dst; m->fix_target[n++] = -1;
+      if (idx > 0) { jobs[n][0] = dst; jobs[n][1] = m->order[idx - 1]; m->fix_target[n++] = idx - 1; }
+      if (idx + 1 < keep) { jobs[n][0] = dst; jobs[n][1] = m->order[idx + 1]; m->fix_target[n++] = idx; }
+      m->n_fix = n;
     }
-    lm_plan_new(s, step + 1);
+    lm_plan_new(m, jobs, step + 1);
     return;
   }
   // all-pairs modes: the new frame takes the free position at the end of the temporal order
-  const int pf = s->free_pos;
+  const int pf = m->free_pos;
   if (threadIdx.x == 0) {
-    s->handle[pf] = step;
-    s->lorder[keep] = pf;
-    for (int j = 0; j < keep; ++j) {
-      const int q = s->lorder[j];
-      s->S[q * stride + pf] = s->S[pf * stride + q] = cosj(nf + j);
-    }
-    s->S[pf * stride + pf] = LM_NEG;
+    m->handle[pf] = step;
+    m->lorder[keep] = pf;
+    S[pf * stride + pf] = LM_NEG;
+  }
+  for (int j = threadIdx.x; j < keep; j += LM_THREADS) {
+    const int q = m->lorder[j];
+    S[q * stride + pf] = S[pf * stride + q] = cosj(nf + j);
   }
   __syncthreads();
   int left, right;
-  lm_argmax_pairs(s, keep + 1, &left, &right, sv, si);
+  lm_argmax_pairs(m, S, keep + 1, &left, &right, sv, si);
   if (threadIdx.x != 0) return;
   decisions[2 * d] = left;
   decisions[2 * d + 1] = right;
   if (mode == LM_KDROP) {
-    const int idx = coins[d] ? left : right;
-    s->free_pos = s->lorder[idx];
-    for (int j = idx; j < keep; ++j) s->lorder[j] = s->lorder[j + 1];
-    s->n_fix = 0;
+    const int idx = coin ? left : right;
+    m->free_pos = m->lorder[idx];
+    for (int j = idx; j < keep; ++j) m->lorder[j] = m->lorder[j + 1];
+    m->n_fix = 0;
   } else {
-    const int pl = s->lorder[left], pr = s->lorder[right];
-    const int ha = s->handle[pl], hb = s->handle[pr];
-    const int dst = s->free_slots[--s->n_free];
-    if (ha >= s->n_in) s->free_slots[s->n_free++] = ha;
-    if (hb >= s->n_in) s->free_slots[s->n_free++] = hb;
-    s->avg_a = ha; s->avg_b = hb; s->avg_dst = dst;
-    s->handle[pr] = dst;
-    s->free_pos = pl;
-    for (int j = left; j < keep; ++j) s->lorder[j] = s->lorder[j + 1];
+    const int pl = m->lorder[left], pr = m->lorder[right];
+    const int ha = m->handle[pl], hb = m->handle[pr];
+    const int dst = m->free_slots[--m->n_free];
+    if (ha >= m->n_in) m->free_slots[m->n_free++] = ha;
+    if (hb >= m->n_in) m->free_slots[m->n_free++] = hb;
+    m->avg_a = ha; m->avg_b = hb; m->avg_dst = dst;
+    m->handle[pr] = dst;
+    m->free_pos = pl;
+    for (int j = left; j < keep; ++j) m->lorder[j] = m->lorder[j + 1];
     int n = 0;
-    s->jobs[n][0] = dst; s->jobs[n][1] = dst; s->fix_target[n++] = -1;
+    jobs[n][0] = dst; jobs[n][1] = dst; m->fix_target[n++] = -1;
     for (int j = 0; j < keep; ++j) {
-      const int q = s->lorder[j];
+      const int q = m->lorder[j];
       if (q == pr) continue;
-      s->jobs[n][0] = dst; s->jobs[n][1] = s->handle[q]; s->fix_target[n++] = q;
+      jobs[n][0] = dst; jobs[n][1] = m->handle[q]; m->fix_target[n++] = q;
     }
-    s->fix_pos = pr;
-    s->n_fix = n;
+    m->fix_pos = pr;
+    m->n_fix = n;
   }
-  lm_plan_new(s, step + 1);
+  lm_plan_new(m, jobs, step + 1);
 }
 
 template <typename T>
@@ -278,64 +287,77 @@ __global__ void __launch_bounds__(LM_THREADS) lm_stream_kernel(const T* __restri
                                                                float* partial, const uint8_t* __restrict__ coins,
                                                                int* decisions, long long L, int phase, int step) {
   constexpr int V = Vec<T>::N;
-  __shared__ float s_dots[LM_MAX_JOBS * 3];   // 24 KB; the first 24 floats double as the block-reduce scratch
-  __shared__ float s_val[LM_THREADS];
-  __shared__ int s_idx[LM_THREADS];
+  extern __shared__ __align__(16) unsigned char lm_smem[];
+  // the deciding CTA's workspace: dots [jobs][3] | state copy | argmax scratch | (k modes) similarity matrix
+  float* s_dots = reinterpret_cast<float*>(lm_smem);
+  __shared__ float s_red[24];
   __shared__ bool s_last;
+  pdl_trigger();
+  pdl_wait();                                   // state, scratch rows and partial sums of the previous launch
   const int job = blockIdx.y, sp = blockIdx.x, splits = gridDim.x;
-  const int n_jobs = s->n_fix + s->n_new;
+  // everything a CTA needs from the state in ONE round trip (independent loads)
+  const int n_jobs = s->sm.n_fix + s->sm.n_new;
+  const int keep_ = s->sm.keep;
+  const int n_in = s->sm.n_in;
+  const int ha = s->jobs[job][0], hb = s->jobs[job][1];
+  const int avg_dst = s->sm.avg_dst, avg_a = s->sm.avg_a, avg_b = s->sm.avg_b;
+  // issued early so that the deciding CTA does not pay a dependent round trip for it
+  const int coin = (coins != nullptr && phase == LM_PHASE_FRAME && threadIdx.x == 0) ? coins[step - keep_] : 0;
   if (job < n_jobs) {
-    const int n_in = s->n_in;
-    const int ha = s->jobs[job][0], hb = s->jobs[job][1];
-    const int avg_dst = s->avg_dst;
     const bool a_avg = avg_dst >= 0 && ha == avg_dst, b_avg = avg_dst >= 0 && hb == avg_dst;
     const T* pa = lm_row(x, scratch, n_in, L, ha);
     const T* pb = lm_row(x, scratch, n_in, L, hb);
-    const T* qa = nullptr;
-    const T* qb = nullptr;
-    T* pd = nullptr;
-    if (a_avg || b_avg) {
-      qa = lm_row(x, scratch, n_in, L, s->avg_a);
-      qb = lm_row(x, scratch, n_in, L, s->avg_b);
-      if (job == 0) pd = scratch + static_cast<long long>(avg_dst - n_in) * L;   // job 0 always names the average
-    }
     const long long nvec = L / V;
     const long long per = (nvec + splits - 1) / splits;
     const long long v0 = sp * per, v1 = v0 + per < nvec ? v0 + per : nvec;
     float acc[3] = {0.f, 0.f, 0.f};
-    for (long long v = v0 + threadIdx.x; v < v1; v += LM_THREADS) {
-      float fa[V], fb[V];
-      if (a_avg || b_avg) {
-        float ma[V], mb[V];
-        Vec<T>::load(qa + v * V, ma);
-        Vec<T>::load(qb + v * V, mb);
-#pragma unroll
-        for (int k = 0; k < V; ++k) ma[k] = lm_avg<T>(ma[k], mb[k]);
-        if (pd != nullptr) Vec<T>::store(pd + v * V, ma);
-        if (a_avg) {
-#pragma unroll
-          for (int k = 0; k < V; ++k) fa[k] = ma[k];
-        } else {
-          Vec<T>::load(pa + v * V, fa);
-        }
-        if (b_avg) {
-#pragma unroll
-          for (int k = 0; k < V; ++k) fb[k] = ma[k];
-        } else {
-          Vec<T>::load(pb + v * V, fb);
-        }
-      } else {
-        Vec<T>::load(pa + v * V, fa);
-        Vec<T>::load(pb + v * V, fb);
-      }
+    auto fma3 = [&](const float (&fa)[V], const float (&fb)[V]) {
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         acc[0] = fmaf(fa[k], fb[k], acc[0]);
         acc[1] = fmaf(fa[k], fa[k], acc[1]);
         acc[2] = fmaf(fb[k], fb[k], acc[2]);
       }
+    };
+    if (a_avg || b_avg) {
+      const T* qa = lm_row(x, scratch, n_in, L, avg_a);
+      const T* qb = lm_row(x, scratch, n_in, L, avg_b);
+      T* pd = job == 0 ? scratch + static_cast<long long>(avg_dst - n_in) * L : nullptr;   // job 0 always names the average
+      for (long long v = v0 + threadIdx.x; v < v1; v += LM_THREADS) {
+        float fa[V], fb[V], ma[V], mb[V];
+        Vec<T>::load_plain(qa + v * V, ma);
+        Vec<T>::load_plain(qb + v * V, mb);
+        if (!a_avg) Vec<T>::load_plain(pa + v * V, fa);
+        if (!b_avg) Vec<T>::load_plain(pb + v * V, fb);
+#pragma unroll
+        for (int k = 0; k < V; ++k) ma[k] = lm_avg<T>(ma[k], mb[k]);
+        if (pd != nullptr) Vec<T>::store(pd + v * V, ma);
+        if (a_avg) {
+#pragma unroll
+          for (int k = 0; k < V; ++k) fa[k] = ma[k];
+        }
+        if (b_avg) {
+#pragma unroll
+          for (int k = 0; k < V; ++k) fb[k] = ma[k];
+        }
+        fma3(fa, fb);
+      }
+    } else {
+      // two vectors per row in flight per thread: the loop is a chain of DRAM round trips otherwise
+      for (long long v = v0 + threadIdx.x; v < v1; v += 2 * LM_THREADS) {
+        float fa[V], fb[V], ga[V], gb[V];
+        const bool two = v + LM_THREADS < v1;
+        Vec<T>::load_plain(pa + v * V, fa);
+        Vec<T>::load_plain(pb + v * V, fb);
+        if (two) {
+          Vec<T>::load_plain(pa + (v + LM_THREADS) * V, ga);
+          Vec<T>::load_plain(pb + (v + LM_THREADS) * V, gb);
+        }
+        fma3(fa, fb);
+        if (two) fma3(ga, gb);
+      }
     }
-    block_sum<3>(acc, s_dots);
+    block_sum<3>(acc, s_red);
     if (threadIdx.x == 0) {
       float* p = partial + (static_cast<long long>(job) * splits + sp) * 3;
       p[0] = acc[0]; p[1] = acc[1]; p[2] = acc[2];
@@ -344,48 +366,83 @@ __global__ void __launch_bounds__(LM_THREADS) lm_stream_kernel(const T* __restri
   // ticket: the last CTA of the grid folds the partial sums (fixed order) and takes the decision
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(&s->ticket, 1u) == gridDim.x * gridDim.y - 1;
+  if (threadIdx.x == 0) s_last = atomicAdd(&s->sm.ticket, 1u) == gridDim.x * gridDim.y - 1;
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  for (int j = threadIdx.x; j < n_jobs; j += LM_THREADS) {
-    float ab = 0.f, aa = 0.f, bb = 0.f;
-    const float* p = partial + static_cast<long long>(j) * splits * 3;
-    for (int i = 0; i < splits; ++i) {
-      ab += __ldcg(p + 3 * i);
-      aa += __ldcg(p + 3 * i + 1);
-      bb += __ldcg(p + 3 * i + 2);
+  const bool kmode = s->sm.mode == LM_KDROP || s->sm.mode == LM_KMERGE;
+  LmSmall* m = reinterpret_cast<LmSmall*>(s_dots + LM_MAX_JOBS * 3);
+  float* s_val = reinterpret_cast<float*>(m) + LM_SMALL_WORDS;
+  int* s_idx = reinterpret_cast<int*>(s_val + LM_THREADS);
+  float* S = reinterpret_cast<float*>(s_idx + LM_THREADS);
+  // state in: one parallel round trip
+  {
+    const int* src = reinterpret_cast<const int*>(&s->sm);
+    int* dst = reinterpret_cast<int*>(m);
+    for (int i = threadIdx.x; i < LM_SMALL_WORDS; i += LM_THREADS) dst[i] = __ldcg(src + i);
+    if (kmode)       // positions 0..keep are the only live ones
+      for (int i = threadIdx.x; i < (keep_ + 1) * (keep_ + 1); i += LM_THREADS) {
+        const int e = (i / (keep_ + 1)) * (LM_CAP + 1) + i % (keep_ + 1);
+        S[e] = __ldcg(s->S + e);
+      }
+  }
+  // fold: one warp per job, lanes over the splits, fixed shuffle tree
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int j = warp; j < n_jobs; j += LM_THREADS / 32) {
+      const float* p = partial + static_cast<long long>(j) * splits * 3;
+      float ab = 0.f, aa = 0.f, bb = 0.f;
+      for (int i = lane; i < splits; i += 32) {
+        ab += __ldcg(p + 3 * i);
+        aa += __ldcg(p + 3 * i + 1);
+        bb += __ldcg(p + 3 * i + 2);
+      }
+      ab = warp_sum(ab); aa = warp_sum(aa); bb = warp_sum(bb);
+      if (lane == 0) { s_dots[3 * j] = ab; s_dots[3 * j + 1] = aa; s_dots[3 * j + 2] = bb; }
     }
-    s_dots[3 * j] = ab; s_dots[3 * j + 1] = aa; s_dots[3 * j + 2] = bb;
   }
   __syncthreads();
-  lm_decide<T>(s, s_dots, phase, step, coins, decisions, s_val, s_idx);
+  lm_decide<T>(m, S, s->jobs, s_dots, phase, step, coin, decisions, s_val, s_idx);
   __syncthreads();
-  if (threadIdx.x == 0) s->ticket = 0;
+  if (threadIdx.x == 0) m->ticket = 0;
+  __syncthreads();
+  {
+    int* dst = reinterpret_cast<int*>(&s->sm);
+    const int* src = reinterpret_cast<const int*>(m);
+    for (int i = threadIdx.x; i < LM_SMALL_WORDS; i += LM_THREADS) dst[i] = src[i];
+    if (kmode)
+      for (int i = threadIdx.x; i < (keep_ + 1) * (keep_ + 1); i += LM_THREADS) {
+        const int e = (i / (keep_ + 1)) * (LM_CAP + 1) + i % (keep_ + 1);
+        s->S[e] = S[e];
+      }
+  }
 }
+constexpr size_t LM_STREAM_SMEM = LM_MAX_JOBS * 3 * sizeof(float) + sizeof(LmSmall) + LM_THREADS * 8 +
+                                  (LM_CAP + 1) * (LM_CAP + 1) * sizeof(float);
 
 __global__ void lm_init_kernel(LmState* s, int mode, int keep, int n_in) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  s->mode = mode; s->keep = keep; s->n_in = n_in;
-  s->avg_a = s->avg_b = s->avg_dst = -1;
-  s->fix_pos = 0;
-  s->ticket = 0;
-  s->n_fix = 0;
+  LmSmall* m = &s->sm;
+  m->mode = mode; m->keep = keep; m->n_in = n_in;
+  m->avg_a = m->avg_b = m->avg_dst = -1;
+  m->fix_pos = 0;
+  m->ticket = 0;
+  m->n_fix = 0;
   const int stride = LM_CAP + 1;
   int n = 0;
   if (mode == LM_DROP || mode == LM_MERGE) {
-    for (int j = 0; j < keep; ++j) s->order[j] = j;
+    for (int j = 0; j < keep; ++j) m->order[j] = j;
     for (int j = 0; j + 1 < keep; ++j, ++n) { s->jobs[n][0] = j; s->jobs[n][1] = j + 1; }
   } else {
-    for (int j = 0; j < keep; ++j) { s->lorder[j] = j; s->handle[j] = j; }
+    for (int j = 0; j < keep; ++j) { m->lorder[j] = j; m->handle[j] = j; }
     for (int p = 0; p <= keep; ++p) s->S[p * stride + p] = LM_NEG;
-    s->free_pos = keep;
+    m->free_pos = keep;
     for (int a = 0; a < keep; ++a)
       for (int b = a + 1; b < keep; ++b, ++n) { s->jobs[n][0] = a; s->jobs[n][1] = b; }
   }
-  s->n_new = n;
-  s->n_free = 0;
-  for (int j = keep + 2; j >= 0; --j) s->free_slots[s->n_free++] = n_in + j;   // scratch rows, slot 0 handed out first
+  m->n_new = n;
+  m->n_free = 0;
+  for (int j = keep + 2; j >= 0; --j) m->free_slots[m->n_free++] = n_in + j;   // scratch rows, slot 0 handed out first
 }
 
 template <typename T>
@@ -393,32 +450,44 @@ __global__ void __launch_bounds__(LM_THREADS) lm_finish_kernel(const T* __restri
                                                                const LmState* s, T* __restrict__ out,
                                                                float* __restrict__ out_sim, long long L) {
   constexpr int V = Vec<T>::N;
-  const int j = blockIdx.y, keep = s->keep;
-  const bool adjacent = s->mode == LM_DROP || s->mode == LM_MERGE;
-  const int h = adjacent ? s->order[j] : s->handle[s->lorder[j]];
-  const T* src = lm_row(x, scratch, s->n_in, L, h);
+  const LmSmall* m = &s->sm;
+  const int j = blockIdx.y, keep = m->keep;
+  const bool adjacent = m->mode == LM_DROP || m->mode == LM_MERGE;
+  const int h = adjacent ? m->order[j] : m->handle[m->lorder[j]];
+  const T* src = lm_row(x, scratch, m->n_in, L, h);
   T* dst = out + static_cast<long long>(j) * L;
   const long long nvec = L / V;
   for (long long v = static_cast<long long>(blockIdx.x) * LM_THREADS + threadIdx.x; v < nvec;
        v += static_cast<long long>(gridDim.x) * LM_THREADS) {
     float f[V];
-    Vec<T>::load(src + v * V, f);
+    Vec<T>::load_plain(src + v * V, f);
     Vec<T>::store(dst + v * V, f);
   }
   if (blockIdx.x == 0 && out_sim != nullptr) {
     if (adjacent) {
-      if (threadIdx.x == 0 && j + 1 < keep) out_sim[j] = s->sim[j];
+      if (threadIdx.x == 0 && j + 1 < keep) out_sim[j] = m->sim[j];
     } else {
       for (int r = threadIdx.x; r < keep; r += LM_THREADS)
-        out_sim[j * keep + r] = s->S[s->lorder[j] * (LM_CAP + 1) + s->lorder[r]];
+        out_sim[j * keep + r] = s->S[m->lorder[j] * (LM_CAP + 1) + m->lorder[r]];
     }
   }
 }
 
+constexpr int LM_STREAM_MAX_SPLITS = 256;
 static int lm_splits(long long nvec) {
   long long s = nvec / (LM_THREADS * 4);
   if (s < 1) s = 1;
   if (s > LM_MAX_SPLITS) s = LM_MAX_SPLITS;
+  return static_cast<int>(s);
+}
+// streaming kernels: a launch is a chain of round trips, so spread each row pair over as many CTAs as stay
+// co-resident (4 per SM) with at most ~2 vectors per thread and row
+static int lm_stream_splits(long long nvec, int jobs) {
+  long long s = (4LL * sm_count()) / std::max(jobs, 1);
+  const long long by_work = (nvec + LM_THREADS - 1) / LM_THREADS;
+  if (s > by_work) s = by_work;
+  if (s > LM_STREAM_MAX_SPLITS) s = LM_STREAM_MAX_SPLITS;
+  if (s < 1) s = 1;
   return static_cast<int>(s);
 }
 
@@ -432,10 +501,10 @@ static LmLayout lm_layout(int64_t row_elems, int keep, int mode, int dtype) {
   LmLayout l;
   const int vec = dtype == MAVLM_F32 ? 4 : 8;
   const size_t esz = dtype == MAVLM_F32 ? 4 : 2;
-  l.splits = lm_splits(row_elems / vec);
   const int init_jobs = (mode == LM_DROP || mode == LM_MERGE) ? keep - 1 : keep * (keep - 1) / 2;
   const int step_jobs = mode == LM_DROP ? 2 : mode == LM_MERGE ? 4 : mode == LM_KDROP ? keep : 2 * keep + 1;
   l.max_jobs = std::max(std::max(init_jobs, step_jobs), 1);
+  l.splits = lm_stream_splits(row_elems / vec, step_jobs);
   l.state = 0;
   l.partial = lm_align(sizeof(LmState));
   l.scratch = l.partial + lm_align(static_cast<size_t>(l.max_jobs) * l.splits * 3 * sizeof(float));
@@ -455,19 +524,33 @@ static int lm_stream_launch(const void* x, int64_t n_frames, int64_t L, int keep
   const T* xin = static_cast<const T*>(x);
   lm_init_kernel<<<1, 32, 0, st>>>(s, mode, keep, static_cast<int>(n_frames));
   MAVLM_LAUNCH_OK();
+  static bool configured[64][3] = {};     // the attribute is per device and per instantiation
+  const int ti = sizeof(T) == 4 ? 0 : (std::is_same<T, __nv_bfloat16>::value ? 1 : 2);
+  int dev_id = 0;
+  MAVLM_CUDA_OK(cudaGetDevice(&dev_id));
+  if (!configured[dev_id & 63][ti]) {
+    MAVLM_CUDA_OK(cudaFuncSetAttribute(lm_stream_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(LM_STREAM_SMEM)));
+    configured[dev_id & 63][ti] = true;
+  }
   const int init_jobs = (mode == LM_DROP || mode == LM_MERGE) ? keep - 1 : keep * (keep - 1) / 2;
   const int step_jobs = mode == LM_DROP ? 2 : mode == LM_MERGE ? 4 : mode == LM_KDROP ? keep : 2 * keep + 1;
-  lm_stream_kernel<T><<<dim3(lay.splits, std::max(init_jobs, 1)), LM_THREADS, 0, st>>>(xin, scratch, s, partial, coins,
-                                                                                         decisions, L, LM_PHASE_INIT, 0);
-  MAVLM_LAUNCH_OK();
-  for (int64_t i = keep; i < n_frames; ++i) {
-    lm_stream_kernel<T><<<dim3(lay.splits, step_jobs), LM_THREADS, 0, st>>>(xin, scratch, s, partial, coins, decisions, L,
-                                                                            LM_PHASE_FRAME, static_cast<int>(i));
+  auto launch = [&](int jobs_y, int phase, int step) -> int {
+    LaunchCfg lc;
+    make_launch(lc, dim3(lay.splits, jobs_y), dim3(LM_THREADS), LM_STREAM_SMEM, st, 1, 8);
+    MAVLM_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, lm_stream_kernel<T>, xin, scratch, s, partial, coins, decisions,
+                                     static_cast<long long>(L), phase, step));
     MAVLM_LAUNCH_OK();
+    return MAVLM_OK;
+  };
+  int rc = launch(std::max(init_jobs, 1), LM_PHASE_INIT, 0);
+  if (rc != MAVLM_OK) return rc;
+  for (int64_t i = keep; i < n_frames; ++i) {
+    rc = launch(step_jobs, LM_PHASE_FRAME, static_cast<int>(i));
+    if (rc != MAVLM_OK) return rc;
   }
-  lm_stream_kernel<T><<<dim3(lay.splits, step_jobs), LM_THREADS, 0, st>>>(xin, scratch, s, partial, coins, decisions, L,
-                                                                          LM_PHASE_FLUSH, static_cast<int>(n_frames));
-  MAVLM_LAUNCH_OK();
+  rc = launch(step_jobs, LM_PHASE_FLUSH, static_cast<int>(n_frames));
+  if (rc != MAVLM_OK) return rc;
   const long long nvec = L / Vec<T>::N;
   const int gx = static_cast<int>(std::min<long long>((nvec + LM_THREADS - 1) / LM_THREADS, 2LL * sm_count()));
   lm_finish_kernel<T><<<dim3(std::max(gx, 1), keep), LM_THREADS, 0, st>>>(xin, scratch, s, static_cast<T*>(out), out_sim, L);

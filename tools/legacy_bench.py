@@ -1,0 +1,164 @@
+#!/usr/bin/env python
+"""Measure the legacy memories / scene segmentation on one B200: device time per op with CUDA
+events, algorithmic bytes -> achieved GB/s against the measured HBM peak, and the numpy oracle on a bounded sample
+of the same workload beside it.
+
+    python tools/legacy_bench.py [--frames 512] [--out gpurun_out/legacy_bench.json]
+
+Algorithmic bytes (bf16, row = 729 x 1152 tokens = 1.68 MB): drop / merge 2 rows per streamed frame (+1 written row per
+merge), k_drop keep + 1 rows, k_merge 2 keep + 3 rows; k-means per iteration (keep + 1) rows read per frame for
+the distances (centroids from L2 counted once) + 1 row per frame for the update; segmentation 1 row per frame.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import random
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+def peak_hbm():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            j = json.load(f)
+        for k in ("hbm_gbps", "hbm_gb_s", "hbm_GBps"):
+            if k in j:
+                return float(j[k]), "MEASURED_PEAKS.json"
+        for k, v in j.items():
+            if "hbm" in k.lower() and isinstance(v, (int, float)):
+                return float(v), "MEASURED_PEAKS.json"
+    except Exception:
+        pass
+    return 6550.0, "fallback"
+
+
+def dev_time(fn, warm=1, reps=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b))
+    return best
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=512)
+    ap.add_argument("--keep", type=int, default=3)
+    ap.add_argument("--cpu-frames", type=int, default=24)
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "legacy_bench.json"))
+    args = ap.parse_args()
+    import mavlm_b200  # noqa: F401
+    from mavlm_b200 import legacy as L
+    from mavlm_b200 import _lib
+    from gen_golden_legacy import ntm_params, scene_frames
+    from oracle import legacy_memory_oracle as O
+
+    torch.cuda.set_device(0)
+    T, T0, P, D = args.frames, args.keep, 729, 1152
+    row_b = P * D * 2
+    peak, peak_src = peak_hbm()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    base = torch.randn(8, P, D, device="cuda", generator=g)
+    scene = torch.randint(0, 8, (T,), device="cuda", generator=g).sort()[0]
+    x = (base[scene] + 0.5 * torch.randn(T, P, D, device="cuda", generator=g)).to(torch.bfloat16)
+    del base
+    res = {"frames": T, "keep": T0, "row_bytes": row_b, "hbm_peak_gbps": peak, "peak_source": peak_src, "ops": {}}
+    lib = _lib.load()
+
+    def record(name, ms, bytes_, launches, extra=None):
+        r = {"ms": ms, "frames_per_s": T / ms * 1e3, "algorithmic_gb": bytes_ / 1e9, "achieved_gbps": bytes_ / ms / 1e6,
+             "frac_of_hbm_peak": bytes_ / ms / 1e6 / peak, "launches": launches}
+        if extra:
+            r.update(extra)
+        res["ops"][name] = r
+        print(name, json.dumps(r), flush=True)
+
+    n = T - T0
+    coins = [random.randint(0, 1) for _ in range(n)]
+    per_frame_rows = {L.DROP: 2, L.MERGE: 3, L.K_DROP: T0 + 1, L.K_MERGE: 2 * T0 + 4}
+    for name, mode in (("drop", L.DROP), ("merge", L.MERGE), ("k_drop", L.K_DROP), ("k_merge", L.K_MERGE)):
+        c0 = lib.mavlm_launch_count()
+        L.stream_compress(x, T0, mode, coins, return_steps=False)
+        launches = lib.mavlm_launch_count() - c0
+        ms = dev_time(lambda: L.stream_compress(x, T0, mode, coins, return_steps=False))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        L.stream_compress(x, T0, mode, coins, return_steps=False)
+        host_ms = (time.perf_counter() - t0) * 1e3          # time the host needs to enqueue the launches
+        torch.cuda.synchronize()
+        record(f"stream_{name}", ms, n * per_frame_rows[mode] * row_b, launches,
+               {"us_per_frame": ms * 1e3 / n, "host_enqueue_ms": host_ms})
+
+    w = torch.ones(T, device="cuda")
+    init = torch.arange(T0)
+    X = x.reshape(T, -1)
+    c0 = lib.mavlm_launch_count()
+    _, _, _, iters = L._kmeans(X, T0, w, init)
+    launches = lib.mavlm_launch_count() - c0
+    ms = dev_time(lambda: L._kmeans(X, T0, w, init))
+    record("weighted_kmeans", ms, (iters + 1) * T * 2 * row_b, launches, {"iterations": iters + 1})
+
+    ms = dev_time(lambda: L.adjacent_cosine(x))
+    record("adjacent_cosine", ms, T * row_b, 1)
+    ms = dev_time(lambda: L.frame_means(x))
+    record("frame_means", ms, T * row_b, 1)
+    pooled = torch.randn(T, 196, 3584, device="cuda", generator=g).to(torch.bfloat16)
+    ms = dev_time(lambda: L.sample_scenes_priority(pooled, 32))
+    record("sample_scenes_priority_196x3584", ms, T * 196 * 3584 * 2, 4)
+    del pooled
+
+    ntm = L.NeuralTuringMachine().eval().cuda().to(torch.bfloat16)
+    ntm.load_state_dict({k: torch.from_numpy(v) for k, v in ntm_params(700, D).items()})
+    ntm = ntm.to(torch.bfloat16)
+    Tn = min(T, 64)
+    fn = lambda m, nf, update_ratio: ntm.gated_update(m, nf, update_ratio)   # noqa: E731
+    with torch.no_grad():
+        c0 = lib.mavlm_launch_count()
+        L.attention_feature(x[:Tn], T0, fn, 0.2)
+        launches = lib.mavlm_launch_count() - c0
+        ms = dev_time(lambda: L.attention_feature(x[:Tn], T0, fn, 0.2))
+    steps = (Tn - T0 + T0 - 1) // T0
+    m_rows = T0 * P
+    flops = steps * (2 * 2 * m_rows * D * D + 2 * 2 * m_rows * m_rows * D)
+    res["ops"]["turing_memory"] = {"frames": Tn, "ms": ms, "frames_per_s": Tn / ms * 1e3, "tflops": flops / ms / 1e9,
+                                   "launches": launches}
+    print("turing_memory", json.dumps(res["ops"]["turing_memory"]), flush=True)
+
+    # numpy oracle on a bounded sample of the same frames (host cores: numpy / BLAS threads as configured)
+    Tc = args.cpu_frames
+    xc = x[:Tc].float().cpu().numpy()
+    cpu = {}
+    for name, fn_ in (("drop", lambda: O.drop_feature(xc, T0, coins[:Tc - T0])), ("merge", lambda: O.merge_feature(xc, T0)),
+                      ("k_drop", lambda: O.k_drop_feature(xc, T0, coins[:Tc - T0])),
+                      ("k_merge", lambda: O.k_merge_feature(xc, T0))):
+        t0 = time.perf_counter()
+        fn_()
+        cpu[f"stream_{name}"] = {"frames": Tc, "frames_per_s": Tc / (time.perf_counter() - t0)}
+    t0 = time.perf_counter()
+    O.kmeans_feature(xc, T0, list(range(T0)), random.randint, weights=np.ones(Tc, np.float32), weighted=True)
+    cpu["weighted_kmeans"] = {"frames": Tc, "frames_per_s": Tc / (time.perf_counter() - t0)}
+    res["cpu_oracle"] = {"kind": "port", "cores": os.cpu_count(), "sample": f"first {Tc} frames", "ops": cpu}
+    print("cpu_oracle", json.dumps(res["cpu_oracle"]), flush=True)
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    with open(args.out, "w") as f:
+        json.dump(res, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
