@@ -677,29 +677,40 @@ __global__ void __launch_bounds__(128) avg_pool_kernel(const T* __restrict__ x, 
 // ---------------------------------------------------------------------------------------------------------------
 // k-means over whole frames (rows of L elements)
 // ---------------------------------------------------------------------------------------------------------------
-// partial[t][split][k] = sum over the split of (x[t] - c[k])^2; x slice read once, centroids from L2
+// partial[t][split][k] = sum over the split of (x[t] - c[k])^2.  The frame slice is read once per group of 8
+// centroids (registers), the centroid slices come from L2 (every frame's CTAs read the same ones).
 template <typename T>
 __global__ void __launch_bounds__(LM_THREADS) kmeans_dist_kernel(const T* __restrict__ x, const T* __restrict__ cent,
                                                                  long long L, int K, float* __restrict__ partial) {
   constexpr int V = Vec<T>::N;
-  __shared__ float red[8];
+  constexpr int KG = 8;
+  __shared__ float red[KG * 8];
   const int t = blockIdx.y, sp = blockIdx.x, splits = gridDim.x;
   const long long nvec = L / V;
   const long long per = (nvec + splits - 1) / splits;
   const long long v0 = sp * per, v1 = v0 + per < nvec ? v0 + per : nvec;
   const T* px = x + static_cast<long long>(t) * L;
-  for (int k = 0; k < K; ++k) {
-    const T* pc = cent + static_cast<long long>(k) * L;
-    float acc[1] = {0.f};
-    for (long long v = v0 + threadIdx.x; v < v1; v += LM_THREADS) {
-      float fx[V], fc[V];
-      Vec<T>::load(px + v * V, fx);
-      Vec<T>::load(pc + v * V, fc);
+  for (int k0 = 0; k0 < K; k0 += KG) {
+    const int kn = K - k0 < KG ? K - k0 : KG;
+    float acc[KG];
 #pragma unroll
-      for (int c = 0; c < V; ++c) { const float d = fx[c] - fc[c]; acc[0] = fmaf(d, d, acc[0]); }
+    for (int k = 0; k < KG; ++k) acc[k] = 0.f;
+    for (long long v = v0 + threadIdx.x; v < v1; v += LM_THREADS) {
+      float fx[V];
+      Vec<T>::load(px + v * V, fx);
+#pragma unroll
+      for (int k = 0; k < KG; ++k) {
+        if (k < kn) {
+          float fc[V];
+          Vec<T>::load(cent + static_cast<long long>(k0 + k) * L + v * V, fc);
+#pragma unroll
+          for (int c = 0; c < V; ++c) { const float d = fx[c] - fc[c]; acc[k] = fmaf(d, d, acc[k]); }
+        }
+      }
     }
-    block_sum<1>(acc, red);
-    if (threadIdx.x == 0) partial[(static_cast<long long>(t) * splits + sp) * K + k] = acc[0];
+    block_sum<KG>(acc, red);
+    if (threadIdx.x == 0)
+      for (int k = 0; k < kn; ++k) partial[(static_cast<long long>(t) * splits + sp) * K + k0 + k] = acc[k];
   }
 }
 
