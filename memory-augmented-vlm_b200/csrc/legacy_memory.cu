@@ -480,6 +480,15 @@ static int lm_splits(long long nvec) {
   if (s > LM_MAX_SPLITS) s = LM_MAX_SPLITS;
   return static_cast<int>(s);
 }
+// k-means: frames x splits CTAs; a few waves of fat CTAs instead of tens of thousands of thin ones
+static int lm_kmeans_splits(long long nvec, long long frames) {
+  long long s = (16LL * sm_count() + frames - 1) / std::max<long long>(frames, 1);
+  const long long by_work = nvec / (LM_THREADS * 4);
+  if (s > by_work) s = by_work;
+  if (s > LM_MAX_SPLITS) s = LM_MAX_SPLITS;
+  if (s < 1) s = 1;
+  return static_cast<int>(s);
+}
 // streaming kernels: a launch is a chain of round trips, so spread each row pair over as many CTAs as stay
 // co-resident (4 per SM) with at most ~2 vectors per thread and row
 static int lm_stream_splits(long long nvec, int jobs) {
@@ -983,7 +992,7 @@ int mavlm_avg_pool_fwd(const void* x, void* out, int frames, int side, int windo
 
 size_t mavlm_kmeans_workspace_bytes(int64_t n_frames, int64_t row_elems, int clusters, int dtype) {
   if (n_frames <= 0 || row_elems <= 0 || clusters < 1 || !dtype_ok(dtype)) return 0;
-  const int splits = lm_splits(row_elems / (dtype == MAVLM_F32 ? 4 : 8));
+  const int splits = lm_kmeans_splits(row_elems / (dtype == MAVLM_F32 ? 4 : 8), n_frames);
   return lm_align(static_cast<size_t>(n_frames) * splits * clusters * sizeof(float)) +   // distance partials
          lm_align(static_cast<size_t>(n_frames) * sizeof(int)) +                         // members
          lm_align(static_cast<size_t>(clusters + 1) * sizeof(int)) +                     // offsets
@@ -1004,7 +1013,7 @@ int mavlm_kmeans_iter_fwd(const void* x, const float* weights, const void* cent,
   MAVLM_REQUIRE(workspace != nullptr && workspace_bytes >= need, MAVLM_E_WORKSPACE, "kmeans: workspace %zu < %zu bytes",
                 workspace_bytes, need);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int splits = lm_splits(row_elems / vec);
+  const int splits = lm_kmeans_splits(row_elems / vec, n_frames);
   char* base = static_cast<char*>(workspace);
   float* partial = reinterpret_cast<float*>(base);
   base += lm_align(static_cast<size_t>(n_frames) * splits * clusters * sizeof(float));

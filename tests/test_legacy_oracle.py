@@ -137,3 +137,25 @@ def test_whole_legacy_memory(sample_type, seed):
     assert list(res.shape) == list(G[f"temporal.{sample_type}.shape"])
     close(res[TEMPORAL_SAMPLE], G[f"temporal.{sample_type}.sample"], 2e-5)
     close(res.sum(axis=(1, 2)), G[f"temporal.{sample_type}.frame_sums"], 2e-4)
+
+
+def test_host_side_of_the_drop_in():
+    """What runs without a GPU: boundary lists, step replay, and the refusal to compute on CPU tensors."""
+    from mavlm_b200 import legacy as L
+    for key, want in META["uniform_segment"].items():
+        T, d = map(int, key.split("_"))
+        assert L.uniform_segment(T, d) == want, key
+    # decisions (idx, idx+1) of a merge run rebuild the reference's step lists
+    want = META["merge3.steps"]
+    dec = []
+    for before, after in zip(want[:-1], want[1:]):
+        allg = before + [[max(max(g) for g in before) + 1]]
+        idx = next(i for i in range(len(after)) if after[i] != allg[i])
+        dec.append((idx, idx + 1))
+    assert L._replay_steps(L.MERGE, INP["stream"].shape[0], 3, dec, None) == want
+    with pytest.raises(RuntimeError):
+        L.segment(torch.from_numpy(INP["seg_feat"]))
+    with pytest.raises(RuntimeError):
+        L.merge_feature(torch.from_numpy(INP["stream"]), 3)
+    f, s_, st = L.merge_feature(torch.from_numpy(INP["stream"][:2]), 3)          # short video: passes through untouched
+    assert f.shape[0] == 2 and s_ is None and st == [[[0], [1]]]
