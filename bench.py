@@ -439,8 +439,73 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_legacy(args):
+    """`--workload legacy`: the Flash-VStream-style memories / scene segmentation of SURVEY.md 8f-4 on one GPU
+    (tools/legacy_bench.py), with the numpy oracle timed beside it.  Headline of this line: merge_feature, 512 frames of
+    729 x 1152 bf16 tokens kept to 3; the other ops are under "ops".  One step = one whole video."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import legacy_bench
+    from oracle import legacy_memory_oracle as O
+    frames, keep = 512, 3
+    if args.impl == "reference":
+        import random
+        import numpy as np
+        use_all_host_cores()
+        steps = args.steps if args.steps is not None else 3
+        warmup = args.warmup if args.warmup is not None else 1
+        sample_frames = 24
+        x = np.random.default_rng(0).standard_normal((sample_frames, 729, 1152)).astype(np.float32)
+        for _ in range(warmup):
+            O.merge_feature(x, keep)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.merge_feature(x, keep)
+        dt = time.perf_counter() - t0
+        fps = sample_frames * steps / dt
+        cb = {"value": fps, "unit": "frames/s", "cores": blas_threads(), "kind": "port",
+              "sample": f"merge_feature on the first {sample_frames} frames per step (numpy oracle)"}
+        print(json.dumps({"impl": "reference", "metric": "legacy_merge_feature_frames_per_s", "value": fps, "unit": "frames/s",
+                          "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * dt / steps,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": f"legacy merge_feature, {frames} frames x 729 x 1152, keep {keep}"},
+                          "gpu_launches": 0, "cpu_baseline": cb,
+                          "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
+    import torch
+    sampler = ClockSampler(0)
+    sampler.mark_start()
+    res = legacy_bench.run(frames, keep, cpu_frames=24, oracle=None if args.no_cpu_baseline else O, quiet=True)
+    sampler.mark_end()
+    clocks = sampler.stop()
+    op = res["ops"]["stream_merge"]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "legacy_stream_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh).get("dram_bytes_per_launch")
+    line = {"metric": "legacy_merge_feature_frames_per_s", "value": op["frames_per_s"], "unit": "frames/s", "n_gpus": 1,
+            "steps": 3, "warmup": 1, "ms_per_step": op["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"legacy merge_feature (SURVEY 8f-4), {frames} frames x 729 x 1152 bf16 kept to {keep}; "
+                                   "inputs (860 MB) larger than L2"},
+            "clocks": clocks, "gpu_launches": op["launches"],
+            "roofline": {"bound": "hbm", "achieved": op["achieved_gbps"], "peak": res["hbm_peak_gbps"], "unit": "GB/s",
+                         "frac": op["frac_of_hbm_peak"], "traffic": traffic,
+                         "note": "one launch per streamed frame; 3 rows of 1.68 MB per launch; latency-chain bound"},
+            "ops": res["ops"]}
+    if "cpu_oracle" in res:
+        c = res["cpu_oracle"]
+        line["cpu_baseline"] = {"value": c["ops"]["stream_merge"]["frames_per_s"], "unit": "frames/s", "cores": c["cores"],
+                                "kind": "port", "sample": "merge_feature, " + c["sample"], "ops": c["ops"]}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="path", choices=["path", "legacy"],
+                    help="path: the headline visual-memory path (BASELINE.json); legacy: SURVEY 8f-4 memories")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
@@ -450,7 +515,9 @@ def main():
                     help="only the device-timed graph replays (no e2e / breakdown / CPU passes): the short run that is "
                          "put under `ncu` for the per-launch list in profiles/")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "legacy":
+        run_legacy(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

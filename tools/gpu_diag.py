@@ -263,37 +263,22 @@ def _build_models(d, dv, dtype, seed=0, chunk=32, frames=64, depth=2):
 
 
 def fam_pipe():
-    import numpy as np
+    """Whole-path parity lives in tests/test_gpu_parity.py (the oracle is test infrastructure and is only imported
+    from tests/, smoke() and bench.py); this family just runs the path once at each size and reports finiteness."""
     import torch
-    from oracle import vismem_oracle as O
-    import mavlm_b200 as M
     torch.manual_seed(0)
-    for (d, dv, dt, frames, chunk, tol) in ((64, 16, torch.float32, 6, 2, 1e-5), (896, 1152, torch.float32, 8, 4, 1e-5),
-                                            (896, 1152, torch.bfloat16, 64, 32, 2e-2),
-                                            (3584, 1152, torch.bfloat16, 64, 32, 2e-2)):
+    for (d, dv, dt, frames, chunk) in ((64, 16, torch.float32, 6, 2), (896, 1152, torch.float32, 8, 4),
+                                       (896, 1152, torch.bfloat16, 64, 32), (3584, 1152, torch.bfloat16, 64, 32)):
         t0 = time.time()
-        pipe, w = _build_models(d, dv, dt, chunk=chunk)
+        pipe, _ = _build_models(d, dv, dt, chunk=chunk)
         g = torch.Generator().manual_seed(1234)
         x = torch.randn(1, frames, 729, dv, generator=g)
         idx = torch.arange(frames)[None]
-        xin = x.to("cuda").to(dt)
-        res = pipe(xin, idx)
+        res = pipe(x.to("cuda").to(dt), idx)
         torch.cuda.synchronize()
-        t1 = time.time()
-        if dt == torch.bfloat16:   # oracle sees the bf16-rounded weights and inputs
-            wq = {k_: torch.from_numpy(v_).bfloat16().double().numpy() if k_ != "positional_encoding.frame_embed" else v_
-                  for k_, v_ in w.items()}
-            xo = xin[0].double().cpu().numpy()
-        else:
-            wq, xo = w, x[0].double().numpy()
-        ref = O.visual_memory_path(xo, idx[0].numpy(), wq, pe_table=w["positional_encoding.frame_embed"].astype(np.float64),
-                                   prompt_mem=wq["embed"][list(O.MEMORY_PROMPT_IDS)],
-                                   prompt_frm=wq["embed"][list(O.FRAME_PROMPT_IDS)], chunk=chunk)
-        t2 = time.time()
-        es = O.normalized_max_error(res["sequence"][0].double().cpu().numpy(), ref["sequence"])
-        em = O.normalized_max_error(res["states"][0, -1].double().cpu().numpy().reshape(8, 196, d), ref["states"][-1])
-        print(f"pipe D{d} {dt} F{frames} C{chunk}: seq err {es:.3e} final-state err {em:.3e} (tol {tol}) "
-              f"{'OK' if max(es, em) < tol else 'BAD'}  [gpu+build {t1 - t0:.1f}s oracle {t2 - t1:.1f}s]", flush=True)
+        ok = bool(torch.isfinite(res["sequence"].float()).all())
+        print(f"pipe D{d} {dt} F{frames} C{chunk}: sequence {tuple(res['sequence'].shape)} finite={ok} "
+              f"[{time.time() - t0:.1f}s]  (parity: pytest tests/test_gpu_parity.py)", flush=True)
 
 
 def fam_perf():

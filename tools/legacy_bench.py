@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Measure the legacy memories / scene segmentation on one B200: device time per op with CUDA
-events, algorithmic bytes -> achieved GB/s against the measured HBM peak, and the numpy oracle on a bounded sample
-of the same workload beside it.
+events, algorithmic bytes -> achieved GB/s against the measured HBM peak.  The CPU arm (numpy oracle on a bounded
+sample of the same workload) is added by `python bench.py --workload legacy`, the only place besides tests/ and
+smoke() that may execute oracle/.
 
     python tools/legacy_bench.py [--frames 512] [--out gpurun_out/legacy_bench.json]
 
@@ -56,21 +57,16 @@ def dev_time(fn, warm=1, reps=3):
     return best
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--frames", type=int, default=512)
-    ap.add_argument("--keep", type=int, default=3)
-    ap.add_argument("--cpu-frames", type=int, default=24)
-    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "legacy_bench.json"))
-    args = ap.parse_args()
+def run(frames: int = 512, keep: int = 3, cpu_frames: int = 24, oracle=None, out=None, quiet: bool = False) -> dict:
+    """`oracle`: the oracle module (passed in by bench.py) or None to skip the CPU arm."""
     import mavlm_b200  # noqa: F401
     from mavlm_b200 import legacy as L
     from mavlm_b200 import _lib
-    from gen_golden_legacy import ntm_params, scene_frames
-    from oracle import legacy_memory_oracle as O
+    from gen_golden_legacy import ntm_params
+    O = oracle
 
     torch.cuda.set_device(0)
-    T, T0, P, D = args.frames, args.keep, 729, 1152
+    T, T0, P, D = frames, keep, 729, 1152
     row_b = P * D * 2
     peak, peak_src = peak_hbm()
     g = torch.Generator(device="cuda").manual_seed(0)
@@ -87,7 +83,8 @@ def main():
         if extra:
             r.update(extra)
         res["ops"][name] = r
-        print(name, json.dumps(r), flush=True)
+        if not quiet:
+            print(name, json.dumps(r), flush=True)
 
     n = T - T0
     coins = [random.randint(0, 1) for _ in range(n)]
@@ -138,10 +135,13 @@ def main():
     flops = steps * (2 * 2 * m_rows * D * D + 2 * 2 * m_rows * m_rows * D)
     res["ops"]["turing_memory"] = {"frames": Tn, "ms": ms, "frames_per_s": Tn / ms * 1e3, "tflops": flops / ms / 1e9,
                                    "launches": launches}
-    print("turing_memory", json.dumps(res["ops"]["turing_memory"]), flush=True)
+    if not quiet:
+        print("turing_memory", json.dumps(res["ops"]["turing_memory"]), flush=True)
+    if O is None:
+        return _save(res, out)
 
     # numpy oracle on a bounded sample of the same frames (host cores: numpy / BLAS threads as configured)
-    Tc = args.cpu_frames
+    Tc = cpu_frames
     xc = x[:Tc].float().cpu().numpy()
     cpu = {}
     for name, fn_ in (("drop", lambda: O.drop_feature(xc, T0, coins[:Tc - T0])), ("merge", lambda: O.merge_feature(xc, T0)),
@@ -154,10 +154,26 @@ def main():
     O.kmeans_feature(xc, T0, list(range(T0)), random.randint, weights=np.ones(Tc, np.float32), weighted=True)
     cpu["weighted_kmeans"] = {"frames": Tc, "frames_per_s": Tc / (time.perf_counter() - t0)}
     res["cpu_oracle"] = {"kind": "port", "cores": os.cpu_count(), "sample": f"first {Tc} frames", "ops": cpu}
-    print("cpu_oracle", json.dumps(res["cpu_oracle"]), flush=True)
-    os.makedirs(os.path.dirname(args.out), exist_ok=True)
-    with open(args.out, "w") as f:
-        json.dump(res, f, indent=1)
+    if not quiet:
+        print("cpu_oracle", json.dumps(res["cpu_oracle"]), flush=True)
+    return _save(res, out)
+
+
+def _save(res: dict, out) -> dict:
+    if out:
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        with open(out, "w") as f:
+            json.dump(res, f, indent=1)
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=512)
+    ap.add_argument("--keep", type=int, default=3)
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "legacy_bench.json"))
+    args = ap.parse_args()
+    run(args.frames, args.keep, out=args.out)
 
 
 if __name__ == "__main__":
