@@ -493,7 +493,7 @@ def run_legacy(args):
             "clocks": clocks, "gpu_launches": op["launches"],
             "roofline": {"bound": "hbm", "achieved": op["achieved_gbps"], "peak": res["hbm_peak_gbps"], "unit": "GB/s",
                          "frac": op["frac_of_hbm_peak"], "traffic": traffic,
-                         "note": "one launch per streamed frame; 3 rows of 1.68 MB per launch; latency-chain bound"},
+                         "note": "one launch per streamed frame; 6 rows of 1.68 MB per launch (5 read, 1 written); latency-chain bound"},
             "ops": res["ops"]}
     if "cpu_oracle" in res:
         c = res["cpu_oracle"]

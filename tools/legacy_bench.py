@@ -6,8 +6,9 @@ smoke() that may execute oracle/.
 
     python tools/legacy_bench.py [--frames 512] [--out gpurun_out/legacy_bench.json]
 
-Algorithmic bytes (bf16, row = 729 x 1152 tokens = 1.68 MB): drop / merge 2 rows per streamed frame (+1 written row per
-merge), k_drop keep + 1 rows, k_merge 2 keep + 3 rows; k-means per iteration (keep + 1) rows read per frame for
+Algorithmic bytes (bf16, row = 729 x 1152 tokens = 1.68 MB), distinct rows per streamed frame: drop 2 (last kept + new),
+merge 6 at keep >= 3 (the two sources of the pending average, its two neighbours, the new frame, the written average),
+k_drop keep + 1, k_merge keep + 3; k-means per iteration (keep + 1) rows read per frame for
 the distances (centroids from L2 counted once) + 1 row per frame for the update; segmentation 1 row per frame.
 """
 from __future__ import annotations
@@ -88,7 +89,9 @@ def run(frames: int = 512, keep: int = 3, cpu_frames: int = 24, oracle=None, out
 
     n = T - T0
     coins = [random.randint(0, 1) for _ in range(n)]
-    per_frame_rows = {L.DROP: 2, L.MERGE: 3, L.K_DROP: T0 + 1, L.K_MERGE: 2 * T0 + 4}
+    # distinct rows a streamed frame touches (repeats across a launch's row pairs are L2 hits: ncu shows 3.43 MB DRAM
+    # per drop launch = 2 rows, 8.47 MB per merge launch = 5 rows read, the written row stays in L2)
+    per_frame_rows = {L.DROP: 2, L.MERGE: 2 + min(2, T0 - 1) + 1 + 1, L.K_DROP: T0 + 1, L.K_MERGE: 2 + (T0 - 1) + 1 + 1}
     for name, mode in (("drop", L.DROP), ("merge", L.MERGE), ("k_drop", L.K_DROP), ("k_merge", L.K_MERGE)):
         c0 = lib.mavlm_launch_count()
         L.stream_compress(x, T0, mode, coins, return_steps=False)
