@@ -480,14 +480,12 @@ static int lm_splits(long long nvec) {
   if (s > LM_MAX_SPLITS) s = LM_MAX_SPLITS;
   return static_cast<int>(s);
 }
-// k-means: frames x splits CTAs; a few waves of fat CTAs instead of tens of thousands of thin ones
+// k-means: frames x splits CTAs.  Thin CTAs (a few vectors per thread) measured faster than a few waves of fat ones
+// (2.4 vs 3.2 ms for 512 frames x 3 iterations): the loops are latency-bound per thread, so parallelism across CTAs
+// is what keeps HBM busy.
 static int lm_kmeans_splits(long long nvec, long long frames) {
-  long long s = (16LL * sm_count() + frames - 1) / std::max<long long>(frames, 1);
-  const long long by_work = nvec / (LM_THREADS * 4);
-  if (s > by_work) s = by_work;
-  if (s > LM_MAX_SPLITS) s = LM_MAX_SPLITS;
-  if (s < 1) s = 1;
-  return static_cast<int>(s);
+  (void)frames;
+  return lm_splits(nvec);
 }
 // streaming kernels: a launch is a chain of round trips, so spread each row pair over as many CTAs as stay
 // co-resident (4 per SM) with at most ~2 vectors per thread and row
@@ -686,40 +684,31 @@ __global__ void __launch_bounds__(128) avg_pool_kernel(const T* __restrict__ x, 
 // ---------------------------------------------------------------------------------------------------------------
 // k-means over whole frames (rows of L elements)
 // ---------------------------------------------------------------------------------------------------------------
-// partial[t][split][k] = sum over the split of (x[t] - c[k])^2.  The frame slice is read once per group of 8
-// centroids (registers), the centroid slices come from L2 (every frame's CTAs read the same ones).
+// partial[t][split][k] = sum over the split of (x[t] - c[k])^2.  One pass per centroid; the frame slice (26 KB per CTA)
+// is re-read from L1/L2.  A variant that kept the slice in registers against 8 centroids at once was slower
+// (2.9 vs 2.4 ms for 512 frames x 3 iterations: thin CTAs, the 8-wide block reduction dominated).
 template <typename T>
 __global__ void __launch_bounds__(LM_THREADS) kmeans_dist_kernel(const T* __restrict__ x, const T* __restrict__ cent,
                                                                  long long L, int K, float* __restrict__ partial) {
   constexpr int V = Vec<T>::N;
-  constexpr int KG = 8;
-  __shared__ float red[KG * 8];
+  __shared__ float red[8];
   const int t = blockIdx.y, sp = blockIdx.x, splits = gridDim.x;
   const long long nvec = L / V;
   const long long per = (nvec + splits - 1) / splits;
   const long long v0 = sp * per, v1 = v0 + per < nvec ? v0 + per : nvec;
   const T* px = x + static_cast<long long>(t) * L;
-  for (int k0 = 0; k0 < K; k0 += KG) {
-    const int kn = K - k0 < KG ? K - k0 : KG;
-    float acc[KG];
-#pragma unroll
-    for (int k = 0; k < KG; ++k) acc[k] = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const T* pc = cent + static_cast<long long>(k) * L;
+    float acc[1] = {0.f};
     for (long long v = v0 + threadIdx.x; v < v1; v += LM_THREADS) {
-      float fx[V];
+      float fx[V], fc[V];
       Vec<T>::load(px + v * V, fx);
+      Vec<T>::load(pc + v * V, fc);
 #pragma unroll
-      for (int k = 0; k < KG; ++k) {
-        if (k < kn) {
-          float fc[V];
-          Vec<T>::load(cent + static_cast<long long>(k0 + k) * L + v * V, fc);
-#pragma unroll
-          for (int c = 0; c < V; ++c) { const float d = fx[c] - fc[c]; acc[k] = fmaf(d, d, acc[k]); }
-        }
-      }
+      for (int c = 0; c < V; ++c) { const float d = fx[c] - fc[c]; acc[0] = fmaf(d, d, acc[0]); }
     }
-    block_sum<KG>(acc, red);
-    if (threadIdx.x == 0)
-      for (int k = 0; k < kn; ++k) partial[(static_cast<long long>(t) * splits + sp) * K + k0 + k] = acc[k];
+    block_sum<1>(acc, red);
+    if (threadIdx.x == 0) partial[(static_cast<long long>(t) * splits + sp) * K + k] = acc[0];
   }
 }
 
@@ -779,7 +768,21 @@ __global__ void __launch_bounds__(LM_THREADS) kmeans_update_kernel(const T* __re
       float acc[V];
 #pragma unroll
       for (int c = 0; c < V; ++c) acc[c] = 0.f;
-      for (int m = m0; m < m1; ++m) {
+      int m = m0;
+      for (; m + 4 <= m1; m += 4) {          // 4 frames in flight per thread
+        float fx[4][V], w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int t = members[m + u];
+          w[u] = weights != nullptr ? weights[t] : 1.0f;
+          Vec<T>::load(x + static_cast<long long>(t) * L + v * V, fx[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int c = 0; c < V; ++c) acc[c] = fmaf(w[u], fx[u][c], acc[c]);
+      }
+      for (; m < m1; ++m) {
         const int t = members[m];
         const float w = weights != nullptr ? weights[t] : 1.0f;
         float fx[V];
