@@ -157,6 +157,16 @@ MAVLM_API size_t mavlm_stream_compress_workspace_bytes(int64_t row_elems, int ke
 MAVLM_API int mavlm_stream_compress_fwd(const void* x, int64_t n_frames, int64_t row_elems, int keep, int mode,
                                         const uint8_t* coins, void* out, float* out_sim, int32_t* decisions,
                                         void* workspace, size_t workspace_bytes, int dtype, void* stream);
+/* The same for a batch of independent videos in one launch sequence (grid.z = video; one launch per frame index up to
+ * the longest video): x_ptrs DEVICE array of `batch` base pointers, n_frames HOST array, coins [batch, coin_stride],
+ * decisions [batch, coin_stride, 2] with coin_stride >= longest - keep, out [batch, keep, row_elems], out_sim
+ * [batch, keep - 1] (at least 1) or [batch, keep, keep].  Frames and decisions are those of `batch` single calls
+ * (similarities agree to fp32 rounding: the number of partial sums per row pair depends on the batch). */
+MAVLM_API size_t mavlm_stream_compress_batched_workspace_bytes(int batch, int64_t row_elems, int keep, int mode, int dtype);
+MAVLM_API int mavlm_stream_compress_batched_fwd(const void* const* x_ptrs, const int64_t* n_frames, int batch,
+                                                int64_t row_elems, int keep, int mode, const uint8_t* coins,
+                                                int64_t coin_stride, void* out, float* out_sim, int32_t* decisions,
+                                                void* workspace, size_t workspace_bytes, int dtype, void* stream);
 /* out[t, :] = mean over the tokens of frame t: the `features.mean(dim=1)` feeding segment() (segment.py:266) and the
  * scheduler (llava_arch.py:528).  x [frames, tokens, dim]. */
 MAVLM_API int mavlm_frame_mean_fwd(const void* x, void* out, int frames, int tokens, int dim, int dtype, void* stream);

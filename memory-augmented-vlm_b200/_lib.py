@@ -65,6 +65,9 @@ PROTOTYPES = {
     "mavlm_stream_compress_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int]),
     "mavlm_stream_compress_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_size_t, c_int, c_void_p]),
+    "mavlm_stream_compress_batched_workspace_bytes": (c_size_t, [c_int, c_int64, c_int, c_int, c_int]),
+    "mavlm_stream_compress_batched_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_int64, c_void_p,
+                                                  c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "mavlm_frame_mean_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mavlm_adjacent_cosine_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
     "mavlm_adjacent_cosine_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p, c_void_p, c_size_t, c_int,

@@ -282,11 +282,30 @@ __device__ void lm_decide(LmSmall* m, float* S, int (*jobs)[2], const float* dot
   lm_plan_new(m, jobs, step + 1);
 }
 
+// Videos of a batch are independent chains: grid.z = video, each with its own state / partial sums / scratch rows
+// (one workspace block per video), coins and decision log.  A video shorter than the longest one simply has no
+// new-frame jobs left (n_new = 0) and its CTAs fall through.
+struct LmBatch {
+  const void* x_single;        // batch == 1: the video itself
+  const void* const* xs;       // batch > 1: DEVICE array of per-video base pointers
+  char* ws;                    // workspace, `per_video` bytes per video
+  size_t per_video, partial_off, scratch_off;
+  const uint8_t* coins;        // [batch, coin_stride] or NULL
+  int* decisions;              // [batch, coin_stride, 2]
+  long long coin_stride;
+};
+
 template <typename T>
-__global__ void __launch_bounds__(LM_THREADS) lm_stream_kernel(const T* __restrict__ x, T* scratch, LmState* s,
-                                                               float* partial, const uint8_t* __restrict__ coins,
-                                                               int* decisions, long long L, int phase, int step) {
+__global__ void __launch_bounds__(LM_THREADS) lm_stream_kernel(LmBatch b, long long L, int phase, int step) {
   constexpr int V = Vec<T>::N;
+  const int vid = blockIdx.z;
+  const T* __restrict__ x = static_cast<const T*>(b.xs != nullptr ? b.xs[vid] : b.x_single);
+  char* wsv = b.ws + static_cast<size_t>(vid) * b.per_video;
+  LmState* s = reinterpret_cast<LmState*>(wsv);
+  float* partial = reinterpret_cast<float*>(wsv + b.partial_off);
+  T* scratch = reinterpret_cast<T*>(wsv + b.scratch_off);
+  const uint8_t* coins = b.coins != nullptr ? b.coins + vid * b.coin_stride : nullptr;
+  int* decisions = b.decisions + vid * b.coin_stride * 2;
   extern __shared__ __align__(16) unsigned char lm_smem[];
   // the deciding CTA's workspace: dots [jobs][3] | state copy | argmax scratch | (k modes) similarity matrix
   float* s_dots = reinterpret_cast<float*>(lm_smem);
@@ -302,7 +321,7 @@ __global__ void __launch_bounds__(LM_THREADS) lm_stream_kernel(const T* __restri
   const int ha = s->jobs[job][0], hb = s->jobs[job][1];
   const int avg_dst = s->sm.avg_dst, avg_a = s->sm.avg_a, avg_b = s->sm.avg_b;
   // issued early so that the deciding CTA does not pay a dependent round trip for it
-  const int coin = (coins != nullptr && phase == LM_PHASE_FRAME && threadIdx.x == 0) ? coins[step - keep_] : 0;
+  const int coin = (coins != nullptr && phase == LM_PHASE_FRAME && threadIdx.x == 0 && step < n_in) ? coins[step - keep_] : 0;
   if (job < n_jobs) {
     const bool a_avg = avg_dst >= 0 && ha == avg_dst, b_avg = avg_dst >= 0 && hb == avg_dst;
     const T* pa = lm_row(x, scratch, n_in, L, ha);
@@ -446,11 +465,17 @@ __global__ void lm_init_kernel(LmState* s, int mode, int keep, int n_in) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(LM_THREADS) lm_finish_kernel(const T* __restrict__ x, const T* __restrict__ scratch,
-                                                               const LmState* s, T* __restrict__ out,
-                                                               float* __restrict__ out_sim, long long L) {
+__global__ void __launch_bounds__(LM_THREADS) lm_finish_kernel(LmBatch b, T* __restrict__ out_all,
+                                                               float* __restrict__ out_sim_all, int n_sim, long long L) {
   constexpr int V = Vec<T>::N;
+  const int vid = blockIdx.z;
+  const T* __restrict__ x = static_cast<const T*>(b.xs != nullptr ? b.xs[vid] : b.x_single);
+  const char* wsv = b.ws + static_cast<size_t>(vid) * b.per_video;
+  const LmState* s = reinterpret_cast<const LmState*>(wsv);
+  const T* scratch = reinterpret_cast<const T*>(wsv + b.scratch_off);
   const LmSmall* m = &s->sm;
+  T* out = out_all + static_cast<long long>(vid) * m->keep * L;
+  float* out_sim = out_sim_all != nullptr ? out_sim_all + static_cast<long long>(vid) * n_sim : nullptr;
   const int j = blockIdx.y, keep = m->keep;
   const bool adjacent = m->mode == LM_DROP || m->mode == LM_MERGE;
   const int h = adjacent ? m->order[j] : m->handle[m->lorder[j]];
@@ -504,14 +529,14 @@ struct LmLayout {
   size_t state, partial, scratch, total;
   int splits, max_jobs;
 };
-static LmLayout lm_layout(int64_t row_elems, int keep, int mode, int dtype) {
+static LmLayout lm_layout(int64_t row_elems, int keep, int mode, int dtype, int batch = 1) {
   LmLayout l;
   const int vec = dtype == MAVLM_F32 ? 4 : 8;
   const size_t esz = dtype == MAVLM_F32 ? 4 : 2;
   const int init_jobs = (mode == LM_DROP || mode == LM_MERGE) ? keep - 1 : keep * (keep - 1) / 2;
   const int step_jobs = mode == LM_DROP ? 2 : mode == LM_MERGE ? 4 : mode == LM_KDROP ? keep : 2 * keep + 1;
   l.max_jobs = std::max(std::max(init_jobs, step_jobs), 1);
-  l.splits = lm_stream_splits(row_elems / vec, step_jobs);
+  l.splits = lm_stream_splits(row_elems / vec, step_jobs * std::max(batch, 1));
   l.state = 0;
   l.partial = lm_align(sizeof(LmState));
   l.scratch = l.partial + lm_align(static_cast<size_t>(l.max_jobs) * l.splits * 3 * sizeof(float));
@@ -521,16 +546,20 @@ static LmLayout lm_layout(int64_t row_elems, int keep, int mode, int dtype) {
 }
 
 template <typename T>
-static int lm_stream_launch(const void* x, int64_t n_frames, int64_t L, int keep, int mode, const uint8_t* coins,
-                            void* out, float* out_sim, int32_t* decisions, void* ws, const LmLayout& lay,
-                            cudaStream_t st) {
-  char* base = static_cast<char*>(ws);
-  LmState* s = reinterpret_cast<LmState*>(base + lay.state);
-  float* partial = reinterpret_cast<float*>(base + lay.partial);
-  T* scratch = reinterpret_cast<T*>(base + lay.scratch);
-  const T* xin = static_cast<const T*>(x);
-  lm_init_kernel<<<1, 32, 0, st>>>(s, mode, keep, static_cast<int>(n_frames));
-  MAVLM_LAUNCH_OK();
+static int lm_stream_launch(const void* x_single, const void* const* xs, const int64_t* n_frames, int batch, int64_t L,
+                            int keep, int mode, const uint8_t* coins, int64_t coin_stride, void* out, float* out_sim,
+                            int32_t* decisions, void* ws, const LmLayout& lay, cudaStream_t st) {
+  LmBatch b;
+  b.x_single = x_single; b.xs = xs; b.ws = static_cast<char*>(ws);
+  b.per_video = lay.total; b.partial_off = lay.partial; b.scratch_off = lay.scratch;
+  b.coins = coins; b.decisions = decisions; b.coin_stride = coin_stride;
+  int64_t longest = 0;
+  for (int v = 0; v < batch; ++v) {
+    lm_init_kernel<<<1, 32, 0, st>>>(reinterpret_cast<LmState*>(b.ws + static_cast<size_t>(v) * lay.total), mode, keep,
+                                     static_cast<int>(n_frames[v]));
+    MAVLM_LAUNCH_OK();
+    longest = std::max(longest, n_frames[v]);
+  }
   static bool configured[64][3] = {};     // the attribute is per device and per instantiation
   const int ti = sizeof(T) == 4 ? 0 : (std::is_same<T, __nv_bfloat16>::value ? 1 : 2);
   int dev_id = 0;
@@ -544,23 +573,24 @@ static int lm_stream_launch(const void* x, int64_t n_frames, int64_t L, int keep
   const int step_jobs = mode == LM_DROP ? 2 : mode == LM_MERGE ? 4 : mode == LM_KDROP ? keep : 2 * keep + 1;
   auto launch = [&](int jobs_y, int phase, int step) -> int {
     LaunchCfg lc;
-    make_launch(lc, dim3(lay.splits, jobs_y), dim3(LM_THREADS), LM_STREAM_SMEM, st, 1, 8);
-    MAVLM_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, lm_stream_kernel<T>, xin, scratch, s, partial, coins, decisions,
-                                     static_cast<long long>(L), phase, step));
+    make_launch(lc, dim3(lay.splits, jobs_y, batch), dim3(LM_THREADS), LM_STREAM_SMEM, st, 1, 8);
+    MAVLM_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, lm_stream_kernel<T>, b, static_cast<long long>(L), phase, step));
     MAVLM_LAUNCH_OK();
     return MAVLM_OK;
   };
   int rc = launch(std::max(init_jobs, 1), LM_PHASE_INIT, 0);
   if (rc != MAVLM_OK) return rc;
-  for (int64_t i = keep; i < n_frames; ++i) {
+  for (int64_t i = keep; i < longest; ++i) {
     rc = launch(step_jobs, LM_PHASE_FRAME, static_cast<int>(i));
     if (rc != MAVLM_OK) return rc;
   }
-  rc = launch(step_jobs, LM_PHASE_FLUSH, static_cast<int>(n_frames));
+  rc = launch(step_jobs, LM_PHASE_FLUSH, static_cast<int>(longest));
   if (rc != MAVLM_OK) return rc;
   const long long nvec = L / Vec<T>::N;
-  const int gx = static_cast<int>(std::min<long long>((nvec + LM_THREADS - 1) / LM_THREADS, 2LL * sm_count()));
-  lm_finish_kernel<T><<<dim3(std::max(gx, 1), keep), LM_THREADS, 0, st>>>(xin, scratch, s, static_cast<T*>(out), out_sim, L);
+  const int gx = static_cast<int>(std::min<long long>((nvec + LM_THREADS - 1) / LM_THREADS,
+                                                      std::max(1LL, 2LL * sm_count() / (keep * batch))));
+  const int n_sim = (mode == LM_DROP || mode == LM_MERGE) ? std::max(keep - 1, 1) : keep * keep;
+  lm_finish_kernel<T><<<dim3(std::max(gx, 1), keep, batch), LM_THREADS, 0, st>>>(b, static_cast<T*>(out), out_sim, n_sim, L);
   MAVLM_LAUNCH_OK();
   return MAVLM_OK;
 }
@@ -899,30 +929,68 @@ size_t mavlm_stream_compress_workspace_bytes(int64_t row_elems, int keep, int mo
   return lm_layout(row_elems, keep, mode, dtype).total;
 }
 
+size_t mavlm_stream_compress_batched_workspace_bytes(int batch, int64_t row_elems, int keep, int mode, int dtype) {
+  if (batch < 1 || row_elems <= 0 || keep < 1 || keep > LM_CAP || mode < 0 || mode > 3 || !dtype_ok(dtype)) return 0;
+  return lm_layout(row_elems, keep, mode, dtype, batch).total * static_cast<size_t>(batch);
+}
+
+static int lm_check_common(const char* what, int64_t row_elems, int keep, int mode, int dtype, const void* out,
+                           const void* decisions, const void* workspace, const uint8_t* coins) {
+  MAVLM_REQUIRE(dtype_ok(dtype), MAVLM_E_INVALID, "%s: bad dtype %d", what, dtype);
+  MAVLM_REQUIRE(mode >= 0 && mode <= 3, MAVLM_E_INVALID, "%s: mode %d (0 drop, 1 merge, 2 k_drop, 3 k_merge)", what, mode);
+  MAVLM_REQUIRE(keep >= 1 && keep <= LM_CAP, MAVLM_E_INVALID, "%s: keep %d must be in [1, %d]", what, keep, LM_CAP);
+  const int vec = dtype == MAVLM_F32 ? 4 : 8;
+  MAVLM_REQUIRE(row_elems > 0 && row_elems % vec == 0, MAVLM_E_INVALID, "%s: P*D = %lld must be a positive multiple of %d",
+                what, static_cast<long long>(row_elems), vec);
+  MAVLM_REQUIRE(out != nullptr && decisions != nullptr, MAVLM_E_INVALID, "%s: NULL buffer", what);
+  MAVLM_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+                MAVLM_E_INVALID, "%s: out must be 16-byte, workspace 256-byte aligned", what);
+  MAVLM_REQUIRE((mode != LM_DROP && mode != LM_KDROP) || coins != nullptr, MAVLM_E_INVALID,
+                "%s: drop / k_drop need one coin per streamed frame", what);
+  return MAVLM_OK;
+}
+
 int mavlm_stream_compress_fwd(const void* x, int64_t n_frames, int64_t row_elems, int keep, int mode,
                               const uint8_t* coins, void* out, float* out_sim, int32_t* decisions, void* workspace,
                               size_t workspace_bytes, int dtype, void* stream) {
-  MAVLM_REQUIRE(dtype_ok(dtype), MAVLM_E_INVALID, "stream_compress: bad dtype %d", dtype);
-  MAVLM_REQUIRE(mode >= 0 && mode <= 3, MAVLM_E_INVALID, "stream_compress: mode %d (0 drop, 1 merge, 2 k_drop, 3 k_merge)", mode);
-  MAVLM_REQUIRE(keep >= 1 && keep <= LM_CAP, MAVLM_E_INVALID, "stream_compress: keep %d must be in [1, %d]", keep, LM_CAP);
-  const int vec = dtype == MAVLM_F32 ? 4 : 8;
-  MAVLM_REQUIRE(row_elems > 0 && row_elems % vec == 0, MAVLM_E_INVALID,
-                "stream_compress: P*D = %lld must be a positive multiple of %d", static_cast<long long>(row_elems), vec);
+  const int rc = lm_check_common("stream_compress", row_elems, keep, mode, dtype, out, decisions, workspace, coins);
+  if (rc != MAVLM_OK) return rc;
   MAVLM_REQUIRE(n_frames > keep && n_frames < (1 << 30), MAVLM_E_INVALID,
                 "stream_compress: needs more frames (%lld) than kept (%d); shorter videos pass through on the host",
                 static_cast<long long>(n_frames), keep);
-  MAVLM_REQUIRE(x != nullptr && out != nullptr && decisions != nullptr, MAVLM_E_INVALID, "stream_compress: NULL buffer");
-  MAVLM_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
-                    (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
-                MAVLM_E_INVALID, "stream_compress: x / out must be 16-byte, workspace 256-byte aligned");
-  MAVLM_REQUIRE((mode != LM_DROP && mode != LM_KDROP) || coins != nullptr, MAVLM_E_INVALID,
-                "stream_compress: drop / k_drop need one coin per streamed frame");
+  MAVLM_REQUIRE(x != nullptr && (reinterpret_cast<uintptr_t>(x) & 15) == 0, MAVLM_E_INVALID,
+                "stream_compress: x must be a 16-byte aligned device pointer");
   const LmLayout lay = lm_layout(row_elems, keep, mode, dtype);
   MAVLM_REQUIRE(workspace != nullptr && workspace_bytes >= lay.total, MAVLM_E_WORKSPACE,
                 "stream_compress: workspace %zu < %zu bytes", workspace_bytes, lay.total);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  MAVLM_DISPATCH_DTYPE(dtype, return lm_stream_launch<T>(x, n_frames, row_elems, keep, mode, coins, out, out_sim, decisions,
-                                                         workspace, lay, st));
+  MAVLM_DISPATCH_DTYPE(dtype, return lm_stream_launch<T>(x, nullptr, &n_frames, 1, row_elems, keep, mode, coins,
+                                                         n_frames - keep, out, out_sim, decisions, workspace, lay, st));
+}
+
+int mavlm_stream_compress_batched_fwd(const void* const* x_ptrs, const int64_t* n_frames, int batch, int64_t row_elems,
+                                      int keep, int mode, const uint8_t* coins, int64_t coin_stride, void* out,
+                                      float* out_sim, int32_t* decisions, void* workspace, size_t workspace_bytes,
+                                      int dtype, void* stream) {
+  const int rc = lm_check_common("stream_compress_batched", row_elems, keep, mode, dtype, out, decisions, workspace, coins);
+  if (rc != MAVLM_OK) return rc;
+  MAVLM_REQUIRE(batch >= 1 && batch <= 65535 && x_ptrs != nullptr && n_frames != nullptr, MAVLM_E_INVALID,
+                "stream_compress_batched: batch %d / NULL pointer table", batch);
+  int64_t longest = 0;
+  for (int v = 0; v < batch; ++v) {
+    MAVLM_REQUIRE(n_frames[v] > keep && n_frames[v] < (1 << 30), MAVLM_E_INVALID,
+                  "stream_compress_batched: video %d has %lld frames, needs more than keep = %d", v,
+                  static_cast<long long>(n_frames[v]), keep);
+    longest = std::max(longest, n_frames[v]);
+  }
+  MAVLM_REQUIRE(coin_stride >= longest - keep, MAVLM_E_INVALID, "stream_compress_batched: coin / decision stride %lld < %lld",
+                static_cast<long long>(coin_stride), static_cast<long long>(longest - keep));
+  const LmLayout lay = lm_layout(row_elems, keep, mode, dtype, batch);
+  MAVLM_REQUIRE(workspace != nullptr && workspace_bytes >= lay.total * static_cast<size_t>(batch), MAVLM_E_WORKSPACE,
+                "stream_compress_batched: workspace %zu < %zu bytes", workspace_bytes, lay.total * static_cast<size_t>(batch));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MAVLM_DISPATCH_DTYPE(dtype, return lm_stream_launch<T>(nullptr, x_ptrs, n_frames, batch, row_elems, keep, mode, coins,
+                                                         coin_stride, out, out_sim, decisions, workspace, lay, st));
 }
 
 int mavlm_frame_mean_fwd(const void* x, void* out, int frames, int tokens, int dim, int dtype, void* stream) {

@@ -266,6 +266,49 @@ def stream_compress(img_feature: torch.Tensor, video_max_frames: int, mode: int,
     return out, sim, steps
 
 
+def stream_compress_batched(videos, video_max_frames: int, mode: int, coins=None, return_steps: bool = True):
+    """Several independent videos ([T_i, P, D], same P, D, dtype; every T_i > video_max_frames) compressed together:
+    one launch per frame index with grid.z = video, so the per-frame latency chain is shared by the batch.
+    `coins`: one list per video (drop / k_drop).  Returns a list of (features, similarities, step_indices) with the frames and
+    decisions of per-video `stream_compress` calls."""
+    T0 = int(video_max_frames)
+    xs = [_rows(v) for v in videos]
+    B = len(xs)
+    L = xs[0].shape[1]
+    dev, dt = xs[0].device, xs[0].dtype
+    if any(x.shape[1] != L or x.dtype != dt or x.device != dev for x in xs):
+        raise RuntimeError("mavlm: batched streaming compression needs videos of one token shape, dtype and device")
+    lens = [int(x.shape[0]) for x in xs]
+    stride = max(lens) - T0
+    lib = _lib.load()
+    code = ops.dtype_code(xs[0])
+    tail = tuple(videos[0].shape[1:])
+    out = torch.empty((B, T0) + tail, dtype=dt, device=dev)
+    n_sim = max(T0 - 1, 1) if mode in (DROP, MERGE) else T0 * T0
+    sim = torch.empty((B, n_sim), dtype=torch.float32, device=dev)
+    dec = torch.empty((B, max(stride, 1), 2), dtype=torch.int32, device=dev)
+    coin_t = None
+    if mode in (DROP, K_DROP):
+        host = torch.zeros((B, max(stride, 1)), dtype=torch.uint8)
+        for i, c in enumerate(coins):
+            host[i, :lens[i] - T0] = torch.tensor(list(c)[:lens[i] - T0], dtype=torch.uint8)
+        coin_t = host.to(dev)
+    ptrs = torch.tensor([x.data_ptr() for x in xs], dtype=torch.int64).to(dev)
+    import ctypes
+    n_host = (ctypes.c_int64 * B)(*lens)
+    ws = _ws(lib.mavlm_stream_compress_batched_workspace_bytes(B, L, T0, mode, code), dev)
+    _lib.check(lib.mavlm_stream_compress_batched_fwd(ptrs.data_ptr(), ctypes.cast(n_host, ctypes.c_void_p), B, L, T0, mode,
+                                                     ops._ptr(coin_t), max(stride, 1), out.data_ptr(), sim.data_ptr(),
+                                                     dec.data_ptr(), ws.data_ptr(), ws.numel(), code, ops._stream()),
+               "stream_compress_batched")
+    dec_h = dec.cpu().tolist() if return_steps else None
+    res = []
+    for i in range(B):
+        steps = _replay_steps(mode, lens[i], T0, dec_h[i], coins[i] if coins is not None else None) if return_steps else None
+        res.append((out[i], sim[i], steps))
+    return res
+
+
 def _short(img_feature, extra):
     return img_feature, extra, [[[i] for i in range(img_feature.shape[0])]]
 

@@ -153,6 +153,25 @@ def test_streaming_compression_at_tower_size(L, mode, dtype):
         assert err(got[1], want[1]) <= (1e-5 if dtype == torch.float32 else 1e-2)
 
 
+@pytest.mark.parametrize("mode", ["drop", "merge", "kdrop", "kmerge"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_batched_streaming_equals_per_video_calls(L, mode, dtype):
+    """Ragged batch (different lengths) in one launch sequence: same decisions and frames as one call per video."""
+    m = {"drop": L.DROP, "merge": L.MERGE, "kdrop": L.K_DROP, "kmerge": L.K_MERGE}[mode]
+    lens, T0 = (23, 9, 40, 6), 4
+    vids = [cu(scene_frames(40 + i, t, 196, 512, scenes=4), dtype) for i, t in enumerate(lens)]
+    cs = [coins(90 + i, t - T0) for i, t in enumerate(lens)]
+    batched = L.stream_compress_batched(vids, T0, m, cs)
+    for v, c, (bf, bs, bst) in zip(vids, cs, batched):
+        f, s, st = L.stream_compress(v, T0, m, c)
+        assert torch.equal(bf, f) and st == bst
+        if m != L.K_DROP:
+            n = T0 - 1 if m in (L.DROP, L.MERGE) else T0 * T0
+            assert err(bs[:n], s[:n].cpu().numpy()) <= 1e-6            # partial-sum count per row pair depends on the batch
+    with pytest.raises(RuntimeError):
+        L.stream_compress_batched([vids[0], vids[1][:, :, :256].contiguous()], T0, m, cs[:2])
+
+
 @pytest.mark.parametrize("T0", [3, 5])
 def test_kmeans_matches_the_reference(L, T0):
     x = cu(INP["stream"])
