@@ -450,7 +450,6 @@ def run_legacy(args):
     from oracle import legacy_memory_oracle as O
     frames, keep = 512, 3
     if args.impl == "reference":
-        import random
         import numpy as np
         use_all_host_cores()
         steps = args.steps if args.steps is not None else 3

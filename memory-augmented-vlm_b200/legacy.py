@@ -101,16 +101,12 @@ def _pick_boundaries(depth: torch.Tensor, alpha: float, k: Optional[int], cap: O
     return b.tolist()
 
 
-def _sim_in_dtype(features: torch.Tensor, eps: float) -> torch.Tensor:
-    return adjacent_cosine(features, eps)
-
-
 def segment(features: torch.Tensor, alpha: float = 0.5, k: Optional[int] = None):
     """segment.py:27-49: features [T, D] -> (boundaries, depth_scores)."""
     T = features.shape[0]
     if T == 1:
         return [0], torch.zeros(1)
-    sim = _sim_in_dtype(features, 1e-2)
+    sim = adjacent_cosine(features, 1e-2)
     if sim.numel() < 2:
         raise IndexError("index 1 is out of bounds for dimension 0 with size 1")        # segment.py:31 on 2 frames
     sim[0:1].copy_(sim[1:2])
@@ -128,7 +124,7 @@ def adjusted_segment(features: torch.Tensor, alpha: float = 0.5, k: Optional[int
     T = features.shape[0]
     if T == 1:
         return [0]
-    depth = _depth(_sim_in_dtype(features, 1e-8), False)
+    depth = _depth(adjacent_cosine(features, 1e-8), False)
     b = _pick_boundaries(depth, alpha, k, cap=15)
     if not b or b[-1] != T:
         b.append(T)
@@ -171,7 +167,7 @@ def uniform_segment(features, d: int = 32) -> List[int]:
 
 def segment_left(features: torch.Tensor, alpha: float = 0.5, k: Optional[int] = None) -> List[int]:
     """segment.py:226-250."""
-    depth = _depth(_sim_in_dtype(features, 1e-8), True)
+    depth = _depth(adjacent_cosine(features, 1e-8), True)
     b = _pick_boundaries(depth, alpha, k)
     if b == []:
         b.append(features.shape[0] - 1)

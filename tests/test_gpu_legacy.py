@@ -222,11 +222,9 @@ def test_turing_memory_matches_the_reference(L):
     with torch.no_grad():
         assert err(ntm.get_weight(a, b), G["ntm.weight"]) <= 1e-5
         assert err(ntm(a, b), G["ntm.forward"]) <= 1e-5
-        holder = types.SimpleNamespace(attention_model=ntm)
         fn = lambda m, n, update_ratio: ntm.gated_update(m, n, update_ratio)   # noqa: E731
         assert err(L.attention_feature(fr, 3, fn, update_ratio=0.2)[0], G["ntm.attention_feature"]) <= 1e-5
         assert err(L.attention_feature(fr, 2, fn, update_ratio=0.5)[0], G["ntm.attention_feature_r05"]) <= 1e-5
-        assert holder is not None
         ntm.train()
         with pytest.raises(NotImplementedError):
             ntm(a, b)
