@@ -376,15 +376,26 @@ class MemoryFuser(nn.Module):
         if self.training and self.dropout > 0:
             raise NotImplementedError("MemoryFuser: train-mode dropout is not implemented on the B200 path; "
                                       "call .eval()")
-        x = ops.linear(memory_tokens, self.input_proj.weight, self.input_proj.bias)
-        b, s_len, d = x.shape
+        b, s_len, d = memory_tokens.shape
         h = self.num_heads
         dh = d // h
-        dt = x.dtype
+        dt = memory_tokens.dtype
         tc = dt in (torch.bfloat16, torch.float16) and dh in (128, 448)   # head dims the fused tensor-core kernel handles
+        # other head dims in bf16 (7B: dh = 896, 0.5B: 224): attention as batched tcgen05 GEMMs around a row softmax,
+        # on sequences padded to a multiple of 8 tokens (the GEMM's K alignment); the pad keys get zero probability
+        gemm_attn = dt == torch.bfloat16 and not tc and dh % 8 == 0 and d % 8 == 0
+        s_pad = (s_len + 7) // 8 * 8 if gemm_attn else s_len
+        if s_pad != s_len:
+            padded = memory_tokens.new_zeros((b, s_pad, d))
+            padded[:, :s_len].copy_(memory_tokens)
+            memory_tokens = padded
+        x = ops.linear(memory_tokens, self.input_proj.weight, self.input_proj.bias)
         for layer in self.transformer_encoder.layers:
             sa = layer.self_attn
-            if tc or dt == torch.float32:
+            if gemm_attn:
+                qkv = ops.linear(x, sa.in_proj_weight, sa.in_proj_bias)
+                ctx = self._gemm_attention(qkv, b, s_pad, s_len, h, dh)
+            elif tc or dt == torch.float32:
                 qkv = ops.linear(x, sa.in_proj_weight, sa.in_proj_bias)
                 ctx, _, _ = ops.xattn(qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:], h)
             else:                                                # e.g. 7B: dh = 896 -> fp32-tier attention on fp32 q/k/v
@@ -396,7 +407,37 @@ class MemoryFuser(nn.Module):
             f = ops.linear(x, layer.linear1.weight, layer.linear1.bias, act=ACT_GELU_ERF)
             pre = ops.linear(f, layer.linear2.weight, layer.linear2.bias, resid=x, out_dtype=torch.float32)
             x = ops.layernorm(pre, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps, out_dtype=dt)
-        return ops.linear(x, self.output_proj.weight, self.output_proj.bias)
+        y = ops.linear(x, self.output_proj.weight, self.output_proj.bias)
+        return y[:, :s_len] if s_pad != s_len else y
+
+    @staticmethod
+    def _gemm_attention(qkv: torch.Tensor, b: int, s_pad: int, s_len: int, h: int, dh: int) -> torch.Tensor:
+        """softmax(q k^T / sqrt(dh)) v per (row, head) of qkv [b, s_pad, 3 h dh] (bf16): two batched GEMMs (fp32 scores)
+        and one row-softmax kernel that masks the pad keys."""
+        from . import _lib
+        from .autograd import _DT, _p, _s
+        d = h * dh
+        lib = _lib.load()
+        dev = qkv.device
+        scores = torch.empty((b * h * s_pad, s_pad), dtype=torch.float32, device=dev)
+        ctx = torch.empty((b, s_pad, d), dtype=qkv.dtype, device=dev)
+        import ctypes
+        ld = 3 * d
+
+        def strides(*v):
+            return (ctypes.c_int64 * 6)(*v)
+
+        q, k, v = qkv, qkv[..., d:], qkv[..., 2 * d:]
+        # scores[b, h] = q[b, :, h] k[b, :, h]^T      (outer = rows of the batch, inner = heads)
+        _lib.check(lib.mavlm_gemm_ex(_p(q), ld, 0, k.data_ptr(), ld, 1, _p(scores), s_pad, s_pad, s_pad, dh, 1.0, 0, b, h,
+                                     strides(s_pad * ld, dh, s_pad * ld, dh, h * s_pad * s_pad, s_pad * s_pad),
+                                     _DT[qkv.dtype], _DT[torch.float32], _s()), "gemm_ex")
+        probs = ops.softmax_rows(scores, s_len, 1.0 / math.sqrt(dh), qkv.dtype)
+        # ctx[b, :, h] = probs[b, h] v[b, :, h]
+        _lib.check(lib.mavlm_gemm_ex(_p(probs), s_pad, 0, v.data_ptr(), ld, 0, _p(ctx), d, s_pad, dh, s_pad, 1.0, 0, b, h,
+                                     strides(h * s_pad * s_pad, s_pad * s_pad, s_pad * ld, dh, s_pad * d, dh),
+                                     _DT[qkv.dtype], _DT[qkv.dtype], _s()), "gemm_ex")
+        return ctx
 
 
 def build_vision_projector(config, delay_load=False, **kwargs):

@@ -303,3 +303,17 @@ def assemble(seq: torch.Tensor, mem: Optional[torch.Tensor], n_mem_rows: int, fr
                                         prompt_frm_ids.numel(), d, int(drop_frames), dtype_code(seq), _stream())
     _lib.check(st, "assemble_fwd")
     return seq
+
+
+def softmax_rows(scores: torch.Tensor, n: int, scale: float, dtype: torch.dtype, ratio: float = 1.0) -> torch.Tensor:
+    """w[r, :n] = ratio * softmax(scale * scores[r, :n]) in `dtype`, columns [n, ld) zero-filled so that w can be the
+    A operand of a tensor-core GEMM whose K is padded to a multiple of 8.  scores: fp32 [R, ld] (mavlm_ntm_softmax_fwd)."""
+    _need_cuda(scores)
+    if scores.dtype != torch.float32 or scores.dim() != 2 or scores.stride(1) != 1:
+        raise RuntimeError("mavlm.softmax_rows: scores must be fp32 [rows, ld] with unit inner stride")
+    rows, ld = scores.shape
+    w = torch.empty((rows, ld), dtype=dtype, device=scores.device)
+    st = _lib.load().mavlm_ntm_softmax_fwd(scores.data_ptr(), scores.stride(0), rows, int(n), float(scale), float(ratio),
+                                           w.data_ptr(), ld, ld, None, None, 0, _DTYPES[dtype], _stream())
+    _lib.check(st, "softmax_rows")
+    return w
