@@ -50,6 +50,26 @@ def algorithmic_gflop(frames: int, chunk: int, d: int = HIDDEN, dv: int = VISION
     return fl / 1e9
 
 
+_REAL_STDOUT = None
+
+
+def isolate_stdout():
+    """stdout carries exactly ONE JSON line (the driver parses it).  Libraries write there too -- NCCL prints its
+    "NCCL version ..." banner to fd 1 at communicator creation -- so point fd 1 at stderr for the run and keep the
+    real stdout for the result line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit_line(text, flush=True):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(text + "\n")
+    out.flush()
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -192,7 +212,7 @@ def run_reference(args):
             "config": workload_config(int(os.environ.get("WORLD_SIZE", "1"))), "gpu_launches": 0,
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit_line(json.dumps(line), flush=True)
 
 
 def workload_config(world):
@@ -282,7 +302,7 @@ def run_ours(args):
 
     if args.timed_only:
         if rank == 0:
-            print(json.dumps({"metric": METRIC, "value": world * FRAMES * steps / (ms_total * 1e-3), "unit": "frames/s",
+            emit_line(json.dumps({"metric": METRIC, "value": world * FRAMES * steps / (ms_total * 1e-3), "unit": "frames/s",
                               "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_total / steps,
                               "note": "--timed-only (profiling run)"}), flush=True)
         if world > 1:
@@ -434,7 +454,7 @@ def run_ours(args):
             "algorithmic_gflop_per_step": gflop_step,
             "path_tflops": gflop_step * 1e9 / (ms_total / steps * 1e-3) / 1e12,
             "path_frac_of_peak": gflop_step * 1e9 / (ms_total / steps * 1e-3) / 1e12 / peaks["tflops"]}
-    print(json.dumps(line), flush=True)
+    emit_line(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -465,7 +485,7 @@ def run_legacy(args):
         fps = sample_frames * steps / dt
         cb = {"value": fps, "unit": "frames/s", "cores": blas_threads(), "kind": "port",
               "sample": f"merge_feature on the first {sample_frames} frames per step (numpy oracle)"}
-        print(json.dumps({"impl": "reference", "metric": "legacy_merge_feature_frames_per_s", "value": fps, "unit": "frames/s",
+        emit_line(json.dumps({"impl": "reference", "metric": "legacy_merge_feature_frames_per_s", "value": fps, "unit": "frames/s",
                           "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * dt / steps,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                           "config": {"workload": f"legacy merge_feature, {frames} frames x 729 x 1152, keep {keep}"},
@@ -498,7 +518,7 @@ def run_legacy(args):
         c = res["cpu_oracle"]
         line["cpu_baseline"] = {"value": c["ops"]["stream_merge"]["frames_per_s"], "unit": "frames/s", "cores": c["cores"],
                                 "kind": "port", "sample": "merge_feature, " + c["sample"], "ops": c["ops"]}
-    print(json.dumps(line), flush=True)
+    emit_line(json.dumps(line), flush=True)
 
 
 def main():
@@ -514,6 +534,7 @@ def main():
                     help="only the device-timed graph replays (no e2e / breakdown / CPU passes): the short run that is "
                          "put under `ncu` for the per-launch list in profiles/")
     args = ap.parse_args()
+    isolate_stdout()
     if args.workload == "legacy":
         run_legacy(args)
     elif args.impl == "reference":
