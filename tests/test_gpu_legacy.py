@@ -154,6 +154,43 @@ def test_streaming_compression_at_tower_size(L, mode, dtype):
 
 
 @pytest.mark.parametrize("mode", ["drop", "merge", "kdrop", "kmerge"])
+@pytest.mark.parametrize("T,T0", [(9, 1), (12, 2), (6, 5), (90, 64), (70, 33)])
+def test_streaming_compression_edge_sizes(L, mode, T, T0):
+    """keep = 1 (no similarities at all), keep = 2, one streamed frame only, the cap of 64 kept frames (2016 initial
+    pairs, 129 row pairs per launch in k_merge) and an odd keep, against the oracle on the same fp32 frames."""
+    x = scene_frames(50 + T0, T, 4, 16, scenes=min(6, T))
+    c = coins(60 + T0, T - T0)
+    xt = cu(x)
+    if mode == "drop":
+        got, want = L.stream_compress(xt, T0, L.DROP, c), O.drop_feature(x, T0, c)
+    elif mode == "merge":
+        got, want = L.stream_compress(xt, T0, L.MERGE), O.merge_feature(x, T0)
+    elif mode == "kdrop":
+        got, want = L.stream_compress(xt, T0, L.K_DROP, c), O.k_drop_feature(x, T0, c)
+    else:
+        got, want = L.stream_compress(xt, T0, L.K_MERGE), O.k_merge_feature(x, T0)
+    assert got[2] == want[2], "streaming decisions differ"
+    assert err(got[0], want[0]) <= 1e-6
+    if mode in ("drop", "merge") and T0 > 1:
+        assert err(got[1][:T0 - 1], want[1]) <= 1e-5
+    if mode == "kmerge":
+        assert err(got[1].view(T0, T0), want[1]) <= 1e-5
+
+
+def test_streaming_compression_fp16(L):
+    x = cu(scene_frames(70, 20, 8, 64, scenes=4), torch.float16)
+    xr = x.float().cpu().numpy()
+    f, s, st = L.merge_feature(x, 3)
+    wf, ws, wst = O.merge_feature(xr, 3)
+    assert st == wst and err(f, wf) <= 2e-3 and err(s, ws) <= 2e-3
+    c = coins(71, 17)
+    random.seed(71)
+    f, _, st = L.k_drop_feature(x, 3)
+    wf, _, wst = O.k_drop_feature(xr, 3, c)
+    assert st == wst and np.array_equal(f.float().cpu().numpy(), wf)
+
+
+@pytest.mark.parametrize("mode", ["drop", "merge", "kdrop", "kmerge"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_batched_streaming_equals_per_video_calls(L, mode, dtype):
     """Ragged batch (different lengths) in one launch sequence: same decisions and frames as one call per video."""
