@@ -244,6 +244,9 @@ def stream_compress(img_feature: torch.Tensor, video_max_frames: int, mode: int,
     T, T0 = img_feature.shape[0], int(video_max_frames)
     x = _rows(img_feature)
     L = x.shape[1]
+    if T <= T0:
+        raise RuntimeError(f"mavlm: streaming compression needs more frames ({T}) than it keeps ({T0}); the "
+                           "reference returns shorter videos unchanged (see drop_feature & co.)")
     lib = _lib.load()
     code = ops.dtype_code(x)
     dev = x.device
@@ -253,7 +256,10 @@ def stream_compress(img_feature: torch.Tensor, video_max_frames: int, mode: int,
     dec = torch.empty((T - T0, 2), dtype=torch.int32, device=dev)
     coin_t = None
     if mode in (DROP, K_DROP):
-        coin_t = torch.tensor(list(coins), dtype=torch.uint8).to(dev)
+        if coins is None or len(coins) < T - T0:
+            raise ValueError(f"mavlm: drop / k_drop need one coin per streamed frame ({T - T0}), got "
+                             f"{0 if coins is None else len(coins)}")
+        coin_t = torch.tensor(list(coins)[:T - T0], dtype=torch.uint8).to(dev)
     ws = _ws(lib.mavlm_stream_compress_workspace_bytes(L, T0, mode, code), dev)
     _lib.check(lib.mavlm_stream_compress_fwd(x.data_ptr(), T, L, T0, mode, ops._ptr(coin_t), out.data_ptr(), sim.data_ptr(),
                                              dec.data_ptr(), ws.data_ptr(), ws.numel(), code, ops._stream()),
@@ -285,6 +291,8 @@ def stream_compress_batched(videos, video_max_frames: int, mode: int, coins=None
     dec = torch.empty((B, max(stride, 1), 2), dtype=torch.int32, device=dev)
     coin_t = None
     if mode in (DROP, K_DROP):
+        if coins is None or len(coins) != B or any(len(c) < lens[i] - T0 for i, c in enumerate(coins)):
+            raise ValueError("mavlm: drop / k_drop need one coin list per video with one coin per streamed frame")
         host = torch.zeros((B, max(stride, 1)), dtype=torch.uint8)
         for i, c in enumerate(coins):
             host[i, :lens[i] - T0] = torch.tensor(list(c)[:lens[i] - T0], dtype=torch.uint8)

@@ -124,7 +124,11 @@ def test_streaming_compression_short_video_passes_through(L):
     f, s, st = L.merge_feature(x, 5)
     assert f is x and s is None and st == META["merge_identity.steps"]
     with pytest.raises(RuntimeError):
-        L.stream_compress(cu(INP["stream"]), 65, L.MERGE)                  # keep > 64
+        L.stream_compress(cu(INP["stream"]), 65, L.MERGE)                  # keep > 64 / not enough frames
+    with pytest.raises(RuntimeError):
+        L.stream_compress(cu(scene_frames(3, 80, 2, 8)), 65, L.MERGE)      # keep > 64 with enough frames: C ABI refuses
+    with pytest.raises(ValueError):
+        L.stream_compress(cu(INP["stream"]), 3, L.DROP, [1, 0])            # too few coins
 
 
 @pytest.mark.parametrize("mode", ["drop", "merge", "kdrop", "kmerge"])
