@@ -258,7 +258,9 @@ class VisualMemoryPipeline(nn.Module):
         scale = 1.0 / math.sqrt(d // heads)
         cap = rmt.cache_size
         pm_ids, pf_ids = self._const_ids(dev)
-        fine_idx = fine_frame_indices(f, self.max_fine_frames).to(dev)
+        fine_host = fine_frame_indices(f, self.max_fine_frames)
+        fine_all = fine_host.numel() == f and bool((fine_host == torch.arange(f)).all())   # <= 32 frames: every frame is fine
+        fine_idx = fine_host.to(dev)
         emb = self.token_type_embedding.weight
         newline = self.image_newline
         fz = self.memory_fuser
@@ -305,7 +307,7 @@ class VisualMemoryPipeline(nn.Module):
         nl = newline[None, None].to(memtok.dtype).expand(b, 1, d)
         parts = [self.embed_tokens(pm_ids)[None].expand(b, -1, d), memtok, nl]
         if not drop_frames:
-            fine = z[:, fine_idx].reshape(b, -1, d)
+            fine = (z if fine_all else z[:, fine_idx]).reshape(b, -1, d)     # no gather copy when it is the identity
             fine = ops.add_rows(fine, emb[1][None].expand(b, d))                         # + token_type_embedding[1]
             parts += [self.embed_tokens(pf_ids)[None].expand(b, -1, d), fine, nl]
         n = len(states)
