@@ -243,6 +243,62 @@ class AddRowsFn(torch.autograd.Function):
         return (dy if ctx.needs_input_grad[0] else None), dt
 
 
+class AssembleFn(torch.autograd.Function):
+    """Token assembly of memory_forward_train (llava_arch.py:548-554, 620-629, 708-731) for a batch of videos with the
+    assemble kernel instead of torch.cat: prompt rows | memory tokens | newline | prompt rows | fine frames + type
+    embedding 1 | newline.  `memtok` already carries type embedding 0 (added by the fuser GEMM).  Gradients: slices
+    of d(seq) for the memory tokens, column sums for the type embedding / newline, batch sums for the prompt rows
+    (pm_emb / pf_emb are the embedding lookups; their values are re-gathered from the table by the kernel)."""
+
+    @staticmethod
+    def forward(ctx, memtok, z, fine_idx, emb_w, newline, embed_table, pm_ids, pf_ids, pm_emb, pf_emb, drop_frames):
+        ops = _raw()
+        b, n_mem, d = memtok.shape
+        p = z.shape[2]
+        nf = fine_idx.numel()
+        n_pm, n_pf = pm_ids.numel(), pf_ids.numel()
+        length = n_pm + n_mem + 1 + (0 if drop_frames else n_pf + nf * p + 1)
+        dt = memtok.dtype
+        seq = torch.empty((b, length, d), dtype=dt, device=memtok.device)
+        tab = torch.zeros((2, d), dtype=dt, device=memtok.device)
+        tab[1].copy_(emb_w[1])
+        nl = newline.detach().to(dt).contiguous()
+        table = embed_table.detach()
+        table = table if table.dtype == dt and table.is_contiguous() else table.to(dt).contiguous()
+        mt, zz = memtok.detach().contiguous(), z.detach().contiguous()
+        for i in range(b):
+            ops.assemble(seq[i], mt[i], n_mem, zz[i], fine_idx, p, tab, nl, table, pm_ids, pf_ids, drop_frames=drop_frames)
+        ctx.meta = (n_pm, n_mem, n_pf, nf * p, bool(drop_frames), emb_w.dtype, newline.dtype, pm_emb.dtype)
+        return seq
+
+    @staticmethod
+    def backward(ctx, dseq):
+        n_pm, n_mem, n_pf, n_fine, drop, emb_dt, nl_dt, pe_dt = ctx.meta
+        b, _, d = dseq.shape
+        r_nl1 = n_pm + n_mem
+        r_pf = r_nl1 + 1
+        r_fine = r_pf + n_pf
+        need = ctx.needs_input_grad
+        d_mem = dseq[:, n_pm:r_nl1] if need[0] else None
+        d_emb = d_nl = d_pm = d_pf = None
+        if need[3]:
+            d_emb = torch.zeros((2, d), dtype=torch.float32, device=dseq.device)
+            if not drop:
+                for i in range(b):
+                    d_emb[1] += colsum(dseq[i, r_fine:r_fine + n_fine])
+            d_emb = d_emb.to(emb_dt)
+        if need[4]:
+            d_nl = dseq[:, r_nl1].float().sum(0)
+            if not drop:
+                d_nl = d_nl + dseq[:, r_fine + n_fine].float().sum(0)
+            d_nl = d_nl.to(nl_dt)
+        if need[8]:
+            d_pm = dseq[:, :n_pm].float().sum(0).to(pe_dt)
+        if need[9]:
+            d_pf = (dseq[:, r_pf:r_fine].float().sum(0) if not drop else torch.zeros((n_pf, d), device=dseq.device)).to(pe_dt)
+        return d_mem, None, None, d_emb, d_nl, None, None, None, d_pm, d_pf, None
+
+
 def linear(x, w, b, act, resid, addvec, out_dtype):
     if act == ACT_GELU_ERF:                      # keep the pre-activation: GEMM, then the unfused activation
         if resid is not None or addvec is not None:

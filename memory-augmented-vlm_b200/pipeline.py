@@ -258,9 +258,7 @@ class VisualMemoryPipeline(nn.Module):
         scale = 1.0 / math.sqrt(d // heads)
         cap = rmt.cache_size
         pm_ids, pf_ids = self._const_ids(dev)
-        fine_host = fine_frame_indices(f, self.max_fine_frames)
-        fine_all = fine_host.numel() == f and bool((fine_host == torch.arange(f)).all())   # <= 32 frames: every frame is fine
-        fine_idx = fine_host.to(dev)
+        fine_idx = fine_frame_indices(f, self.max_fine_frames).to(dev)
         emb = self.token_type_embedding.weight
         newline = self.image_newline
         fz = self.memory_fuser
@@ -304,14 +302,10 @@ class VisualMemoryPipeline(nn.Module):
         cat = states[0] if len(states) == 1 else torch.cat(states, dim=1)               # [B, n*Lq, D]  llava_arch.py:545
         hid = ops.linear(cat, fz[0].weight, fz[0].bias, act=ACT_GELU_ERF)
         memtok = ops.linear(hid, fz[2].weight, fz[2].bias, addvec=emb[0])              # + token_type_embedding[0]
-        nl = newline[None, None].to(memtok.dtype).expand(b, 1, d)
-        parts = [self.embed_tokens(pm_ids)[None].expand(b, -1, d), memtok, nl]
-        if not drop_frames:
-            fine = (z if fine_all else z[:, fine_idx]).reshape(b, -1, d)     # no gather copy when it is the identity
-            fine = ops.add_rows(fine, emb[1][None].expand(b, d))                         # + token_type_embedding[1]
-            parts += [self.embed_tokens(pf_ids)[None].expand(b, -1, d), fine, nl]
-        n = len(states)
-        return {"sequence": torch.cat(parts, dim=1),
+        from .autograd import AssembleFn
+        seq = AssembleFn.apply(memtok, z, fine_idx, emb, newline, self.embed_tokens.weight, pm_ids, pf_ids,
+                               self.embed_tokens(pm_ids), self.embed_tokens(pf_ids), bool(drop_frames))
+        return {"sequence": seq,
                 "states": torch.stack([s_.reshape(b, m_slots, p, d) for s_ in states], dim=1)}
 
     def graphed(self, batch: int, frames: int, *, return_states: bool = False) -> "GraphedPipeline":
