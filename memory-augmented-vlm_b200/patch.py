@@ -8,7 +8,9 @@ positional_encoding}` are replaced by the same-named drop-ins holding THE SAME p
 (state_dict keys unchanged, so checkpoints keep loading/saving), and `model.get_2dPool` is rebound to the
 fused kernel.  The tower, the LLM, `token_type_embedding`, `image_newline` and
 `prepare_inputs_labels_for_multimodal` itself are untouched: the reference's own loop
-(llava_arch.py:481-557) now calls into libmavlm.so through the unchanged call signatures.
+(llava_arch.py:481-557) now calls into libmavlm.so through the unchanged call signatures.  The legacy
+`MultimodalOpsMixin` methods (`compress_temporal_features`, ...) and an `attention_model`, when the model has
+them, are rebound to `legacy.py` the same way.
 `model.mavlm_pipeline` additionally exposes the fused whole-path call.
 """
 from __future__ import annotations
@@ -121,6 +123,18 @@ def patch_llava(model: nn.Module, *, chunk_size: int = 32, fused: bool = False) 
         mm_projector=proj, recurrent_memory_transformer=rmt, memory_fuser=fuser, positional_encoding=pe,
         token_type_embedding=inner.token_type_embedding, image_newline=inner.image_newline,
         embed_tokens=inner.embed_tokens, chunk_size=chunk_size, num_patches_per_side=side)
+    # legacy memories: the model class mixes in MultimodalOpsMixin (llava_arch.py:267); rebind its methods
+    # to the B200 ones and, when the model carries the Turing-memory module, swap it for the drop-in (same parameters)
+    from . import legacy
+    for name in ("attention", "attention2", "compress_spatial_features", "compress_temporal_features"):
+        if hasattr(model, name):
+            setattr(model, name, types.MethodType(getattr(legacy.MultimodalOpsMixin, name), model))
+    ntm = getattr(inner, "attention_model", None)
+    if isinstance(ntm, nn.Module) and not isinstance(ntm, legacy.NeuralTuringMachine):
+        new_ntm = legacy.NeuralTuringMachine(ntm.input_dim, ntm.output_dim, attention_dropout=ntm.dropout.p)
+        _adopt(new_ntm, ntm)
+        new_ntm.train(ntm.training)
+        inner.attention_model = new_ntm
     if fused:   # replace the whole method; the reference's own stays reachable for training / non-video inputs
         ref = getattr(type(model), "prepare_inputs_labels_for_multimodal", None)
         if ref is not None:

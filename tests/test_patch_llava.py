@@ -71,6 +71,46 @@ def test_patch_keeps_state_dict_and_shares_parameters():
         m.get_2dPool(torch.zeros(1, 729, 32))
 
 
+def test_patch_rebinds_the_legacy_memory_methods():
+    """A model that mixes in the reference-style MultimodalOpsMixin and owns a Turing-memory module gets the B200
+    methods and the drop-in NeuralTuringMachine on the same parameters."""
+    from mavlm_b200 import legacy
+
+    class _RefNTM(nn.Module):                                 # parameter container with memory_builder.py:8-19's names
+        def __init__(self, d=16):
+            super().__init__()
+            self.input_dim = self.output_dim = d
+            self.q_proj, self.k_proj, self.v_proj = nn.Linear(d, d), nn.Linear(d, d), nn.Linear(d, d)
+            self.dropout, self.out_proj, self.out_dropout = nn.Dropout(0.1), nn.Linear(d, d), nn.Dropout(0.1)
+            self.out_ln = nn.LayerNorm(d, eps=1e-12)
+
+    class _LegacyModel(_Model):
+        def compress_temporal_features(self, image_features, video_idx_in_batch, all_video=False):
+            raise AssertionError("the reference method should have been replaced")
+
+        def compress_spatial_features(self, image_features, compress_size=1):
+            raise AssertionError("the reference method should have been replaced")
+
+        def attention(self, turing_memory, new_feature, update_ratio=0.2):
+            raise AssertionError("the reference method should have been replaced")
+
+    m = _LegacyModel()
+    m.get_model().attention_model = _RefNTM().eval()
+    before = {k: v.data_ptr() for k, v in m.state_dict().items()}
+    M.patch_llava(m)
+    assert {k: v.data_ptr() for k, v in m.state_dict().items()} == before
+    assert isinstance(m.get_model().attention_model, legacy.NeuralTuringMachine)
+    assert not m.get_model().attention_model.training
+    assert m.compress_temporal_features.__func__ is legacy.MultimodalOpsMixin.compress_temporal_features
+    x = torch.zeros(2, 36, 8)
+    assert m.compress_spatial_features(x, 6) is x            # 6 x 6 already: returned untouched, like the reference
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.compress_spatial_features(x, 3)
+    with pytest.raises(NotImplementedError):
+        m.config.video_sample_type = "bogus"
+        m.compress_temporal_features([x], [0])
+
+
 def test_patch_accepts_fp16_and_rejects_other_dtypes():
     m = _Model().half()                                      # the reference inference loader's default (builder.py:27)
     M.patch_llava(m)
