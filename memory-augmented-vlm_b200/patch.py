@@ -20,7 +20,7 @@ import types
 import torch
 from torch import nn
 
-from .modules import (sample_frame_indices, Config, MemoryFuserMLP, TemporalPositionalEncoding, TransformerProjector, VisionProjector,
+from .modules import (sample_frame_indices, Config, MemoryFuser, MemoryFuserMLP, TemporalPositionalEncoding, TransformerProjector, VisionProjector,
                       get_2dPool)
 from .pipeline import VisualMemoryPipeline
 from .splice import splice_text_and_vision
@@ -103,7 +103,17 @@ def patch_llava(model: nn.Module, *, chunk_size: int = 32, fused: bool = False) 
     if dtype not in (torch.float32, torch.bfloat16, torch.float16):
         raise TypeError(f"mavlm: {dtype} is not supported on this path (fp32, bf16 and fp16 only)")
     proj = VisionProjector(*[m for m in inner.mm_projector])
-    fuser = MemoryFuserMLP(*[m for m in inner.memory_fuser])
+    if isinstance(inner.memory_fuser, nn.Sequential):
+        fuser = MemoryFuserMLP(*[m for m in inner.memory_fuser])
+    elif hasattr(inner.memory_fuser, "transformer_encoder"):      # the encoder variant (MemoryFuser.py, llava_arch.py:137-143)
+        ref = inner.memory_fuser
+        layers = ref.transformer_encoder.layers
+        fuser = MemoryFuser(ref.input_proj.in_features, num_layers=len(layers), num_heads=layers[0].self_attn.num_heads,
+                            dropout=layers[0].dropout.p, device=str(ref.input_proj.weight.device))
+        _adopt(fuser, ref)
+        fuser.train(ref.training)
+    else:
+        raise TypeError(f"mavlm: unsupported memory_fuser {type(inner.memory_fuser).__name__}")
     rmt = convert_rmt(inner.recurrent_memory_transformer)
     old_pe = inner.positional_encoding
     pe = TemporalPositionalEncoding(old_pe.max_frames, old_pe.embed_dim, learnable=old_pe.learnable)

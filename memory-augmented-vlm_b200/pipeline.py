@@ -27,7 +27,7 @@ from torch import nn
 
 from . import ops
 from ._lib import ACT_GELU_ERF, ACT_NONE, ACT_RELU
-from .modules import (Attention, MemoryFuserMLP, TemporalPositionalEncoding, TransformerProjector, VisionProjector,
+from .modules import (Attention, MemoryFuser, MemoryFuserMLP, TemporalPositionalEncoding, TransformerProjector, VisionProjector,
                       fine_frame_indices, uniform_segment_variant)
 
 MEMORY_PROMPT_IDS = (1986, 374, 264, 1550, 11591, 12126, 315, 279, 2766, 25)      # llava_arch.py:708
@@ -38,7 +38,7 @@ class VisualMemoryPipeline(nn.Module):
     """Holds (references to) the drop-in modules and runs the whole path for B videos."""
 
     def __init__(self, *, mm_projector: Optional[VisionProjector], recurrent_memory_transformer: TransformerProjector,
-                 memory_fuser: MemoryFuserMLP, positional_encoding: TemporalPositionalEncoding,
+                 memory_fuser: "MemoryFuserMLP | MemoryFuser", positional_encoding: TemporalPositionalEncoding,
                  token_type_embedding: nn.Embedding, image_newline: torch.Tensor, embed_tokens: nn.Embedding,
                  chunk_size: int = 32, max_fine_frames: int = 32, num_patches_per_side: int = 27,
                  pool_stride: int = 2, projector_frames_per_pass: int = 64, pool_before_w2: bool = True):
@@ -203,6 +203,19 @@ class VisualMemoryPipeline(nn.Module):
         emb = self.token_type_embedding.weight.detach()
         npm = len(MEMORY_PROMPT_IDS)
         fz = self.memory_fuser
+        if isinstance(fz, MemoryFuser):
+            # encoder-variant fuser (MemoryFuser.py; the mode llava_arch.py:137-143 keeps commented out): self-attention
+            # inside each 196-token memory slot, over the cached states oldest first (llava_arch.py:545-546)
+            order = [(first + i) % cap for i in range(n_keep)]
+            ordered = ring_states[:, :n_keep] if first == 0 else torch.cat([ring_states[:, s_:s_ + 1] for s_ in order], dim=1)
+            tok = fz(ordered.reshape(b * n_keep * (lq // p), p, d)).reshape(b, n_keep * lq, d)
+            for bi in range(b):
+                ops.assemble(seq_out[bi], tok[bi].contiguous(), n_keep * lq, z[bi], fine_idx, p, emb,
+                             self.image_newline.detach(), self.embed_tokens.weight.detach(), pm_ids, pf_ids, drop_frames)
+            out = {"sequence": seq_out}
+            if return_states:
+                out["states"] = ordered
+            return out
         hidden = ops.linear(ring_states[:, :n_keep].reshape(b * n_keep * lq, d), fz[0].weight, fz[0].bias,
                             act=ACT_GELU_ERF).reshape(b, n_keep, lq, 4 * d)
         # reference order is oldest state first: ring slots (first+i) % cap -- at most two contiguous runs of
@@ -262,6 +275,9 @@ class VisualMemoryPipeline(nn.Module):
         emb = self.token_type_embedding.weight
         newline = self.image_newline
         fz = self.memory_fuser
+        if isinstance(fz, MemoryFuser):
+            raise NotImplementedError("mavlm: the encoder-variant MemoryFuser is inference-only on this path; train "
+                                      "with the MLP fuser the reference uses (llava_arch.py:132-136)")
         bounds = uniform_segment_variant(f, self.chunk_size)
         n_chunks = len(bounds) - 1
         z2 = z.reshape(b, f * p, d)

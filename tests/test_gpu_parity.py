@@ -391,6 +391,29 @@ def test_memory_fuser_encoder_variant_golden():
     assert err(enc.bfloat16()(x.bfloat16().to(DEV)).float(), refq) < BF16_TOL
 
 
+def test_fused_pipeline_with_the_encoder_variant_fuser():
+    """The fused path with MemoryFuser as the fuser (3 chunks, ring not wrapped; and cap 2 so that the ring wraps):
+    memory segment == encoder(states oldest first) + type embedding 0, everything else as with the MLP fuser."""
+    for cap in (10, 2):
+        pipe, _ = synthetic.build_pipeline(64, 16, dtype=torch.float32, chunk_size=2, cache_size=cap, device=DEV)
+        torch.manual_seed(3)
+        enc = M.MemoryFuser(64, num_layers=1, num_heads=4).eval().to(DEV)
+        x = torch.randn(1, 6, 729, 16, device=DEV)
+        idx = torch.arange(6, device=DEV)[None]
+        ref = pipe(x, idx, return_states=True)
+        pipe.memory_fuser = enc
+        got = pipe(x, idx, return_states=True)
+        n = got["states"].shape[1]
+        assert n == min(3, cap) and torch.equal(got["states"], ref["states"])
+        lq = 8 * 196
+        want_mem = enc(got["states"].reshape(n * 8, 196, 64)).reshape(n * lq, 64) + pipe.token_type_embedding.weight[0]
+        assert err(got["sequence"][0, 10:10 + n * lq], want_mem.detach().cpu().numpy()) < FP32_TOL
+        assert torch.equal(got["sequence"][0, :10], ref["sequence"][0, :10])
+        assert torch.equal(got["sequence"][0, 10 + n * lq:], ref["sequence"][0, 10 + n * lq:])
+        with pytest.raises(NotImplementedError):
+            pipe.memory_forward_train(torch.randn(1, 2, 196, 64, device=DEV))
+
+
 def test_frame_scores_bf16_tier():
     """K9 (MemoryController.py:135-139) in the bf16 tier: frame scores sum to H*Lq/P = 64 and match the oracle."""
     cfg = M.Config()

@@ -111,6 +111,29 @@ def test_patch_rebinds_the_legacy_memory_methods():
         m.compress_temporal_features([x], [0])
 
 
+def test_patch_adopts_the_encoder_variant_fuser():
+    class _RefEncoderFuser(nn.Module):                        # MemoryFuser.py:4-22's attribute names
+        def __init__(self, d):
+            super().__init__()
+            self.input_proj = nn.Linear(d, d)
+            layer = nn.TransformerEncoderLayer(d_model=d, nhead=4, dim_feedforward=4 * d, dropout=0.1, batch_first=True,
+                                               activation="gelu")
+            self.transformer_encoder = nn.TransformerEncoder(layer, num_layers=2, enable_nested_tensor=False)
+            self.output_proj = nn.Linear(d, d)
+
+    m = _Model()
+    m.get_model().memory_fuser = _RefEncoderFuser(32).eval()
+    before = {k: v.data_ptr() for k, v in m.state_dict().items()}
+    M.patch_llava(m)
+    assert {k: v.data_ptr() for k, v in m.state_dict().items()} == before
+    f = m.get_model().memory_fuser
+    assert isinstance(f, M.MemoryFuser) and f.num_heads == 4 and len(f.transformer_encoder.layers) == 2 and not f.training
+    assert m.mavlm_pipeline.memory_fuser is f
+    m.get_model().memory_fuser = nn.Identity()
+    with pytest.raises(TypeError):
+        M.patch_llava(m)
+
+
 def test_patch_accepts_fp16_and_rejects_other_dtypes():
     m = _Model().half()                                      # the reference inference loader's default (builder.py:27)
     M.patch_llava(m)
