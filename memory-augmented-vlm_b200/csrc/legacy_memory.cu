@@ -997,6 +997,7 @@ int mavlm_frame_mean_fwd(const void* x, void* out, int frames, int tokens, int d
   MAVLM_REQUIRE(dtype_ok(dtype), MAVLM_E_INVALID, "frame_mean: bad dtype %d", dtype);
   const int vec = dtype == MAVLM_F32 ? 4 : 8;
   MAVLM_REQUIRE(dim > 0 && dim % vec == 0 && tokens > 0, MAVLM_E_INVALID, "frame_mean: dim %d must be a multiple of %d", dim, vec);
+  MAVLM_REQUIRE(frames >= 0 && frames <= 65535, MAVLM_E_INVALID, "frame_mean: at most 65535 frames per call (got %d)", frames);
   if (frames == 0) return MAVLM_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const dim3 grid(ceil_div(dim / vec, 128), frames);
