@@ -295,8 +295,9 @@ struct LmBatch {
   long long coin_stride;
 };
 
+// 4 CTAs per SM (<= 64 registers): the 512 CTAs of a drop launch must be co-resident (one wave)
 template <typename T>
-__global__ void __launch_bounds__(LM_THREADS) lm_stream_kernel(LmBatch b, long long L, int phase, int step) {
+__global__ void __launch_bounds__(LM_THREADS, 4) lm_stream_kernel(LmBatch b, long long L, int phase, int step) {
   constexpr int V = Vec<T>::N;
   const int vid = blockIdx.z;
   const T* __restrict__ x = static_cast<const T*>(b.xs != nullptr ? b.xs[vid] : b.x_single);
