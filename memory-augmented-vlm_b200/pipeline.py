@@ -369,42 +369,55 @@ class GraphedPipeline:
 class HostStreamEncoder:
     """Host-buffer front end: pinned host tower tokens in, pinned host sequence out, with the H2D copy of
     video i+1 and the D2H copy of result i-1 overlapped with the graph replay of video i on three
-    streams (copy-in / compute / copy-out).  This is the public end-to-end call bench.py's `e2e` times."""
+    streams (copy-in / compute / copy-out).  Two captured graphs take turns, so the copies go straight into / out of
+    a graph's static buffers (no staging copy on the compute stream): while graph A computes, video i+1 lands in
+    graph B's input and result i-1 leaves graph B's output.  This is the public end-to-end call bench.py's `e2e`
+    times."""
 
     def __init__(self, pipe: VisualMemoryPipeline, batch: int, frames: int):
-        self.g = pipe.graphed(batch, frames)
+        self.gs = [pipe.graphed(batch, frames), GraphedPipeline(pipe, batch, frames)]
+        self.g = self.gs[0]
         dev = self.g.x.device
         self.dev = dev
-        self.stage_in = torch.empty_like(self.g.x)
-        self.stage_out = torch.empty_like(self.g.out["sequence"])
         self.s_in, self.s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-        self.ev_in, self.ev_x_free = torch.cuda.Event(), torch.cuda.Event()
-        self.ev_out_ready, self.ev_out_free = torch.cuda.Event(), torch.cuda.Event()
-        self._first = True
+        self.ev_in = [torch.cuda.Event(), torch.cuda.Event()]
+        self.ev_done = [torch.cuda.Event(), torch.cuda.Event()]         # replay finished: input consumed, output ready
+        self.ev_out_free = [torch.cuda.Event(), torch.cuda.Event()]     # D2H of the output finished
+        self._used = [False, False]
+        self._k = 0
+        self._idx_synced = False
 
     @torch.no_grad()
     def submit(self, host_tokens: torch.Tensor, frame_idx: torch.Tensor, host_out: torch.Tensor) -> None:
         """Enqueue one batch: host_tokens (pinned) -> device -> path -> host_out (pinned).  Asynchronous;
         call synchronize() before reading host_out."""
+        k = self._k
+        g = self.gs[k]
         cur = torch.cuda.current_stream(self.dev)
         with torch.cuda.stream(self.s_in):
-            if not self._first:
-                self.s_in.wait_event(self.ev_x_free)                    # staging buffer consumed by the previous step
-            self.stage_in.copy_(host_tokens.reshape(self.stage_in.shape), non_blocking=True)
-            self.ev_in.record(self.s_in)
-        cur.wait_event(self.ev_in)
-        self.g.x.copy_(self.stage_in, non_blocking=True)
-        self.ev_x_free.record(cur)
-        out = self.g(None, frame_idx if frame_idx is not None else None)
-        if not self._first:
-            cur.wait_event(self.ev_out_free)                            # previous D2H finished reading stage_out
-        self.stage_out.copy_(out["sequence"], non_blocking=True)
-        self.ev_out_ready.record(cur)
+            if self._used[k]:
+                self.s_in.wait_event(self.ev_done[k])                   # this graph's previous replay has read its input
+            g.x.copy_(host_tokens.reshape(g.x.shape), non_blocking=True)
+            self.ev_in[k].record(self.s_in)
+        cur.wait_event(self.ev_in[k])
+        if self._used[k]:
+            cur.wait_event(self.ev_out_free[k])                         # ... and its previous output has left
+        if frame_idx is not None:                                       # new indices go to both graphs
+            self.gs[0].pipe.positional_encoding.validate(frame_idx)
+            for gg in self.gs:
+                gg.idx.copy_(frame_idx.reshape(gg.idx.shape), non_blocking=True)
+            self._idx_synced = True
+        elif not self._idx_synced:                                      # None = keep the indices of pipe.graphed(...)
+            self.gs[1].idx.copy_(self.gs[0].idx, non_blocking=True)
+            self._idx_synced = True
+        out = g(None, None)
+        self.ev_done[k].record(cur)
         with torch.cuda.stream(self.s_out):
-            self.s_out.wait_event(self.ev_out_ready)
-            host_out.copy_(self.stage_out, non_blocking=True)
-            self.ev_out_free.record(self.s_out)
-        self._first = False
+            self.s_out.wait_event(self.ev_done[k])
+            host_out.copy_(out["sequence"], non_blocking=True)
+            self.ev_out_free[k].record(self.s_out)
+        self._used[k] = True
+        self._k = k ^ 1
 
     def synchronize(self) -> None:
         self.s_out.synchronize()

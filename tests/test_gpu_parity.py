@@ -344,6 +344,14 @@ def test_graph_replay_and_host_streaming_match_eager():
     enc.synchronize()
     assert torch.equal(host_out[0], eager.cpu()) and torch.equal(host_out[2], eager.cpu())
     assert not torch.equal(host_out[1], eager.cpu())
+    half = pipe(xs[1].to(DEV), idx)["sequence"]
+    assert torch.equal(host_out[1], half.cpu())                                  # the second (ping-pong) graph, same indices
+    idx2 = (torch.arange(32) * 3)[None]                                          # new indices reach both graphs
+    shifted = pipe(x.to(DEV), idx2)["sequence"].cpu()
+    for ho in host_out[:2]:
+        enc.submit(x, idx2, ho)
+    enc.synchronize()
+    assert torch.equal(host_out[0], shifted) and torch.equal(host_out[1], shifted) and not torch.equal(shifted, eager.cpu())
     with pytest.raises(ValueError):
         g(x.to(DEV), torch.full((1, 32), 600))                                   # PE index check survives the graph path
 
