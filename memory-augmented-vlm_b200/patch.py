@@ -136,9 +136,10 @@ def patch_llava(model: nn.Module, *, chunk_size: int = 32, fused: bool = False) 
     # legacy memories: the model class mixes in MultimodalOpsMixin (llava_arch.py:267); rebind its methods
     # to the B200 ones and, when the model carries the Turing-memory module, swap it for the drop-in (same parameters)
     from . import legacy
-    for name in ("attention", "attention2", "compress_spatial_features", "compress_temporal_features"):
-        if hasattr(model, name):
-            setattr(model, name, types.MethodType(getattr(legacy.MultimodalOpsMixin, name), model))
+    if hasattr(model, "compress_temporal_features"):         # the mixin's marker method; `attention` alone is too generic
+        for name in ("attention", "attention2", "compress_spatial_features", "compress_temporal_features"):
+            if hasattr(model, name):
+                setattr(model, name, types.MethodType(getattr(legacy.MultimodalOpsMixin, name), model))
     ntm = getattr(inner, "attention_model", None)
     if isinstance(ntm, nn.Module) and not isinstance(ntm, legacy.NeuralTuringMachine):
         new_ntm = legacy.NeuralTuringMachine(ntm.input_dim, ntm.output_dim, attention_dropout=ntm.dropout.p)
