@@ -153,6 +153,28 @@ def test_host_side_of_the_drop_in():
         idx = next(i for i in range(len(after)) if after[i] != allg[i])
         dec.append((idx, idx + 1))
     assert L._replay_steps(L.MERGE, INP["stream"].shape[0], 3, dec, None) == want
+    # the other three modes: recover each step's decision from the reference's lists by search, then replay the log
+    T = INP["stream"].shape[0]
+
+    def apply(mode, groups, i, a, b):
+        allg = [list(g) for g in groups] + [[i]]
+        if mode in (L.DROP, L.K_DROP):
+            del allg[a]
+        else:
+            allg[b] = allg[a] + allg[b]
+            del allg[a]
+        return allg
+
+    for mode, key in ((L.DROP, "drop5"), (L.K_DROP, "kdrop5"), (L.K_MERGE, "kmerge5")):
+        want = META[f"{key}.steps"]
+        dec = []
+        for n, (before, after) in enumerate(zip(want[:-1], want[1:])):
+            found = [(a, b) for a in range(6) for b in range(6)
+                     if (mode in (L.DROP, L.K_DROP) or a != b) and apply(mode, before, 5 + n, a, b) == after]
+            assert found, (key, n)
+            dec.append(found[0])
+        coins_ = [1] * len(dec)                                  # k_drop with coin 1 drops `left` = the index we recovered
+        assert L._replay_steps(mode, T, 5, dec, coins_) == want, key
     with pytest.raises(RuntimeError):
         L.segment(torch.from_numpy(INP["seg_feat"]))
     with pytest.raises(RuntimeError):
