@@ -120,8 +120,10 @@ class VisualMemoryPipeline(nn.Module):
 
     @torch.no_grad()
     def memory_forward(self, z: torch.Tensor, *, seq_out: Optional[torch.Tensor] = None, drop_frames: bool = False,
-                       return_states: bool = True) -> Dict[str, torch.Tensor]:
-        """z: pooled + PE'd frames [B, F, P, D].  Runs the recurrence, the fuser and the assembly."""
+                       return_states: bool = True, boundaries: Optional[Sequence[int]] = None) -> Dict[str, torch.Tensor]:
+        """z: pooled + PE'd frames [B, F, P, D].  Runs the recurrence, the fuser and the assembly.
+        `boundaries`: chunk boundaries [0, ..., F] replacing the uniform scheduler of llava_arch.py:528-534, e.g. the
+        scene-based ones of `legacy.adjusted_segment(legacy.frame_means(z[0]))` (segment.py:52-128)."""
         rmt = self.recurrent_memory_transformer
         b, f, p, d = z.shape
         dtype, dev = z.dtype, z.device
@@ -139,7 +141,12 @@ class VisualMemoryPipeline(nn.Module):
         wf, bf = self._formation_kv_weights()
         kvf = ops.linear(z2, wf, bf)                                    # [B, F*P, depth*2*hd]
 
-        bounds = uniform_segment_variant(f, self.chunk_size)
+        if boundaries is None:
+            bounds = uniform_segment_variant(f, self.chunk_size)
+        else:
+            bounds = [int(v) for v in boundaries]
+            if len(bounds) < 2 or bounds[0] != 0 or bounds[-1] != f or any(b1 <= b0 for b0, b1 in zip(bounds, bounds[1:])):
+                raise ValueError(f"mavlm: chunk boundaries must rise from 0 to the frame count {f}, got {bounds}")
         n_chunks = len(bounds) - 1
         n_keep = min(n_chunks, cap)
         evo = rmt.memory_update_attention

@@ -283,6 +283,30 @@ def test_cache_ring_buffer_beyond_ten_chunks_matches_module_path():
     assert err(res["states"][0, 0].reshape(8, 196, 64), ref["states"][0]) < 5e-5
 
 
+def test_custom_chunk_boundaries_match_the_module_loop():
+    """Scene-style ragged chunks (boundaries=...) through the fused path == feeding the same segments to the
+    reference-shaped module one by one (llava_arch.py:530-537)."""
+    pipe, _ = synthetic.build_pipeline(64, 16, dtype=torch.float32, chunk_size=4, device=DEV)
+    x = synthetic.synthetic_tower_tokens(1, 12, 16, dtype=torch.float32).to(DEV)
+    idx = torch.arange(12, device=DEV)
+    bounds = [0, 3, 4, 9, 12]
+    res = pipe(x, idx[None], boundaries=bounds)
+    z = pipe.encode_frames(x[0], idx)
+    rmt = pipe.recurrent_memory_transformer
+    rmt.memory_cache = []
+    for b0, b1 in zip(bounds, bounds[1:]):
+        cache, _ = rmt(z[b0:b1])
+    assert res["states"].shape[1] == 4 == len(cache)
+    for i, st in enumerate(cache):
+        assert err(res["states"][0, i].reshape(8, 196, 64), st.detach().cpu().numpy()) < FP32_TOL
+    uniform = pipe(x, idx[None])
+    assert uniform["states"].shape[1] == 3 and not torch.equal(uniform["sequence"][0, :100], res["sequence"][0, :100])
+    for bad in ([1, 12], [0, 5, 5, 12], [0, 13], [0]):
+        with pytest.raises(ValueError):
+            pipe(x, idx[None], boundaries=bad)
+    rmt.memory_cache = []
+
+
 # ------------------------------------------------------------------------------------------------
 # full-size properties (no oracle needed)
 # ------------------------------------------------------------------------------------------------
