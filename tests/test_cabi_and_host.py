@@ -52,6 +52,21 @@ def test_argument_validation_without_gpu():
                                        None) == _lib.E_INVALID
     with pytest.raises(ValueError, match="Unexpected mm_spatial_pool_mode"):
         M.get_2dPool(torch.zeros(1, 729, 8), mode="nearest")           # llava_arch.py:294 raises the same
+    # SURVEY 8f-4 entry points: geometry is checked before any CUDA call
+    assert lib.mavlm_stream_compress_fwd(None, 10, 64, 0, 1, None, None, None, None, None, 0, _lib.F32, None) == _lib.E_INVALID
+    assert b"keep" in lib.mavlm_last_error_string()
+    assert lib.mavlm_stream_compress_fwd(None, 10, 64, 65, 1, None, None, None, None, None, 0, _lib.F32, None) == _lib.E_INVALID
+    assert lib.mavlm_stream_compress_fwd(None, 10, 63, 3, 4, None, None, None, None, None, 0, _lib.F32, None) == _lib.E_INVALID
+    assert b"mode" in lib.mavlm_last_error_string()
+    assert lib.mavlm_stream_compress_fwd(None, 10, 62, 3, 1, None, None, None, None, None, 0, _lib.BF16, None) == _lib.E_INVALID
+    assert b"multiple of 8" in lib.mavlm_last_error_string()
+    assert lib.mavlm_stream_compress_workspace_bytes(64, 65, 1, _lib.F32) == 0
+    assert lib.mavlm_avg_pool_fwd(None, None, 1, 6, 7, 8, _lib.F32, None) == _lib.E_INVALID
+    assert lib.mavlm_frame_mean_fwd(None, None, 1, 4, 6, _lib.BF16, None) == _lib.E_INVALID
+    assert lib.mavlm_ntm_softmax_fwd(None, 8, 1, 9, 1.0, 1.0, None, 8, 8, None, None, 0, _lib.F32, None) == _lib.E_INVALID
+    assert lib.mavlm_kmeans_iter_fwd(None, None, None, None, None, None, None, None, 4, 62, 2, None, 0, _lib.BF16,
+                                     None) == _lib.E_INVALID
+    assert lib.mavlm_depth_scores_fwd(None, None, 0, 0, None) == 0                          # nothing to do
 
 
 def test_state_dict_keys_match_reference():
