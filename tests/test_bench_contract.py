@@ -1,0 +1,45 @@
+"""bench.py's output contract, checked on the CPU through the reference arm (the only arm that runs without a GPU):
+exactly one line on stdout, valid JSON, the keys the driver reads."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REQUIRED = {"impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+            "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"}
+
+
+def _run(*args, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True, timeout=600,
+                       cwd=ROOT, env=e)
+    assert p.returncode == 0, p.stderr[-2000:]
+    return p.stdout
+
+
+def test_reference_arm_prints_one_json_line():
+    out = _run("--workload", "legacy", "--impl", "reference", "--steps", "1", "--warmup", "0")
+    lines = [l for l in out.split("\n") if l.strip()]
+    assert len(lines) == 1, out
+    j = json.loads(lines[0])
+    assert REQUIRED <= set(j), REQUIRED - set(j)
+    assert j["impl"] == "reference" and j["value"] > 0 and j["higher_is_better"] is True
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and "workload" in j["config"]
+    assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_reference_arm_is_silent_on_other_ranks():
+    out = _run("--workload", "legacy", "--impl", "reference", "--steps", "1", "--warmup", "0",
+               env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    assert out.strip() == ""
+
+
+def test_library_noise_on_fd1_does_not_reach_stdout():
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; bench.isolate_stdout(); "
+            "os.write(1, b'NCCL version banner\\n'); print('python noise'); bench.emit_line('{\"ok\": 1}')" % ROOT)
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr
+    assert p.stdout == '{"ok": 1}\n'
+    assert "NCCL version banner" in p.stderr and "python noise" in p.stderr
