@@ -43,3 +43,26 @@ def test_library_noise_on_fd1_does_not_reach_stdout():
     assert p.returncode == 0, p.stderr
     assert p.stdout == '{"ok": 1}\n'
     assert "NCCL version banner" in p.stderr and "python noise" in p.stderr
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_gpu_arm_line_has_every_contract_key():
+    out = _run("--steps", "5", "--warmup", "3")
+    lines = [l for l in out.split("\n") if l.strip()]
+    assert len(lines) == 1, out[:2000]
+    j = json.loads(lines[0])
+    need = (REQUIRED - {"impl"}) | {"clocks", "gpu_launches", "roofline"}
+    assert need <= set(j), need - set(j)
+    assert j["n_gpus"] == 1 and j["steps"] == 5 and j["warmup"] == 3 and j["dtype"] == "bf16" and j["scaling"] == "weak"
+    assert j["value"] > 1000 and abs(j["value"] - 64 * 1e3 / j["ms_per_step"]) < 1e-6 * j["value"]
+    r = j["roofline"]
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["traffic"] is None or r["traffic"] > 0
+    e = j["e2e"]
+    assert e["value"] > 1000 and e["h2d_bytes_per_step"] == 64 * 729 * 1152 * 2 and e["d2h_bytes_per_step"] > 0
+    c = j["cpu_baseline"]
+    assert c["kind"] == "port" and c["value"] > 0 and c["cores"] >= 1 and c["sample"]
+    assert j["gpu_launches"] > 0 and set(j["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
