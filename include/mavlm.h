@@ -211,7 +211,7 @@ MAVLM_API int mavlm_ntm_softmax_fwd(const float* scores, int64_t ld_scores, int6
  * {a_outer, a_inner, b_outer, b_inner, c_outer, c_inner} or NULL.  dgrad: dX = dY W (trans_b = 0);
  * wgrad: dW (+)= dY^T X (trans_a = 1, trans_b = 0, accumulate over chunks).  MAVLM_BF16 runs on the tcgen05
  * kernel (transposed operands are consumed as MN-major UMMA operands; alpha must be 1; out_dtype may be
- * MAVLM_F32), MAVLM_F32 on the SIMT tier. */
+ * MAVLM_F32), MAVLM_F16 likewise for the inference layouts (trans_a = 0), MAVLM_F32 on the SIMT tier. */
 MAVLM_API int mavlm_gemm_ex(const void* A, int64_t lda, int trans_a, const void* B, int64_t ldb, int trans_b, void* C,
                             int64_t ldc, int M, int N, int K, float alpha, int accumulate, int outer, int inner,
                             const int64_t* host_strides, int dtype, int out_dtype, void* stream);

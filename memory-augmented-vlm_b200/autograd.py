@@ -16,7 +16,7 @@ import torch
 from . import _lib
 from ._lib import ACT_GELU_ERF, ACT_NONE, ACT_RELU
 
-_DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+_DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}   # fp16: inference-only GEMM layouts
 
 
 def _s() -> int:

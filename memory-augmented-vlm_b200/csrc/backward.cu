@@ -11,7 +11,7 @@ int gemm_ex_fp32(const float* A, long long lda, int trans_a, const float* B, lon
                  const long long* strides, cudaStream_t st);
 int gemm_ex_bf16(const __nv_bfloat16* A, long long lda, int trans_a, const __nv_bfloat16* B, long long ldb, int trans_b,
                  void* C, long long ldc, int M, int N, int K, int accumulate, int out_f32, int outer, int inner,
-                 const long long* s6, cudaStream_t st);
+                 const long long* s6, cudaStream_t st, int half = 0);
 
 template <typename T>
 __device__ __forceinline__ float ldf(const T* p);
@@ -265,10 +265,14 @@ int mavlm_gemm_ex(const void* A, int64_t lda, int trans_a, const void* B, int64_
     return gemm_ex_fp32(static_cast<const float*>(A), lda, trans_a, static_cast<const float*>(B), ldb, trans_b,
                         static_cast<float*>(C), ldc, M, N, K, alpha, accumulate, outer, inner, st6, st);
   }
-  MAVLM_REQUIRE(dtype == MAVLM_BF16, MAVLM_E_INVALID, "gemm_ex: bad dtype %d", dtype);
+  MAVLM_REQUIRE(dtype == MAVLM_BF16 || dtype == MAVLM_F16, MAVLM_E_INVALID, "gemm_ex: bad dtype %d", dtype);
   MAVLM_REQUIRE(alpha == 1.f, MAVLM_E_INVALID, "gemm_ex: the tensor-core tier has no alpha scaling (got %f)", alpha);
+  MAVLM_REQUIRE(out_dtype == MAVLM_F32 || out_dtype == dtype, MAVLM_E_INVALID, "gemm_ex: output must be fp32 or the input dtype");
+  MAVLM_REQUIRE(dtype == MAVLM_BF16 || trans_a == 0, MAVLM_E_INVALID,
+                "gemm_ex: fp16 is the inference dtype (trans_a = 1 is a training layout)");
   return gemm_ex_bf16(static_cast<const __nv_bfloat16*>(A), lda, trans_a, static_cast<const __nv_bfloat16*>(B), ldb,
-                      trans_b, C, ldc, M, N, K, accumulate, out_dtype == MAVLM_F32, outer, inner, st6, st);
+                      trans_b, C, ldc, M, N, K, accumulate, out_dtype == MAVLM_F32, outer, inner, st6, st,
+                      dtype == MAVLM_F16 ? 1 : 0);
 }
 
 int mavlm_colsum(const void* x, int64_t ld, float* out, int M, int N, int accumulate, int dtype, void* stream) {

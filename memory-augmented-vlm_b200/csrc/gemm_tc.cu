@@ -495,6 +495,23 @@ static int dispatch_bn(int bn, int cg, const CUtensorMap& tmA, const CUtensorMap
       }
     }
   }
+  if constexpr (!A_MN && B_MN) {
+    if (p.half) {  // fp16 with an MN-major B operand ([K, N] row-major: P @ V, w @ new in the inference-only modules)
+      if (cg == 2) {
+        if (bn >= 192) return launch_gemm_tc<256, false, true, 2, __half>(tmA, tmB, tmC, p, st);
+        return launch_gemm_tc<128, false, true, 2, __half>(tmA, tmB, tmC, p, st);
+      }
+      switch (bn) {
+        case 256: return launch_gemm_tc<256, false, true, 1, __half>(tmA, tmB, tmC, p, st);
+        case 192: return launch_gemm_tc<192, false, true, 1, __half>(tmA, tmB, tmC, p, st);
+        case 128: return launch_gemm_tc<128, false, true, 1, __half>(tmA, tmB, tmC, p, st);
+        default:  return launch_gemm_tc<64, false, true, 1, __half>(tmA, tmB, tmC, p, st);
+      }
+    }
+  }
+  if constexpr (A_MN) {
+    MAVLM_REQUIRE(!p.half, MAVLM_E_INVALID, "fp16 gemm: a transposed A operand is a training layout; fp16 is inference-only");
+  }
   if constexpr (A_MN || B_MN) {
     if (cg == 2) {  // transposed operands (dgrad / wgrad): CTA-pair tiles of 256 x 256 or 256 x 128
       if (bn >= 192) return launch_gemm_tc<256, A_MN, B_MN, 2>(tmA, tmB, tmC, p, st);
@@ -629,8 +646,9 @@ int gemm_bf16_tc(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, 
 // Backward-pass entry (mavlm_gemm_ex, bf16): trans_a = 1 -> A stored [K,M]; trans_b = 0 -> B stored [K,N].
 int gemm_ex_bf16(const __nv_bfloat16* A, long long lda, int trans_a, const __nv_bfloat16* B, long long ldb, int trans_b,
                  void* C, long long ldc, int M, int N, int K, int accumulate, int out_f32, int outer, int inner,
-                 const long long* s6, cudaStream_t st) {
+                 const long long* s6, cudaStream_t st, int half) {
   GemmTcParams p{};
+  p.half = half;
   p.M = M; p.N = N; p.K = K;
   p.C = C; p.ldc = ldc; p.act = MAVLM_ACT_NONE; p.out_f32 = out_f32; p.accumulate = accumulate;
   return gemm_tc_general(A, lda, trans_a != 0, B, ldb, trans_b == 0, p, outer, inner, s6, st);

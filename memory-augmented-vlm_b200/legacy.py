@@ -452,8 +452,6 @@ def _pad8(n: int) -> int:
 
 def _ntm_weight(q: torch.Tensor, k: torch.Tensor, scale: float, ratio: float, mem: Optional[torch.Tensor] = None):
     """w = ratio * softmax(q k^T * scale) as [M, pad8(n)] (zero padding) and, with mem, mem * (1 - rowsum(w))."""
-    if q.dtype not in (torch.float32, torch.bfloat16):
-        raise TypeError("mavlm: the Turing memory runs in float32 or bfloat16")
     M, n = q.shape[0], k.shape[0]
     n_pad = _pad8(n)
     scores = torch.empty((M, n_pad), dtype=torch.float32, device=q.device)      # row stride padded for the GEMM's stores

@@ -381,9 +381,9 @@ class MemoryFuser(nn.Module):
         dh = d // h
         dt = memory_tokens.dtype
         tc = dt in (torch.bfloat16, torch.float16) and dh in (128, 448)   # head dims the fused tensor-core kernel handles
-        # other head dims in bf16 (7B: dh = 896, 0.5B: 224): attention as batched tcgen05 GEMMs around a row softmax,
+        # other head dims in bf16 / fp16 (7B: dh = 896, 0.5B: 224): attention as batched tcgen05 GEMMs around a row softmax,
         # on sequences padded to a multiple of 8 tokens (the GEMM's K alignment); the pad keys get zero probability
-        gemm_attn = dt == torch.bfloat16 and not tc and dh % 8 == 0 and d % 8 == 0
+        gemm_attn = dt in (torch.bfloat16, torch.float16) and not tc and dh % 8 == 0 and d % 8 == 0
         s_pad = (s_len + 7) // 8 * 8 if gemm_attn else s_len
         if s_pad != s_len:
             padded = memory_tokens.new_zeros((b, s_pad, d))

@@ -175,6 +175,20 @@ def test_gemm_ex_bf16_all_operand_layouts():
             acc = o32.clone()
             ag.gemm_ex(aa, ta, bb, tb, m, n, k, out=acc, accumulate=True)
             assert _nerr(acc, 2 * ref) < 1e-5, (ta, tb)
+    # fp16: the inference layouts (A K-major; B [N, K] or [K, N]); a transposed A is refused
+    ah, bh = a.half(), b.half()
+    refh = ah.double() @ bh.double().T
+    for tb in (True, False):
+        bb = bh if tb else bh.t().contiguous()
+        out = ag.gemm_ex(ah, False, bb, tb, m, n, k)
+        assert out.dtype == torch.float16 and _nerr(out, refh) < 2e-3, tb
+        o32 = ag.gemm_ex(ah, False, bb, tb, m, n, k, out_dtype=torch.float32)
+        assert _nerr(o32, refh) < 1e-5, tb
+        acc = o32.clone()
+        ag.gemm_ex(ah, False, bb, tb, m, n, k, out=acc, accumulate=True)
+        assert _nerr(acc, 2 * refh) < 1e-5, tb
+    with pytest.raises(Exception, match="fp16"):
+        ag.gemm_ex(ah.t().contiguous(), True, bh, True, m, n, k)
 
 
 def test_op_level_gradients_bf16():

@@ -421,6 +421,10 @@ def test_memory_fuser_encoder_variant_golden():
     wq = {k: torch.from_numpy(v).bfloat16().double().numpy() for k, v in wn.items()}
     refq = O.memory_fuser_encoder(x.bfloat16().double().numpy(), wq, num_layers=1, heads=4)
     assert err(enc.bfloat16()(x.bfloat16().to(DEV)).float(), refq) < BF16_TOL
+    wh = {k: torch.from_numpy(v).half().double().numpy() for k, v in wn.items()}            # fp16: same GEMM-attention branch
+    refh = O.memory_fuser_encoder(x.half().double().numpy(), wh, num_layers=1, heads=4)
+    with torch.no_grad():                                                                   # fp16 is inference-only
+        assert err(enc.half()(x.half().to(DEV)).float(), refh) < 5e-3
 
 
 def test_fused_pipeline_with_the_encoder_variant_fuser():
