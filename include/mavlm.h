@@ -114,9 +114,12 @@ MAVLM_API int mavlm_assemble_fwd(void* seq, const void* mem, int64_t n_mem_rows,
 
 /* ---- text / vision splice + padding (llava_arch.py:745-878), the consumer of the assembled sequence: every output
  * row copies one source row.  row_src (device int64 [n_rows]): >= 0 -> embed_table[row_src] (embed_tokens of a text
- * token), -1 -> zeros (padding), <= -2 -> feats[-(row_src + 2)] (a row of the video token sequence). */
-MAVLM_API int mavlm_gather_rows_fwd(void* out, int64_t ld_out, const void* embed_table, const void* feats,
-                                    const int64_t* row_src, int64_t n_rows, int dim, int dtype, void* stream);
+ * token), -1 -> zeros (padding), <= -2 -> feats[-(row_src + 2)] (a row of the video token sequence).  embed_table has
+ * n_table_rows rows and feats n_feat_rows rows, both of `dtype`; a source row outside its table is written as zeros
+ * (never read): the host validates token ids first and raises like the reference's embedding lookup. */
+MAVLM_API int mavlm_gather_rows_fwd(void* out, int64_t ld_out, const void* embed_table, int64_t n_table_rows,
+                                    const void* feats, int64_t n_feat_rows, const int64_t* row_src, int64_t n_rows,
+                                    int dim, int dtype, void* stream);
 
 /* ---- frame pre-processing, the producer side of the path: decoded uint8 frames [F, H, W, 3] (the
  * `.pt` video tensor of extract_video_frames/video_reader_tmp.py:87, fed at train.py:1239) ->

@@ -36,7 +36,8 @@ PROTOTYPES = {
                                         c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mavlm_gemm_bias_pe_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                        c_int64, c_int, c_int, c_int, c_int, c_void_p]),
-    "mavlm_gather_rows_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "mavlm_gather_rows_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int,
+                                      c_int, c_void_p]),
     "mavlm_cast_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "mavlm_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_int,
                                     c_void_p]),
@@ -102,8 +103,6 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if os.environ.get("MAVLM_DEBUG_FLAGS"):                       # development only (see mavlm_debug_set_flags)
-        lib.mavlm_debug_set_flags(int(os.environ["MAVLM_DEBUG_FLAGS"]))
     _lib = lib
     return lib
 

@@ -15,6 +15,7 @@ import torch
 
 from . import _lib
 from ._lib import ACT_GELU_ERF, ACT_NONE, ACT_RELU
+from ._device import on_tensor_device
 
 _DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}   # fp16: inference-only GEMM layouts
 
@@ -32,6 +33,7 @@ def _raw():
     return ops
 
 
+@on_tensor_device
 def gemm_ex(a: torch.Tensor, trans_a: bool, b: torch.Tensor, trans_b: bool, m: int, n: int, k: int, *,
             out: Optional[torch.Tensor] = None, alpha: float = 1.0, accumulate: bool = False,
             out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
@@ -45,6 +47,7 @@ def gemm_ex(a: torch.Tensor, trans_a: bool, b: torch.Tensor, trans_b: bool, m: i
     return out
 
 
+@on_tensor_device
 def colsum(x2: torch.Tensor) -> torch.Tensor:
     """fp32 column sums of a 2-D row-major tensor."""
     out = torch.empty(x2.shape[1], dtype=torch.float32, device=x2.device)
@@ -53,6 +56,7 @@ def colsum(x2: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@on_tensor_device
 def _act_bwd(dy: torch.Tensor, ref: torch.Tensor, act: int) -> torch.Tensor:
     dx = torch.empty_like(dy)
     st = _lib.load().mavlm_act_bwd(_p(dy), _p(ref), _p(dx), dy.numel(), act, _DT[dy.dtype], _s())
@@ -68,6 +72,7 @@ class LinearFn(torch.autograd.Function):
     """y = act(x W^T + b) (+ resid) (+ addvec); act in {none, relu} (GELU is kept unfused when training)."""
 
     @staticmethod
+    @on_tensor_device
     def forward(ctx, x, w, b, resid, addvec, act, out_dtype):
         ops = _raw()
         y = ops._linear_raw(x, w, b, act=act, resid=resid, addvec=addvec, out_dtype=out_dtype)
@@ -81,6 +86,7 @@ class LinearFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @on_tensor_device
     def backward(ctx, dy):
         x, w, y = ctx.saved_tensors
         n, k = w.shape
@@ -113,6 +119,7 @@ class ActFn(torch.autograd.Function):
     """Unfused activation (training keeps the GELU pre-activation)."""
 
     @staticmethod
+    @on_tensor_device
     def forward(ctx, x, act):
         xc = x.contiguous()
         y = torch.empty_like(xc)
@@ -123,6 +130,7 @@ class ActFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @on_tensor_device
     def backward(ctx, dy):
         (ref,) = ctx.saved_tensors
         return _act_bwd(dy.contiguous(), ref, ctx.act), None
@@ -132,6 +140,7 @@ class LayerNormFn(torch.autograd.Function):
     """LayerNorm of the fp32 pre-LN sum."""
 
     @staticmethod
+    @on_tensor_device
     def forward(ctx, pre, gamma, beta, eps, out_dtype):
         y = _raw()._layernorm_raw(pre, gamma, beta, eps, out_dtype)
         ctx.save_for_backward(pre, gamma)
@@ -139,6 +148,7 @@ class LayerNormFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @on_tensor_device
     def backward(ctx, dy):
         pre, gamma = ctx.saved_tensors
         d = pre.shape[-1]
@@ -157,6 +167,7 @@ class XAttnFn(torch.autograd.Function):
     """softmax(q k^T * scale) v per head, backward from the saved log-sum-exp."""
 
     @staticmethod
+    @on_tensor_device
     def forward(ctx, q, k, v, heads, head_dim, scale):
         o, lse, _ = _raw()._xattn_raw(q, k, v, heads, head_dim=head_dim, scale=scale, want_lse=True)
         ctx.save_for_backward(q, k, v, o, lse)
@@ -164,6 +175,7 @@ class XAttnFn(torch.autograd.Function):
         return o
 
     @staticmethod
+    @on_tensor_device
     def backward(ctx, do):
         q, k, v, o, lse = ctx.saved_tensors
         heads, dh, scale = ctx.cfg
@@ -192,6 +204,7 @@ class XAttnKVFn(torch.autograd.Function):
     gradient from autograd's SliceBackward: 720 MB of fills and copies per layer at OV-7B, batch 8)."""
 
     @staticmethod
+    @on_tensor_device
     def forward(ctx, q, kv, heads, head_dim, scale):
         hd = heads * head_dim
         o, lse, _ = _raw()._xattn_raw(q, kv[..., :hd], kv[..., hd:], heads, head_dim=head_dim, scale=scale, want_lse=True)
@@ -200,6 +213,7 @@ class XAttnKVFn(torch.autograd.Function):
         return o
 
     @staticmethod
+    @on_tensor_device
     def backward(ctx, do):
         q, kv, o, lse = ctx.saved_tensors
         heads, dh, scale = ctx.cfg
@@ -228,6 +242,7 @@ class AddRowsFn(torch.autograd.Function):
     """y[t, n, :] = x[t, n, :] + table[t, :]   (initial_memory + memory_pos_embed; x + type embedding with T = 1)."""
 
     @staticmethod
+    @on_tensor_device
     def forward(ctx, x, table):
         idx = torch.arange(x.shape[0], device=x.device)
         y = _raw()._add_pe_raw(x.contiguous(), table.float().contiguous(), idx)
@@ -235,6 +250,7 @@ class AddRowsFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @on_tensor_device
     def backward(ctx, dy):
         dy = dy.contiguous()
         dt = None
@@ -251,6 +267,7 @@ class AssembleFn(torch.autograd.Function):
     (pm_emb / pf_emb are the embedding lookups; their values are re-gathered from the table by the kernel)."""
 
     @staticmethod
+    @on_tensor_device
     def forward(ctx, memtok, z, fine_idx, emb_w, newline, embed_table, pm_ids, pf_ids, pm_emb, pf_emb, drop_frames):
         ops = _raw()
         b, n_mem, d = memtok.shape
@@ -272,6 +289,7 @@ class AssembleFn(torch.autograd.Function):
         return seq
 
     @staticmethod
+    @on_tensor_device
     def backward(ctx, dseq):
         n_pm, n_mem, n_pf, n_fine, drop, emb_dt, nl_dt, pe_dt = ctx.meta
         b, _, d = dseq.shape

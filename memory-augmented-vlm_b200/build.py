@@ -78,7 +78,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if verbose:
                 print(f"--- {os.path.basename(src)}\n{log}")
     if jobs or force or not os.path.exists(LIB):
-        cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+        # the CUDA runtime is linked as a SHARED library (libcudart.so.12): in a PyTorch process the already-loaded
+        # runtime is reused; stand-alone (C / ctypes hosts) the rpath finds the toolkit's copy.  A static runtime would
+        # embed its whole symbol table (every entry point's name as a string) in the shipped artefact.
+        cudart_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.realpath(nvcc))), "lib64")
+        cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "shared",
+               "-Xlinker", f"-rpath={cudart_dir}"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}{r.stderr}")

@@ -10,7 +10,6 @@ int gemm_bf16_tc(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, 
                  void* C, long long ldc, int M, int N, int K, int act, int out_f32, cudaStream_t st, int half = 0,
                  const float* pe_table = nullptr, const long long* pe_idx = nullptr, int pe_tokens = 0);
 void gemm_tc_force_bn(int bn);
-void gemm_tc_set_debug(int flags);
 int xattn_fp32(const float* Q, long long ldq, long long qb, const float* K, long long ldk, long long kb, const float* V,
                long long ldv, long long vb, float* O, long long ldo, long long ob, float* lse, float* col_scores,
                int batch, int heads, int lq, int lk, int dh, float scale, void* ws, size_t ws_bytes, cudaStream_t st);
@@ -98,10 +97,9 @@ MAVLM_API int mavlm_debug_force_gemm_bn(int bn) {
   return MAVLM_OK;
 }
 
-/* development knob: kernel experiment flags (bit 0: GEMM epilogue skips its global stores, bit 1: skips the
-   activation) -- for bottleneck attribution on the GPU only; results are garbage while a flag is set */
+/* development knob: bit 4 (16) turns programmatic dependent launch off (A/B timing of the launch overlap).  No flag
+   changes what a kernel computes or stores. */
 MAVLM_API int mavlm_debug_set_flags(int flags) {
-  gemm_tc_set_debug(flags);
   pdl_force_off((flags & 16) != 0);
   return MAVLM_OK;
 }

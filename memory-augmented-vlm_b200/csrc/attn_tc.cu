@@ -471,8 +471,13 @@ static AttnGeom attn_geometry(int batch, int heads, int lq, int lk) {
   g.ngq = ceil_div(g.qtiles, 16);
   g.gs = ceil_div(g.qtiles, g.ngq);
   g.units = static_cast<long long>(batch) * heads * g.ngq * ceil_div(lk, ATT_BKV);
-  long long groups = sm_count() / g.gs;
-  if (g_force_groups > 0) groups = g_force_groups;
+  // CO-RESIDENCY: parts of an item cut across groups are merged by spin-waiting on flags raised by other CTAs of the
+  // same grid, so every CTA must be resident at once.  One CTA fits per SM (shared memory), hence groups * gs <= SMs --
+  // also for the debug override.  This holds while the kernel has the GPU's SMs to itself, which is how the library
+  // is used (one stream per device; the wait is bounded and traps instead of hanging if that is ever violated).
+  const long long resident = sm_count() / g.gs;
+  long long groups = resident;
+  if (g_force_groups > 0) groups = g_force_groups < resident ? g_force_groups : resident;
   // an item (one (b,h,q-group), J units) must not be cut into more than MERGE_MAX_PARTS parts
   const long long bh = static_cast<long long>(batch) * heads * g.ngq;
   if (groups > bh * (MERGE_MAX_PARTS - 1)) groups = bh * (MERGE_MAX_PARTS - 1);

@@ -296,11 +296,20 @@ __global__ void __launch_bounds__(256) cast_kernel(const TI* __restrict__ x, TO*
 template <typename T>
 __global__ void __launch_bounds__(128) gather_rows_kernel(T* __restrict__ out, long long ld_out,
                                                           const T* __restrict__ table, const T* __restrict__ feats,
-                                                          const int64_t* __restrict__ src, int dim) {
+                                                          const int64_t* __restrict__ src, int dim,
+                                                          long long n_table_rows, long long n_feat_rows) {
   constexpr int V = Vec<T>::N;
   const long long r = blockIdx.x;
   const int64_t sidx = src[r];
-  const T* sp = sidx >= 0 ? table + sidx * dim : (sidx == -1 ? nullptr : feats + (-(sidx + 2)) * dim);
+  // a source row outside its table is never dereferenced: the row is written as zeros (the host layer validates
+  // the ids before the launch and raises like nn.Embedding would)
+  const T* sp = nullptr;
+  if (sidx >= 0) {
+    if (sidx < n_table_rows) sp = table + sidx * dim;
+  } else if (sidx <= -2) {
+    const long long f = -(sidx + 2);
+    if (f < n_feat_rows) sp = feats + f * dim;
+  }
   T* dst = out + r * ld_out;
   for (int i = threadIdx.x * V; i < dim; i += blockDim.x * V) {
     float v[V];
@@ -411,17 +420,19 @@ int mavlm_add_pe_fwd(const void* x, void* y, const float* pe_table, const int64_
   return MAVLM_OK;
 }
 
-int mavlm_gather_rows_fwd(void* out, int64_t ld_out, const void* embed_table, const void* feats, const int64_t* row_src,
-                          int64_t n_rows, int dim, int dtype, void* stream) {
+int mavlm_gather_rows_fwd(void* out, int64_t ld_out, const void* embed_table, int64_t n_table_rows, const void* feats,
+                          int64_t n_feat_rows, const int64_t* row_src, int64_t n_rows, int dim, int dtype, void* stream) {
   MAVLM_REQUIRE(dtype_ok(dtype), MAVLM_E_INVALID, "gather_rows: bad dtype %d", dtype);
   const int vec = dtype == MAVLM_F32 ? 4 : 8;
   MAVLM_REQUIRE(dim > 0 && dim % vec == 0 && ld_out % vec == 0, MAVLM_E_INVALID,
                 "gather_rows: dim %d / ld_out must be multiples of %d", dim, vec);
+  MAVLM_REQUIRE(n_table_rows >= 0 && n_feat_rows >= 0, MAVLM_E_INVALID, "gather_rows: negative table size");
   if (n_rows == 0) return MAVLM_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MAVLM_DISPATCH_DTYPE(dtype, (gather_rows_kernel<T><<<static_cast<unsigned>(n_rows), 128, 0, st>>>(
                                   static_cast<T*>(out), ld_out, static_cast<const T*>(embed_table),
-                                  static_cast<const T*>(feats), row_src, dim)));
+                                  static_cast<const T*>(feats), row_src, dim, static_cast<long long>(n_table_rows),
+                                  static_cast<long long>(n_feat_rows))));
   MAVLM_LAUNCH_OK();
   return MAVLM_OK;
 }

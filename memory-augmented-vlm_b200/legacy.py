@@ -24,6 +24,7 @@ import torch
 from torch import nn
 
 from . import _lib, ops
+from ._device import on_tensor_device
 from ._lib import ACT_GELU_ERF
 from .autograd import gemm_ex
 from .modules import uniform_segment_variant  # noqa: F401  (segment.py:169-192 lives with the scheduler)
@@ -42,6 +43,7 @@ def _rows(x: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------ segmentation
+@on_tensor_device
 def adjacent_cosine(features: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:
     """torch.cosine_similarity(features[:-1], features[1:], eps=eps) over the flattened rows; fp32 [T - 1] holding
     values rounded through features.dtype."""
@@ -58,6 +60,7 @@ def adjacent_cosine(features: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:
     return sim
 
 
+@on_tensor_device
 def _depth(sim: torch.Tensor, left_only: bool) -> torch.Tensor:
     ops._need_cuda(sim)
     s32 = sim if sim.dtype == torch.float32 else ops.cast(sim.contiguous(), torch.float32)
@@ -78,6 +81,7 @@ def cal_left_depth_score(sim_scores: torch.Tensor) -> torch.Tensor:
     return _depth(sim_scores, True)
 
 
+@on_tensor_device
 def frame_means(features: torch.Tensor) -> torch.Tensor:
     """features.mean(dim=1) for [T, P, D] (segment.py:266, llava_arch.py:528)."""
     ops._need_cuda(features)
@@ -238,6 +242,7 @@ def _replay_steps(mode: int, T: int, T0: int, decisions, coins) -> list:
     return steps
 
 
+@on_tensor_device
 def stream_compress(img_feature: torch.Tensor, video_max_frames: int, mode: int, coins=None, return_steps: bool = True):
     """One launch per streamed frame, decisions on the device (mavlm_stream_compress_fwd).
     Returns (features [T0, P, D], similarities fp32, step_indices or None)."""
@@ -268,6 +273,7 @@ def stream_compress(img_feature: torch.Tensor, video_max_frames: int, mode: int,
     return out, sim, steps
 
 
+@on_tensor_device
 def stream_compress_batched(videos, video_max_frames: int, mode: int, coins=None, return_steps: bool = True):
     """Several independent videos ([T_i, P, D], same P, D, dtype; every T_i > video_max_frames) compressed together:
     one launch per frame index with grid.z = video, so the per-frame latency chain is shared by the batch.
@@ -364,6 +370,7 @@ def k_merge_feature(img_feature: torch.Tensor, video_max_frames: int, img_simila
 
 
 # ------------------------------------------------------------------------------------------------ k-means
+@on_tensor_device
 def _kmeans(X: torch.Tensor, K: int, weights: Optional[torch.Tensor], indices: torch.Tensor, tol: float = 1e-4,
             max_iter: int = 10):
     """Lloyd iterations over whole frames; the host only sees K weight sums + K centroid shifts per iteration."""
@@ -428,6 +435,7 @@ def weighted_kmeans_feature(img_feature: torch.Tensor, video_max_frames: int, we
             [[[j for j in range(T) if lab[j] == i] for i in range(T0)]])
 
 
+@on_tensor_device
 def frame_distances(frames: torch.Tensor, keys: torch.Tensor) -> torch.Tensor:
     """fp32 [T, K] Frobenius distances between whole frames and key frames (memory_builder.py:157)."""
     lib = _lib.load()
@@ -450,6 +458,7 @@ def _pad8(n: int) -> int:
     return (n + 7) // 8 * 8
 
 
+@on_tensor_device
 def _ntm_weight(q: torch.Tensor, k: torch.Tensor, scale: float, ratio: float, mem: Optional[torch.Tensor] = None):
     """w = ratio * softmax(q k^T * scale) as [M, pad8(n)] (zero padding) and, with mem, mem * (1 - rowsum(w))."""
     M, n = q.shape[0], k.shape[0]
@@ -550,6 +559,7 @@ class MultimodalOpsMixin:
         assert D1 == D2, f"dimmension not match, {D1} != {D2}"
         return self.get_model().attention_model.forward(turing_memory, new_feature)
 
+    @on_tensor_device
     def compress_spatial_features(self, image_features, compress_size=1):
         compress_type = getattr(self.config, "compress_type", "mean")
         patch_size = round(math.sqrt(image_features.shape[1]))

@@ -9,7 +9,7 @@ attributes, call signatures and state_dict keys as
 
 so that a reference checkpoint loads unchanged and `patch_llava` can swap them in.  The modules own
 parameters (PyTorch storage) and nothing else: every forward runs through the C ABI in
-libmavlm.so (ops.py).  Forward-only in this round (inference path); hyper-parameters that the
+libmavlm.so (ops.py), and under autograd every backward does too (autograd.py); hyper-parameters that the
 reference hard-codes (chunk 32, cache depth 10, 8 slots x 196 tokens, 8 heads, depth 2, PE table 600)
 are constructor arguments whose defaults equal the reference.
 """
@@ -23,6 +23,7 @@ import torch
 from torch import nn
 
 from . import ops
+from ._device import on_tensor_device
 from ._lib import ACT_GELU_ERF, ACT_NONE, ACT_RELU
 
 _ACTS = {"relu": ACT_RELU, "gelu": ACT_GELU_ERF, "none": ACT_NONE}
@@ -222,7 +223,7 @@ class TransformerProjector(nn.Module):
         self.memory_update_attention = Attention(self.config)
         self.frame_attn_scores: List[torch.Tensor] = []
         self.cache_size = getattr(self.config, "cache_size", 10)
-        self._kv_cache: List[torch.Tensor] = []      # projected (k|v) of each cached state, evolution attention
+        self._kv_cache: list = []      # (state, version, projected k|v) per cached state, evolution attention
 
     # the reference resets state by assigning `memory_cache = []`; keep derived caches in sync
     @property
@@ -258,10 +259,17 @@ class TransformerProjector(nn.Module):
             return current_memory
         att = self.memory_update_attention
         m, p, d = current_memory.shape
-        while len(self._kv_cache) < len(self._memory_cache):
-            s = self._memory_cache[len(self._kv_cache)]
-            self._kv_cache.append(att.project_kv(s.reshape(1, m * p, d)))
-        kv = self._kv_cache[0] if len(self._kv_cache) == 1 else torch.cat(self._kv_cache, dim=1)
+        # entries are (state, its version, projection) matched by IDENTITY against the live list, so a cache the caller
+        # mutated in place (pop / clear / slice assignment / in-place edits of a state) never meets a stale projection
+        old = {id(e[0]): e for e in self._kv_cache}
+        entries = []
+        for s in self._memory_cache:
+            e = old.get(id(s))
+            if e is None or e[0] is not s or e[1] != s._version:
+                e = (s, s._version, att.project_kv(s.reshape(1, m * p, d)))
+            entries.append(e)
+        self._kv_cache = entries
+        kv = entries[0][2] if len(entries) == 1 else torch.cat([e[2] for e in entries], dim=1)
         out, _ = att(current_memory.reshape(1, m * p, d), kv_projected=kv)
         return out.reshape(m, p, d)
 
@@ -282,7 +290,8 @@ class TransformerProjector(nn.Module):
         self._memory_cache.append(final_memory)
         if len(self._memory_cache) > self.cache_size:
             self._memory_cache = self._memory_cache[-self.cache_size:]
-            self._kv_cache = self._kv_cache[-(self.cache_size - 1):] if self.cache_size > 1 else []
+            live = {id(t) for t in self._memory_cache}
+            self._kv_cache = [e for e in self._kv_cache if id(e[0]) in live]
         if want_scores:
             cs = self.layers[last].memory_segment_fusion_attention.last_col_scores
             self.frame_attn_scores.append(cs.view(f, p).mean(dim=1).detach())   # MemoryController.py:135-137
@@ -411,6 +420,7 @@ class MemoryFuser(nn.Module):
         return y[:, :s_len] if s_pad != s_len else y
 
     @staticmethod
+    @on_tensor_device
     def _gemm_attention(qkv: torch.Tensor, b: int, s_pad: int, s_len: int, h: int, dh: int) -> torch.Tensor:
         """softmax(q k^T / sqrt(dh)) v per (row, head) of qkv [b, s_pad, 3 h dh] (bf16): two batched GEMMs (fp32 scores)
         and one row-softmax kernel that masks the pad keys."""

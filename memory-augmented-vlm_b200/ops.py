@@ -11,6 +11,7 @@ import torch
 
 from . import _lib
 from ._lib import ACT_GELU_ERF, ACT_NONE, ACT_RELU, BF16, F16, F32
+from ._device import on_tensor_device
 
 _DTYPES = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 _device_checked = set()
@@ -71,6 +72,7 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     return _linear_raw(x, weight, bias, act=act, resid=resid, addvec=addvec, out=out, out_dtype=out_dtype)
 
 
+@on_tensor_device
 def _linear_raw(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: int = ACT_NONE,
                 resid: Optional[torch.Tensor] = None, addvec: Optional[torch.Tensor] = None,
                 out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
@@ -111,6 +113,7 @@ def _linear_raw(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tens
     return out2.reshape(*lead, n)
 
 
+@on_tensor_device
 def linear_pe(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, pe_table: torch.Tensor,
               frame_idx: torch.Tensor) -> torch.Tensor:
     """x [T, N, K] -> x @ weight.T + bias + pe_table[frame_idx][:, None, :] in one launch (bf16 / fp16 tier):
@@ -135,6 +138,7 @@ def linear_pe(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, pe_tabl
     return out
 
 
+@on_tensor_device
 def cast(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     """x.to(dtype) for fp32 <-> bf16 / fp16 (the hand-off between the tensor-core tier and the fp32 tier)."""
     if x.dtype == dtype:
@@ -157,6 +161,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return _layernorm_raw(x, gamma, beta, eps, out_dtype, out)
 
 
+@on_tensor_device
 def _layernorm_raw(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
                    out_dtype: Optional[torch.dtype] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """`out`: a contiguous tensor with x's element count (e.g. a ring-buffer slot) that receives the result."""
@@ -207,6 +212,7 @@ def xattn_kv(q: torch.Tensor, kv: torch.Tensor, heads: int, *, head_dim: int, sc
     return _xattn_raw(q, kv[..., :hd], kv[..., hd:], heads, head_dim=head_dim, scale=sc)[0]
 
 
+@on_tensor_device
 def _xattn_raw(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *, head_dim: Optional[int] = None,
                scale: Optional[float] = None, want_lse: bool = False,
                want_col_scores: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:
@@ -235,6 +241,7 @@ def _xattn_raw(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *,
     return o, lse, cs
 
 
+@on_tensor_device
 def pool_pe(x: torch.Tensor, *, side: int, stride: int = 2, mode: str = "bilinear",
             pe_table: Optional[torch.Tensor] = None, frame_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
     """[F, side*side, D] -> [F, out*out, D] (+ pe_table[frame_idx] when given)."""
@@ -272,6 +279,7 @@ def add_pe(x: torch.Tensor, pe_table: torch.Tensor, frame_idx: torch.Tensor,
     return _add_pe_raw(x, pe_table, frame_idx, out)
 
 
+@on_tensor_device
 def _add_pe_raw(x: torch.Tensor, pe_table: torch.Tensor, frame_idx: torch.Tensor,
                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _need_cuda(x, pe_table, frame_idx)
@@ -288,6 +296,7 @@ def _add_pe_raw(x: torch.Tensor, pe_table: torch.Tensor, frame_idx: torch.Tensor
     return y
 
 
+@on_tensor_device
 def assemble(seq: torch.Tensor, mem: Optional[torch.Tensor], n_mem_rows: int, frames: torch.Tensor,
              fine_idx: torch.Tensor, tokens: int, type_emb: torch.Tensor, newline: torch.Tensor,
              embed_table: torch.Tensor, prompt_mem_ids: torch.Tensor, prompt_frm_ids: torch.Tensor,
@@ -305,6 +314,7 @@ def assemble(seq: torch.Tensor, mem: Optional[torch.Tensor], n_mem_rows: int, fr
     return seq
 
 
+@on_tensor_device
 def softmax_rows(scores: torch.Tensor, n: int, scale: float, dtype: torch.dtype, ratio: float = 1.0) -> torch.Tensor:
     """w[r, :n] = ratio * softmax(scale * scores[r, :n]) in `dtype`, columns [n, ld) zero-filled so that w can be the
     A operand of a tensor-core GEMM whose K is padded to a multiple of 8.  scores: fp32 [R, ld] (mavlm_ntm_softmax_fwd)."""

@@ -58,6 +58,20 @@ def convert_rmt(ref_rmt: nn.Module) -> TransformerProjector:
     return new
 
 
+def _fused_layout_supported(cfg) -> bool:
+    """The fused pipeline emits ONE layout: bilinear pooling, video tokens flattened with `image_newline` appended to
+    each of {memory, frames} -- what llava_arch.py:571-629 produces for an mm_patch_merge_type that starts with 'spatial'
+    AND contains 'unpad' (e.g. 'spatial_unpad', the OneVision setting) with mm_newline_position 'one_token'.  Every other
+    combination the reference honours ('flat' = no newline at all, :567-568; 'spatial' without 'unpad' = flattened, no
+    newline, :620-629; 'frame' / 'grid' / 'no_token' newline positions, :586-631; average / max pooling, :287-296) has a
+    different sequence length or content, so those go to the reference's own method (which then runs on the patched
+    modules)."""
+    merge = getattr(cfg, "mm_patch_merge_type", "flat")
+    newline = getattr(cfg, "mm_newline_position", "one_token")
+    pool = getattr(cfg, "mm_spatial_pool_mode", "bilinear")
+    return merge.startswith("spatial") and "unpad" in merge and newline == "one_token" and pool == "bilinear"
+
+
 def _fused_prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attention_mask, past_key_values, labels,
                                                 images, modalities=["image"], image_sizes=None):
     """Whole-function replacement of LlavaMetaForCausalLM.prepare_inputs_labels_for_multimodal (llava_arch.py:388-878)
@@ -73,7 +87,8 @@ def _fused_prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, a
     if isinstance(modalities, str):
         modalities = [modalities]
     is_list = type(images) is list
-    if not (is_list or images.ndim == 5) or self.training or any(m != "video" for m in modalities):
+    if (not (is_list or images.ndim == 5) or self.training or any(m != "video" for m in modalities)
+            or not _fused_layout_supported(self.config)):
         return self._mavlm_reference_prepare(input_ids, position_ids, attention_mask, past_key_values, labels, images,
                                              modalities, image_sizes)
     pipe = self.mavlm_pipeline

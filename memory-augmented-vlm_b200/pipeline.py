@@ -78,8 +78,9 @@ class VisualMemoryPipeline(nn.Module):
     def _formation_kv_weights(self):
         """[Wk0;Wv0;Wk1;Wv1;...] so the frame-side K/V of every layer come out of one GEMM."""
         rmt = self.recurrent_memory_transformer
-        packs = [l.memory_segment_fusion_attention.packed() for l in rmt.layers]
-        key = tuple(id(p["wkv"]) for p in packs)
+        atts = [l.memory_segment_fusion_attention for l in rmt.layers]
+        packs = [a.packed() for a in atts]
+        key = tuple(a._pack_key for a in atts)                          # (data_ptr, version, ...) of the source parameters
         c = self._consts.get("fkv")
         if c is None or c[0] != key:
             w = torch.cat([p["wkv"] for p in packs], dim=0).contiguous()
@@ -157,7 +158,7 @@ class VisualMemoryPipeline(nn.Module):
         # (q | k | v columns); q is read by the next chunk, k | v by every later chunk that still caches the state
         ring_qkv = torch.empty((b, cap * lq, 3 * hd), dtype=dtype, device=dev) if n_chunks > 1 else None
         if n_chunks > 1:
-            ekey = (id(evo_p["wq"]), id(evo_p["wkv"]))
+            ekey = evo._pack_key                                        # (data_ptr, version, ...) of the source parameters
             c = self._consts.get("evo_qkv")
             if c is None or c[0] != ekey:
                 self._consts["evo_qkv"] = (ekey, torch.cat([evo_p["wq"], evo_p["wkv"]], dim=0).contiguous(),
@@ -345,31 +346,51 @@ class GraphedPipeline:
 
     def __init__(self, pipe: VisualMemoryPipeline, batch: int, frames: int, *, return_states: bool = False):
         self.pipe = pipe
+        self.return_states = return_states
         p0 = pipe.mm_projector[0].weight
         dev, dtype = p0.device, p0.dtype
+        self.dev = dev
         self.x = torch.zeros((batch, frames, pipe.side * pipe.side, p0.shape[1]), dtype=dtype, device=dev)
         self.idx = torch.zeros((batch, frames), dtype=torch.int64, device=dev)
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):                                   # warm-up: packs weights, fills constant caches
-            for _ in range(2):
-                pipe.forward(self.x, self.idx, validate=False, return_states=return_states)
-        torch.cuda.current_stream(dev).wait_stream(side)
-        torch.cuda.synchronize(dev)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.out = pipe.forward(self.x, self.idx, validate=False, return_states=return_states)
+        self._capture()
+
+    def _weights_key(self):
+        """(data_ptr, version) of everything the captured kernels read: the graph bakes in pointers to packed /
+        padded copies of the weights, so an in-place update (optimizer step, load_state_dict) or a re-allocated
+        parameter after capture must trigger a re-capture instead of replaying stale weights."""
+        pipe = self.pipe
+        ts = [*pipe.parameters(), *pipe.buffers(), pipe.image_newline]
+        return tuple((t.data_ptr(), t._version) for t in ts)
+
+    def _capture(self):
+        pipe, dev = self.pipe, self.dev
+        with torch.cuda.device(dev):                                    # capture on the weights' device, whatever is current
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):                               # warm-up: packs weights, fills constant caches
+                for _ in range(2):
+                    pipe.forward(self.x, self.idx, validate=False, return_states=self.return_states)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = pipe.forward(self.x, self.idx, validate=False, return_states=self.return_states)
+        self._key = self._weights_key()
 
     @torch.no_grad()
     def __call__(self, tower_tokens: Optional[torch.Tensor], frame_idx: Optional[torch.Tensor]):
         """Copy the inputs into the static buffers (skipped when they ARE the static buffers / None) and
-        replay.  The returned tensors are overwritten by the next call."""
-        if frame_idx is not None and frame_idx is not self.idx:
-            self.pipe.positional_encoding.validate(frame_idx)           # host-side, like position_encoding.py:73-76
-            self.idx.copy_(frame_idx.reshape(self.idx.shape), non_blocking=True)
-        if tower_tokens is not None and tower_tokens is not self.x:
-            self.x.copy_(tower_tokens.reshape(self.x.shape), non_blocking=True)
-        self.graph.replay()
+        replay.  The returned tensors are overwritten by the next call (and are NEW tensors after a re-capture,
+        which happens when a weight changed since the capture)."""
+        with torch.cuda.device(self.dev):
+            if self._weights_key() != self._key:
+                self._capture()
+            if frame_idx is not None and frame_idx is not self.idx:
+                self.pipe.positional_encoding.validate(frame_idx)       # host-side, like position_encoding.py:73-76
+                self.idx.copy_(frame_idx.reshape(self.idx.shape), non_blocking=True)
+            if tower_tokens is not None and tower_tokens is not self.x:
+                self.x.copy_(tower_tokens.reshape(self.x.shape), non_blocking=True)
+            self.graph.replay()
         return self.out
 
 
@@ -398,6 +419,10 @@ class HostStreamEncoder:
     def submit(self, host_tokens: torch.Tensor, frame_idx: torch.Tensor, host_out: torch.Tensor) -> None:
         """Enqueue one batch: host_tokens (pinned) -> device -> path -> host_out (pinned).  Asynchronous;
         call synchronize() before reading host_out."""
+        with torch.cuda.device(self.dev):
+            self._submit(host_tokens, frame_idx, host_out)
+
+    def _submit(self, host_tokens: torch.Tensor, frame_idx: torch.Tensor, host_out: torch.Tensor) -> None:
         k = self._k
         g = self.gs[k]
         cur = torch.cuda.current_stream(self.dev)

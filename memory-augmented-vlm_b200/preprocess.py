@@ -18,6 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from ._device import on_tensor_device
 from .ops import _DTYPES, _ptr, _stream
 
 
@@ -51,6 +52,7 @@ def resize_tables(in_size: int, out_size: int, device) -> Tuple[int, torch.Tenso
     return _TABLES[key]
 
 
+@on_tensor_device
 def frames_preprocess(frames: torch.Tensor, size: Tuple[int, int] = (384, 384), rescale_factor: float = 1 / 255,
                       image_mean: Sequence[float] = (0.5, 0.5, 0.5), image_std: Sequence[float] = (0.5, 0.5, 0.5),
                       dtype: torch.dtype = torch.float32, return_resized: bool = False):

@@ -16,11 +16,13 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib, ops
+from ._device import on_tensor_device
 
 IGNORE_INDEX = -100          # llava/constants.py:7
 IMAGE_TOKEN_INDEX = -200     # llava/constants.py:8
 
 
+@on_tensor_device
 @torch.no_grad()
 def splice_text_and_vision(input_ids: torch.Tensor, position_ids: Optional[torch.Tensor],
                            attention_mask: Optional[torch.Tensor], labels: Optional[torch.Tensor],
@@ -32,7 +34,19 @@ def splice_text_and_vision(input_ids: torch.Tensor, position_ids: Optional[torch
     (llava_arch.py:857-867).  image_features: the per-sample vision sequences ([L_i, D], same device / dtype as
     embed_table), consumed in order at each IMAGE_TOKEN_INDEX like the reference's cur_image_idx."""
     dev = embed_table.device
-    d = embed_table.shape[1]
+    if not embed_table.is_cuda:
+        raise RuntimeError("mavlm.splice: embed_table is not on a CUDA device; this path has no CPU fallback")
+    if embed_table.dim() != 2 or not embed_table.is_contiguous():
+        raise RuntimeError("mavlm.splice: embed_table must be a contiguous [vocab, D] tensor")
+    vocab, d = embed_table.shape
+    # the kernel reinterprets both sources with ONE dtype code: features in another dtype (an fp32 projector feeding a
+    # bf16 LLM) are cast here, like the reference's `.to(self.device)` / torch.cat promotion would force the caller to
+    image_features = [f if f.dtype == embed_table.dtype else ops.cast(f.contiguous(), embed_table.dtype)
+                      for f in image_features]
+    for f in image_features:
+        if f.device != dev or f.dim() != 2 or f.shape[1] != d:
+            raise RuntimeError(f"mavlm.splice: image features must be [L, {d}] tensors on {dev}, got {tuple(f.shape)} "
+                               f"on {f.device}")
     ids_cpu = input_ids.detach().cpu()
     _labels, _position_ids, _attention_mask = labels, position_ids, attention_mask
     mask_cpu = (torch.ones_like(ids_cpu, dtype=torch.bool) if attention_mask is None
@@ -88,10 +102,15 @@ def splice_text_and_vision(input_ids: torch.Tensor, position_ids: Optional[torch
         labels_pad[i, sl] = l
         mask_pad[i, sl] = True
         pos_pad[i, sl] = torch.arange(n, dtype=pos_pad.dtype)
+    text = table[table >= 0]
+    if text.numel() and int(text.max()) >= vocab:                                              # nn.Embedding raises here too
+        raise IndexError(f"mavlm.splice: token id {int(text.max())} is out of range for an embedding table of {vocab} rows")
+    if int(table.min()) < -(feat_base[-1] + 1):
+        raise RuntimeError("mavlm.splice: inconsistent row-source table")                      # pragma: no cover
     out = torch.empty((bsz, max_len, d), dtype=embed_table.dtype, device=dev)
     tab_dev = table.to(dev)
-    st = _lib.load().mavlm_gather_rows_fwd(out.data_ptr(), d, embed_table.data_ptr(), feats.data_ptr(),
-                                           tab_dev.data_ptr(), bsz * max_len, d, ops.dtype_code(out),
+    st = _lib.load().mavlm_gather_rows_fwd(out.data_ptr(), d, embed_table.data_ptr(), vocab, feats.data_ptr(),
+                                           feats.shape[0], tab_dev.data_ptr(), bsz * max_len, d, ops.dtype_code(out),
                                            torch.cuda.current_stream().cuda_stream)
     _lib.check(st, "gather_rows_fwd")
     new_labels_out = None if _labels is None else labels_pad.to(dev)                           # :857-860

@@ -516,3 +516,60 @@ def test_fp16_is_inference_only():
     z = torch.randn(1, 4, 196, 64, device=DEV).half()
     with pytest.raises(RuntimeError, match="inference dtype"):
         pipe.memory_forward_train(z)
+
+
+def test_graph_recaptures_after_an_in_place_weight_update():
+    """The captured graph bakes in pointers to packed / padded weight copies: after an in-place parameter update the
+    replay must not serve stale weights (caches keyed on (data_ptr, version))."""
+    pipe, _ = synthetic.build_pipeline(896, 1152, dtype=torch.bfloat16, chunk_size=16, device=DEV)
+    x = synthetic.synthetic_tower_tokens(1, 32, 1152).to(DEV)
+    idx = torch.arange(32)[None]
+    g = pipe.graphed(1, 32)
+    before = g(x, idx)["sequence"].clone()
+    with torch.no_grad():
+        att = pipe.recurrent_memory_transformer.layers[0].memory_segment_fusion_attention
+        att.k_proj.weight.mul_(1.5)                                              # feeds the packed [Wk;Wv] copy
+        pipe.recurrent_memory_transformer.memory_update_attention.q_proj.weight.mul_(0.5)
+        pipe.memory_fuser[2].bias.add_(0.25)
+    after = g(x, idx)["sequence"].clone()
+    eager = pipe(x, idx)["sequence"]
+    assert torch.equal(after, eager) and not torch.equal(after, before)
+
+
+def test_module_cache_mutated_in_place_never_meets_a_stale_projection():
+    """rmt.memory_cache is the live list (MemoryController.py:152-158): a caller that pops / replaces states in place gets
+    the evolution attention over exactly the states in the list."""
+    cfg = M.Config()
+    cfg.mm_hidden_size, cfg.mm_intermediate_size, cfg.depth, cfg.mm_dtype = 64, 256, 2, torch.float32
+    torch.manual_seed(0)
+    rmt = M.TransformerProjector(cfg).to(DEV)
+    x = torch.randn(6, 196, 64, device=DEV)
+    rmt.memory_cache = []
+    for i in range(3):
+        cache, _ = rmt(x[i:i + 1])
+    kept = [cache[0].clone(), cache[2].clone()]
+    del cache[1]                                                                 # in place: the setter is not involved
+    out_a = [t.clone() for t in rmt(x[3:4])[0]]
+    rmt.memory_cache = [t.clone() for t in kept]                                 # the same two states through the setter
+    out_b = rmt(x[3:4])[0]
+    assert len(out_a) == len(out_b) == 3
+    assert torch.equal(out_a[-1], out_b[-1])
+    rmt.memory_cache = []
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_tensors_on_a_non_current_device_run_on_their_own_device():
+    """the C ABI launches on the runtime's current device; operands on cuda:1 while cuda:0 is current must
+    run on cuda:1 (and mixed devices are refused)."""
+    torch.cuda.set_device(0)
+    pipe, w = synthetic.build_pipeline(64, 16, dtype=torch.float32, chunk_size=2, device="cuda:1")
+    x = synthetic.synthetic_tower_tokens(1, 4, 16, dtype=torch.float32)
+    res = pipe(x.to("cuda:1"), torch.arange(4)[None])
+    assert torch.cuda.current_device() == 0 and res["sequence"].device.index == 1
+    wq = synthetic.round_weights_like(w, torch.float32)
+    ref = O.visual_memory_path(x[0].double().numpy(), np.arange(4), wq, pe_table=wq["positional_encoding.frame_embed"],
+                               prompt_mem=wq["embed_tokens.weight"][list(O.MEMORY_PROMPT_IDS)],
+                               prompt_frm=wq["embed_tokens.weight"][list(O.FRAME_PROMPT_IDS)], chunk=2)
+    assert err(res["sequence"][0], ref["sequence"]) < FP32_TOL
+    with pytest.raises(RuntimeError, match="different CUDA devices"):
+        ops.linear(torch.zeros(4, 8, device="cuda:0"), torch.zeros(16, 8, device="cuda:1"))

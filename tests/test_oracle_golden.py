@@ -143,3 +143,64 @@ def test_full_path_against_reference_prepare_inputs(name, raw):
     ref = z["inputs_embeds"][0]
     assert seq.shape == ref.shape
     assert err(seq, ref) < 2e-5
+
+
+# ---- the differentiable torch oracle (oracle/vismem_torch_oracle.py) against the reference's own autograd ----
+def _load_grads(name):
+    z = np.load(os.path.join(GOLDEN, name))
+    w = {k[3:]: z[k] for k in z.files if k.startswith("w::")}
+    g = {k[3:]: z[k] for k in z.files if k.startswith("g::")}
+    return z, w, g
+
+
+def test_torch_oracle_gradients_rmt_bptt():
+    """2 chunks (formation x2 + evolution), loss = sum of mean(state^2): every RMT parameter gradient equals the
+    float64 autograd of the unmodified reference module (tools/gen_golden.py::gen_rmt_grads)."""
+    import torch
+    from oracle import vismem_torch_oracle as T
+    z, w, g = _load_grads("rmt_grads.npz")
+    wt = T.leaf_weights(w, torch.float64)
+    frames = torch.from_numpy(z["frames"])
+    cache = T.rmt_video(frames, wt, chunk=2)
+    loss = sum((s * s).mean() for s in cache)
+    assert abs(float(loss.detach()) - float(z["loss"])) < 1e-12 * abs(float(z["loss"])) + 1e-15
+    loss.backward()
+    gmax = max(np.abs(v).max() for v in g.values())
+    assert len(g) == 44
+    for k, ref in g.items():
+        got = wt[k].grad.numpy()
+        assert np.abs(got - ref).max() <= 1e-9 * max(np.abs(ref).max(), 1e-6 * gmax), k
+
+
+def test_torch_oracle_gradients_whole_path():
+    """loss = mean(sequence^2) through 3 chunks + fuser + type embeddings + newline + prompt rows
+    (tools/gen_golden.py::gen_path_grads); the forward also equals the numpy oracle's."""
+    import torch
+    from oracle import vismem_torch_oracle as T
+    z, w, g = _load_grads("path_grads.npz")
+    rows = z["embed_rows"].tolist()
+    tab = {r: w["embed_rows"][i] for i, r in enumerate(rows)}
+    pm = np.stack([tab[i] for i in T.MEMORY_PROMPT_IDS])
+    pf = np.stack([tab[i] for i in T.FRAME_PROMPT_IDS])
+    wn = {k: v for k, v in w.items() if k != "embed_rows"}
+    loss, grads, seqs = T.path_gradients(z["z"][None], wn, chunk=2, dtype=torch.float64, prompt_rows=(pm, pf))
+    assert abs(loss - float(z["loss"])) < 1e-12 * abs(float(z["loss"]))
+    assert err(seqs[0], z["sequence"]) < 1e-12
+    gmax = max(np.abs(v).max() for v in g.values())
+    for k, ref in g.items():
+        if k == "embed_rows":
+            continue
+        assert np.abs(grads[k] - ref).max() <= 1e-9 * max(np.abs(ref).max(), 1e-6 * gmax), k
+    # prompt-row gradients: a token id that occurs in both prompts (279, 2766, 25) accumulates both
+    acc = {r: np.zeros_like(pm[0]) for r in rows}
+    for i, r in enumerate(T.MEMORY_PROMPT_IDS):
+        acc[r] += grads["embed.prompt_mem"][i]
+    for i, r in enumerate(T.FRAME_PROMPT_IDS):
+        acc[r] += grads["embed.prompt_frm"][i]
+    got = np.stack([acc[r] for r in rows])
+    assert np.abs(got - g["embed_rows"]).max() <= 1e-9 * np.abs(g["embed_rows"]).max()
+    # numpy oracle forward on the same inputs
+    fused_seq = O.assemble_sequence(
+        O.memory_fuser_mlp(np.concatenate(O.rmt_video(z["z"], wn, chunk=2)[0], axis=0), wn),
+        z["z"][O.fine_frame_indices(6)], wn, prompt_mem=pm, prompt_frm=pf)
+    assert err(seqs[0], fused_seq) < 1e-12

@@ -200,7 +200,8 @@ def test_fused_prepare_inputs_matches_the_reference_function(name):
             super().__init__()
             self.model = Inner()
             self.config = types.SimpleNamespace(mm_spatial_pool_mode="bilinear", tokenizer_model_max_length=32768,
-                                                tokenizer_padding_side="right")
+                                                tokenizer_padding_side="right", mm_patch_merge_type="spatial_unpad",
+                                                mm_newline_position="one_token")    # the golden harness's setting
 
         def get_model(self):
             return self.model
@@ -233,3 +234,61 @@ def test_fused_prepare_inputs_matches_the_reference_function(name):
     same = m.prepare_inputs_labels_for_multimodal(ids[:, :1], None, None, "kv", None, [video], modalities=["video"])
     assert same[0] is ids[:, :1] or torch.equal(same[0], ids[:, :1])
     assert same[3] == "kv" and same[4] is None
+
+
+def test_fused_prepare_routes_other_layouts_to_the_reference_method():
+    """The fused whole-function replacement only emits the spatial_unpad + one_token + bilinear layout; 'flat' (the
+    reference's DEFAULT merge type: no newline, llava_arch.py:562-568), 'spatial' without 'unpad', the other newline
+    positions and average / max pooling must reach the reference's own method instead of silently producing a
+    sequence of different length.  CPU: the dispatch happens before any kernel call."""
+    d = 16
+
+    class Tower(nn.Module):
+        num_patches_per_side = 27
+
+        def forward(self, images):
+            return images.flatten(2).transpose(1, 2)
+
+    class Inner(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.vision_tower = Tower()
+            self.mm_projector = nn.Sequential(nn.Linear(4, d), nn.GELU(), nn.Linear(d, d))
+            self.recurrent_memory_transformer = _RefLikeRMT(d)
+            self.memory_fuser = nn.Sequential(nn.Linear(d, 4 * d), nn.GELU(), nn.Linear(4 * d, d))
+            self.positional_encoding = M.TemporalPositionalEncoding(600, d, learnable=False)
+            self.token_type_embedding = nn.Embedding(2, d)
+            self.image_newline = nn.Parameter(torch.zeros(d))
+            self.embed_tokens = nn.Embedding(100, d)
+
+    class Model(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.model = Inner()
+            self.config = types.SimpleNamespace(mm_spatial_pool_mode="bilinear")
+
+        def get_model(self):
+            return self.model
+
+        def get_vision_tower(self):
+            return self.model.vision_tower
+
+        def prepare_inputs_labels_for_multimodal(self, *a, **k):          # stands in for llava_arch.py:388
+            return "reference"
+
+    m = Model().eval()
+    M.patch_llava(m, fused=True)
+    ids = torch.tensor([[1, -200, 2]])
+    video = torch.zeros(4, 4, 27, 27)
+    call = lambda: m.prepare_inputs_labels_for_multimodal(ids, None, None, None, None, [video], modalities=["video"])
+    assert call() == "reference"                                          # mm_patch_merge_type defaults to 'flat'
+    for merge, newline, pool in (("flat", "one_token", "bilinear"), ("spatial", "one_token", "bilinear"),
+                                 ("spatial_unpad", "frame", "bilinear"), ("spatial_unpad", "grid", "bilinear"),
+                                 ("spatial_unpad", "no_token", "bilinear"), ("spatial_unpad", "one_token", "average"),
+                                 ("spatial_unpad", "one_token", "max")):
+        m.config = types.SimpleNamespace(mm_spatial_pool_mode=pool, mm_patch_merge_type=merge, mm_newline_position=newline)
+        assert call() == "reference", (merge, newline, pool)
+    m.config = types.SimpleNamespace(mm_spatial_pool_mode="bilinear", mm_patch_merge_type="spatial_unpad",
+                                     mm_newline_position="one_token")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):              # the fused path is taken (and needs the GPU)
+        call()

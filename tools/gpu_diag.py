@@ -403,30 +403,6 @@ def fam_micro():
         print(f"gemm {m}x{n}x{k}: {us:.1f} us {2 * m * n * k / us / 1e6:.0f} TF")
     from mavlm_b200 import _lib
     lib = _lib.load()
-    a = torch.randn(46656, 1152, device=dev).bfloat16()
-    w = torch.randn(3584, 1152, device=dev).bfloat16() / 34
-    b = torch.randn(3584, device=dev).bfloat16()
-    out = torch.empty(46656, 3584, device=dev, dtype=torch.bfloat16)
-    for bn in (1256, 256):
-        lib.mavlm_debug_force_gemm_bn(bn)
-        for flags, name in ((0, "full"), (2, "no GELU"), (1, "no stores"), (3, "no GELU, no stores")):
-            lib.mavlm_debug_set_flags(flags)
-            us = graph_time(lambda: ops.linear(a, w, b, act=1, out=out), n=4, reps=3)
-            print(f"projector L1 46656x3584x1152 GELU tile {bn} [{name}]: {us:.1f} us {2 * 46656 * 3584 * 1152 / us / 1e6:.0f} TF")
-    lib.mavlm_debug_set_flags(0)
-    lib.mavlm_debug_force_gemm_bn(0)
-    for (m, n, k) in ((12544, 14336, 3584), (12544, 3584, 3584), (3136, 3584, 14336), (46656, 3584, 1152)):
-        a = torch.randn(m, k, device=dev).bfloat16()
-        w = torch.randn(n, k, device=dev).bfloat16()
-        b = torch.randn(n, device=dev).bfloat16()
-        out = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
-        line = f"gemm {m}x{n}x{k} raster group (pair tiles of 256 rows):"
-        for g in (0, 2, 4, 8, 16, 32, 64):
-            lib.mavlm_debug_set_flags(g << 8)
-            us = graph_time(lambda: ops.linear(a, w, b, out=out), n=4, reps=3)
-            line += f"  g{g}: {us:.0f}us"
-        lib.mavlm_debug_set_flags(0)
-        print(line, flush=True)
     h, dh = 8, 448
     for (bsz, lq, lk) in ((1, 1568, 6272), (1, 1568, 1568), (8, 1568, 6272), (1, 1568, 15680)):
         q = torch.randn(bsz, lq, h * dh, device=dev).bfloat16()
