@@ -131,17 +131,114 @@ def encode_videos_sharded(pipe, tower_tokens: torch.Tensor, frame_idx: torch.Ten
     return all_gather_rows(res, counts)
 
 
+def piece_schedule(n_frames: int, chunk: int, world: int):
+    """Ownership of the frame-sharded pre-pass of ONE long video.  The video is cut into pieces of `world` chunks
+    (`world * chunk` frames); inside piece j, rank r owns chunk j * world + r, i.e. frames
+    [(j * world + r) * chunk, ... + chunk) clipped to the video.  So every all-gather collects ONE chunk from every
+    rank -- piece j is complete after gather j, and the recurrence (sequential in time) can start on piece 0 while the
+    later pieces are still being projected and gathered.  A contiguous split (rank r owns frames r*F/W ...) would make
+    chunk 0 a broadcast from rank 0 and leave nothing to overlap.
+    Returns (piece_frames, [[(start, stop) for rank in range(world)] for piece in range(n_pieces)])."""
+    piece = world * chunk
+    n_pieces = -(-n_frames // piece)
+    sched = []
+    for j in range(n_pieces):
+        row = []
+        for r in range(world):
+            s0 = min(n_frames, (j * world + r) * chunk)
+            row.append((s0, min(n_frames, s0 + chunk)))
+        sched.append(row)
+    return piece, sched
+
+
+def gather_piece(piece_buf: torch.Tensor, slot: torch.Tensor) -> None:
+    """All-gather one piece IN PLACE: `slot` is this rank's block of `piece_buf` ([world * n, ...]).  NCCL: one
+    ncclAllGather whose send buffer is the receive buffer's rank-th block; gloo (CPU tests): list form."""
+    if dist.get_backend() == "nccl":
+        dist.all_gather_into_tensor(piece_buf, slot)
+    else:
+        parts = list(piece_buf.chunk(dist.get_world_size(), dim=0))
+        dist.all_gather(parts, slot.clone())
+
+
+class FrameShardedEncoder:
+    """One long video [F, 729, Dv] on `world` GPUs: every rank projects + pools + PEs the chunks it owns
+    (piece_schedule), the W2 GEMM's epilogue writes them straight into this rank's slot of the gather buffer, the pooled
+    tokens (1.4 MB per OV-7B frame) are all-gathered piece by piece with NCCL on a SIDE stream, and every rank runs the
+    replicated recurrence, whose first pieces overlap the projection / gather of the later ones.  The recurrence does
+    not shard (state t needs state t-1)."""
+
+    def __init__(self, pipe, n_frames: int):
+        self.pipe = pipe
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.n_frames = n_frames
+        self.piece, self.sched = piece_schedule(n_frames, pipe.chunk_size, self.world)
+        p0 = pipe.mm_projector[0].weight
+        self.dev = p0.device
+        rmt = pipe.recurrent_memory_transformer
+        n_pad = len(self.sched) * self.piece                          # whole pieces: equal-sized gathers
+        self.z = torch.zeros((n_pad, rmt.patch_size, rmt.hidden_size), dtype=p0.dtype, device=self.dev)
+        self.comm = torch.cuda.Stream(device=self.dev) if self.dev.type == "cuda" else None
+        self.gather_events = []
+        self.gathered_bytes = 0
+
+    @torch.no_grad()
+    def __call__(self, tower_tokens: torch.Tensor, frame_idx: torch.Tensor, *, overlap: bool = True, comm: bool = True,
+                 return_states: bool = False, time_gathers: bool = False):
+        """tower_tokens [F, 729, Dv] (device; only this rank's chunks are read), frame_idx [F] (host or device).
+        overlap=False: every gather is waited for before the recurrence starts (the blocking baseline);
+        comm=False: the gathers are skipped (the buffer keeps the previous call's data): times the compute alone."""
+        pipe, chunk, r, w = self.pipe, self.pipe.chunk_size, self.rank, self.world
+        pipe.positional_encoding.validate(frame_idx)
+        frame_idx = frame_idx.to(self.dev)
+        cur = torch.cuda.current_stream(self.dev)
+        done_pre, done_gather = [], []
+        self.gather_events = []
+        self.gathered_bytes = 0
+        for j, row in enumerate(self.sched):
+            s0, s1 = row[r]
+            slot = self.z[j * self.piece + r * chunk: j * self.piece + (r + 1) * chunk]
+            if s1 > s0:
+                pipe.encode_frames(tower_tokens[s0:s1], frame_idx[s0:s1], validate=False, out=slot[: s1 - s0])
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            done_pre.append(ev)
+            if w > 1 and comm:
+                with torch.cuda.stream(self.comm):
+                    self.comm.wait_event(ev)
+                    piece_buf = self.z[j * self.piece:(j + 1) * self.piece]
+                    if time_gathers:
+                        t0 = torch.cuda.Event(enable_timing=True)
+                        t0.record(self.comm)
+                    gather_piece(piece_buf, slot)                      # in place: slot IS piece_buf's rank-th block
+                    ge = torch.cuda.Event(enable_timing=time_gathers)
+                    ge.record(self.comm)
+                    if time_gathers:
+                        self.gather_events.append((t0, ge))
+                    done_gather.append(ge)
+                    self.gathered_bytes += (w - 1) * slot.numel() * slot.element_size()
+        if w > 1 and comm and not overlap:
+            for ge in done_gather:
+                cur.wait_event(ge)
+            done_gather = []
+
+        def before_piece(j):
+            if j < len(done_gather):
+                cur.wait_event(done_gather[j])
+
+        z = self.z[: self.n_frames][None]
+        return pipe.memory_forward(z, piece_frames=self.piece, before_piece=before_piece, return_states=return_states)
+
+    def gather_ms(self) -> float:
+        """Sum of the gathers' durations on the comm stream (after a synchronised call with time_gathers=True)."""
+        return float(sum(a.elapsed_time(b) for a, b in self.gather_events))
+
+
 @torch.no_grad()
-def encode_long_video_frame_sharded(pipe, tower_tokens: torch.Tensor, frame_idx: torch.Tensor):
-    """One long video [F, 729, Dv]: each rank projects + pools + PEs F/world frames, the pooled tokens
-    are all-gathered (1.4 MB per 7B frame), then every rank runs the (replicated) recurrence."""
-    world = dist.get_world_size() if dist.is_initialized() else 1
-    rank = dist.get_rank() if dist.is_initialized() else 0
-    f = tower_tokens.shape[0]
-    mine = shard_range(f, rank, world)
+def encode_long_video_frame_sharded(pipe, tower_tokens: torch.Tensor, frame_idx: torch.Tensor, **kw):
+    """One long video [F, 729, Dv]: frame-sharded pre-pass + piece-wise all-gather overlapped with the replicated
+    recurrence (FrameShardedEncoder).  Single process: the plain path."""
     dev = next(pipe.parameters()).device
-    z_local = pipe.encode_frames(tower_tokens[mine.start:mine.stop].to(dev, non_blocking=True),
-                                 frame_idx[mine.start:mine.stop])
-    counts = [len(shard_range(f, r, world)) for r in range(world)]
-    z = all_gather_rows(z_local, counts)
-    return pipe.memory_forward(z[None])
+    enc = FrameShardedEncoder(pipe, tower_tokens.shape[0])
+    return enc(tower_tokens.to(dev, non_blocking=True), frame_idx, **kw)

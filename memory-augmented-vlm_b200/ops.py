@@ -115,14 +115,17 @@ def _linear_raw(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tens
 
 @on_tensor_device
 def linear_pe(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, pe_table: torch.Tensor,
-              frame_idx: torch.Tensor) -> torch.Tensor:
+              frame_idx: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x [T, N, K] -> x @ weight.T + bias + pe_table[frame_idx][:, None, :] in one launch (bf16 / fp16 tier):
-    the projector's second layer with the temporal PE added in the GEMM epilogue."""
-    _need_cuda(x, weight, bias, pe_table, frame_idx)
+    the projector's second layer with the temporal PE added in the GEMM epilogue.  `out`: a contiguous [T, N, C]
+    destination (e.g. this rank's slot of an all-gather buffer: no staging copy before the collective)."""
+    _need_cuda(x, weight, bias, pe_table, frame_idx, out)
     t, n_tok, k = x.shape
     n = weight.shape[0]
+    if out is not None and (tuple(out.shape) != (t, n_tok, n) or not out.is_contiguous() or out.dtype != x.dtype):
+        raise RuntimeError("mavlm.linear_pe: out must be a contiguous [T, N, C] tensor of the input dtype")
     if x.dtype == torch.float32:
-        return add_pe(linear(x, weight, bias), pe_table, frame_idx)
+        return add_pe(linear(x, weight, bias), pe_table, frame_idx, out=out)
     x2 = x.reshape(t * n_tok, k)
     if x2.stride(1) != 1 or not x2.is_contiguous():
         x2 = x2.contiguous()
@@ -130,7 +133,8 @@ def linear_pe(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, pe_tabl
     if pe_table.dtype != torch.float32 or not pe_table.is_contiguous() or pe_table.shape[1] != n:
         raise RuntimeError("mavlm.linear_pe: pe_table must be contiguous fp32 [max_frames, N]")
     frame_idx = frame_idx.to(device=x.device, dtype=torch.int64).contiguous()
-    out = torch.empty((t, n_tok, n), dtype=x.dtype, device=x.device)
+    if out is None:
+        out = torch.empty((t, n_tok, n), dtype=x.dtype, device=x.device)
     st = _lib.load().mavlm_gemm_bias_pe_fwd(_ptr(x2), x2.stride(0), _ptr(weight), weight.stride(0), _ptr(bias),
                                             _ptr(pe_table), _ptr(frame_idx), n_tok, _ptr(out), n, t * n_tok, n, k,
                                             dtype_code(x), _stream())

@@ -90,14 +90,16 @@ class VisualMemoryPipeline(nn.Module):
 
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def encode_frames(self, tower_tokens: torch.Tensor, frame_idx: torch.Tensor, *, validate: bool = True) -> torch.Tensor:
+    def encode_frames(self, tower_tokens: torch.Tensor, frame_idx: torch.Tensor, *, validate: bool = True,
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """[N, side*side, Dv] tower tokens (+ original frame indices [N]) -> pooled + PE'd [N, P, D]
         (encode_images -> get_2dPool -> positional_encoding, llava_arch.py:481-511).
 
         Bilinear pooling is a fixed convex combination of tokens, so it commutes with the projector's
         second (affine) layer: pool(h W2^T + b2) = pool(h) W2^T + b2 (tap weights sum to 1; verified to
         5e-16 in fp64).  With `pool_before_w2` (default) the second GEMM runs on 196 instead
-        of 729 rows per frame (3.7x fewer); `pool_before_w2=False` keeps the reference's operation order."""
+        of 729 rows per frame (3.7x fewer); `pool_before_w2=False` keeps the reference's operation order.
+        `out` [N, P, D]: destination (e.g. this rank's slot of an all-gather buffer, written by the last kernel)."""
         pe = self.positional_encoding
         if validate:
             pe.validate(frame_idx)
@@ -112,19 +114,31 @@ class VisualMemoryPipeline(nn.Module):
             if self.pool_before_w2 and self.pool_mode == "bilinear":
                 h = ops.linear(x, mp[0].weight, mp[0].bias, act=ACT_GELU_ERF)
                 hp = ops.pool_pe(h, side=self.side, stride=self.pool_stride, mode="bilinear")
-                outs.append(ops.linear_pe(hp, mp[2].weight, mp[2].bias, table, frame_idx[i:i + step]))
+                outs.append(ops.linear_pe(hp, mp[2].weight, mp[2].bias, table, frame_idx[i:i + step],
+                                          out=None if out is None else out[i:i + step]))
             else:
                 y = mp(x)
-                outs.append(ops.pool_pe(y, side=self.side, stride=self.pool_stride, mode=self.pool_mode,
-                                        pe_table=table, frame_idx=frame_idx[i:i + step]))
+                res = ops.pool_pe(y, side=self.side, stride=self.pool_stride, mode=self.pool_mode,
+                                  pe_table=table, frame_idx=frame_idx[i:i + step])
+                if out is not None:
+                    out[i:i + step].copy_(res)
+                outs.append(res)
+        if out is not None:
+            return out
         return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
 
     @torch.no_grad()
     def memory_forward(self, z: torch.Tensor, *, seq_out: Optional[torch.Tensor] = None, drop_frames: bool = False,
-                       return_states: bool = True, boundaries: Optional[Sequence[int]] = None) -> Dict[str, torch.Tensor]:
+                       return_states: bool = True, boundaries: Optional[Sequence[int]] = None,
+                       piece_frames: Optional[int] = None, before_piece=None) -> Dict[str, torch.Tensor]:
         """z: pooled + PE'd frames [B, F, P, D].  Runs the recurrence, the fuser and the assembly.
         `boundaries`: chunk boundaries [0, ..., F] replacing the uniform scheduler of llava_arch.py:528-534, e.g. the
-        scene-based ones of `legacy.adjusted_segment(legacy.frame_means(z[0]))` (segment.py:52-128)."""
+        scene-based ones of `legacy.adjusted_segment(legacy.frame_means(z[0]))` (segment.py:52-128).
+        `piece_frames` / `before_piece`: the frames arrive in pieces of `piece_frames` frames (a multiple of the chunk
+        size; the frame-sharded pre-pass of dist.py all-gathers them piece by piece on a side stream): the frame-side
+        K/V projection is then issued per piece, right before the piece's first chunk and after `before_piece(j)`
+        (which makes the current stream wait for piece j), so the recurrence over piece j overlaps the arrival of
+        piece j + 1.  Same arithmetic as the single projection GEMM (rows are independent)."""
         rmt = self.recurrent_memory_transformer
         b, f, p, d = z.shape
         dtype, dev = z.dtype, z.device
@@ -140,7 +154,12 @@ class VisualMemoryPipeline(nn.Module):
         dhp = packs[0]["dhp"]
         hd = heads * dhp
         wf, bf = self._formation_kv_weights()
-        kvf = ops.linear(z2, wf, bf)                                    # [B, F*P, depth*2*hd]
+        if piece_frames is None:
+            kvf = ops.linear(z2, wf, bf)                                # [B, F*P, depth*2*hd]
+        else:
+            if b != 1 or boundaries is not None or piece_frames % self.chunk_size != 0:
+                raise ValueError("mavlm: piece-wise arrival needs one video, the uniform scheduler and pieces of whole chunks")
+            kvf = torch.empty((b, f * p, wf.shape[0]), dtype=dtype, device=dev)
 
         if boundaries is None:
             bounds = uniform_segment_variant(f, self.chunk_size)
@@ -178,6 +197,12 @@ class VisualMemoryPipeline(nn.Module):
                 ctx, _, _ = ops.xattn(q, kv[..., hd:2 * hd], kv[..., 2 * hd:], heads, head_dim=dhp, scale=scale)
                 mem = evo.residual(ctx, mem, weight=evo_p["wo"])
             r0, r1 = bounds[t] * p, bounds[t + 1] * p
+            if piece_frames is not None and bounds[t] % piece_frames == 0:   # first chunk of a piece: its frames' K/V
+                j = bounds[t] // piece_frames
+                if before_piece is not None:
+                    before_piece(j)
+                e0, e1 = bounds[t] * p, min(f, bounds[t] + piece_frames) * p
+                ops.linear(z2[0, e0:e1], wf, bf, out=kvf[0, e0:e1])
             for li, layer in enumerate(rmt.layers):
                 pk = packs[li]
                 att = layer.memory_segment_fusion_attention

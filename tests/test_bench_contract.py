@@ -54,15 +54,62 @@ def test_gpu_arm_line_has_every_contract_key():
     lines = [l for l in out.split("\n") if l.strip()]
     assert len(lines) == 1, out[:2000]
     j = json.loads(lines[0])
-    need = (REQUIRED - {"impl"}) | {"clocks", "gpu_launches", "roofline"}
+    need = (REQUIRED - {"impl"}) | {"clocks", "gpu_launches", "roofline", "roofline_kernels", "sustained", "config3"}
     assert need <= set(j), need - set(j)
     assert j["n_gpus"] == 1 and j["steps"] == 5 and j["warmup"] == 3 and j["dtype"] == "bf16" and j["scaling"] == "weak"
     assert j["value"] > 1000 and abs(j["value"] - 64 * 1e3 / j["ms_per_step"]) < 1e-6 * j["value"]
     r = j["roofline"]
     assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert r["traffic"] is None or r["traffic"] > 0
+    assert min(abs(r["peak"] - r["achieved"] / r["frac_of_burst"]),
+               abs(r["peak"] - r["achieved"] / r["frac_of_sustained"])) < 1e-6 * r["peak"]   # burst or sustained, stated
+    fams = {k["kernel"].split(" ")[0].split("<")[0]: k for k in j["roofline_kernels"]}
+    assert {"gemm_tc_kernel", "attn_tc_kernel", "layernorm_kernel", "pool_pe_kernel", "assemble_kernel"} <= set(fams)
+    for k in j["roofline_kernels"]:
+        assert k["bound"] in ("tensor", "hbm") and abs(k["frac"] - k["achieved"] / k["peak"]) < 1e-9 and k["ms_per_step"] > 0
+    assert 0.9 < sum(k["share_of_step"] for k in j["roofline_kernels"]) < 1.05
+    s_ = j["sustained"]
+    assert s_["seconds"] >= 5.0 and s_["value"] > 1000 and set(s_["clocks"]) >= {"sm_mhz", "reasons"}
+    c3 = j["config3"]
+    assert c3["scaling"] == "strong" and c3["videos_per_rank"] == 8 and c3["value"] > 1000
+    assert j["e2e"]["copy_only"]["ms_per_step"] > 0 and isinstance(j["e2e"]["bound"], str)
     e = j["e2e"]
     assert e["value"] > 1000 and e["h2d_bytes_per_step"] == 64 * 729 * 1152 * 2 and e["d2h_bytes_per_step"] > 0
     c = j["cpu_baseline"]
-    assert c["kind"] == "port" and c["value"] > 0 and c["cores"] >= 1 and c["sample"]
+    have_ref = os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "llava", "model", "llava_arch.py"))
+    assert c["kind"] == ("reference" if have_ref else "port") and c["value"] > 0 and c["cores"] >= 1 and c["sample"]
+    assert c["gpu_vs_cpu_sequence_err"] < 3e-2
     assert j["gpu_launches"] > 0 and set(j["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+
+
+def test_reference_cpu_runs_the_unmodified_reference_modules_and_agrees_with_the_oracle():
+    """The CPU arm of bench.py (ReferenceCpu) at small dims: when the reference install (baseline/_ref, written by
+    __graft_entry__.build()) or /root/reference is present it drives the UNMODIFIED modules (kind "reference") and its
+    visual token sequence equals the numpy oracle's on the same weights; otherwise it says "port"."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, ROOT)
+    import bench
+    from baseline import ref_arm
+    from mavlm_b200 import synthetic
+    from oracle import vismem_oracle as O
+    old = bench.HIDDEN, bench.VISION, bench.CHUNK
+    bench.HIDDEN, bench.VISION, bench.CHUNK = 64, 16, 32
+    try:
+        _, w = synthetic.build_pipeline(64, 16, dtype=torch.float32, device="cpu", vocab=50000)
+        w32 = {k: v.astype(np.float32) for k, v in w.items()}
+        x = synthetic.synthetic_tower_tokens(1, 40, 16, dtype=torch.float32)[0]
+        ref = bench.ReferenceCpu(w32, x)
+        have = ref_arm.find_reference_root() is not None
+        assert ref.kind == ("reference" if have else "port") and ref.cores >= 1
+        dt, seq = ref.run(40)                                  # 40 raw frames -> 64 sampled (llava_arch.py:437-451)
+        assert dt > 0
+        idx = O.sample_frame_indices(40)
+        want = O.visual_memory_path(x.numpy()[idx] if have else x.numpy(), idx if have else np.arange(40), w32,
+                                    pe_table=w32["positional_encoding.frame_embed"],
+                                    prompt_mem=w32["embed_tokens.weight"][list(O.MEMORY_PROMPT_IDS)],
+                                    prompt_frm=w32["embed_tokens.weight"][list(O.FRAME_PROMPT_IDS)], chunk=32)["sequence"]
+        assert seq.shape == want.shape and O.normalized_max_error(seq, want) < 2e-5
+        assert ("UNMODIFIED reference" in ref.describe(40)) == have
+    finally:
+        bench.HIDDEN, bench.VISION, bench.CHUNK = old

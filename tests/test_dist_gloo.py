@@ -46,7 +46,18 @@ def _worker(rank, world, port, q):
         gathered = [None, None]
         dist.all_gather_object(gathered, draws)
         ok5 = gathered[0] == gathered[1] and any(draws) and not all(draws)
-        q.put((rank, ok1 and ok2 and ok3 and ok4 and ok5))
+        # frame-sharded pre-pass of one long video: pieces of `world` chunks, one chunk per rank per piece, gathered in
+        # place piece by piece; the buffer ends up in frame order on every rank (ragged tail: 70 frames, chunk 16)
+        n_frames, chunk = 70, 16
+        piece, sched = D.piece_schedule(n_frames, chunk, world)
+        z = torch.full((len(sched) * piece, 3), -1.0)
+        for j, row in enumerate(sched):
+            s0, s1 = row[rank]
+            slot = z[j * piece + rank * chunk: j * piece + (rank + 1) * chunk]
+            slot[: s1 - s0] = torch.arange(s0, s1, dtype=torch.float32)[:, None]
+            D.gather_piece(z[j * piece:(j + 1) * piece], slot)
+        ok6 = torch.equal(z[:n_frames, 0], torch.arange(n_frames, dtype=torch.float32)) and piece == world * chunk
+        q.put((rank, ok1 and ok2 and ok3 and ok4 and ok5 and ok6))
     finally:
         dist.destroy_process_group()
 
@@ -59,6 +70,20 @@ def test_shard_range_is_a_partition():
             assert got == list(range(n))
             sizes = [len(D.shard_range(n, r, world)) for r in range(world)]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_piece_schedule_partitions_the_frames_chunk_by_chunk():
+    from mavlm_b200 import dist as D
+    for n in (1, 31, 32, 70, 256, 1024, 1000):
+        for chunk in (8, 16, 32):
+            for world in (1, 2, 4, 8):
+                piece, sched = D.piece_schedule(n, chunk, world)
+                assert piece == world * chunk and len(sched) == -(-n // piece)
+                got = [i for row in sched for (a, b) in row for i in range(a, b)]
+                assert got == list(range(n))                            # piece-major, rank-minor = time order
+                for j, row in enumerate(sched):
+                    for r, (a, b) in enumerate(row):
+                        assert b - a <= chunk and (a == b or a == (j * world + r) * chunk)
 
 
 @pytest.mark.timeout(120)

@@ -50,3 +50,13 @@ def test_splice_none_rules_and_text_only_and_batch_padding():
     assert torch.equal(emb[1, :2], table[torch.tensor([6, 7], device=DEV)]) and emb[1, 2:].abs().sum() == 0
     pos, m2, emb, lab = M.splice_text_and_vision(ids, None, mask, None, [feats], table, padding_side="left")
     assert emb[1, :8].abs().sum() == 0 and torch.equal(emb[1, 8], table[6])
+    # features in another dtype are cast (never reinterpreted bytewise); out-of-range ids raise like nn.Embedding
+    _, _, emb32, _ = M.splice_text_and_vision(ids, None, mask, None, [feats.float()], table)
+    assert torch.equal(emb32, M.splice_text_and_vision(ids, None, mask, None, [feats], table)[2])
+    bad = torch.tensor([[3, M.IMAGE_TOKEN_INDEX, 100, 5]], device=DEV)
+    with pytest.raises(IndexError):
+        M.splice_text_and_vision(bad, None, None, None, [feats], table)
+    with pytest.raises(RuntimeError):
+        M.splice_text_and_vision(ids, None, mask, None, [feats[:, :16]], table)                    # wrong width
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        M.splice_text_and_vision(ids.cpu(), None, mask.cpu(), None, [feats.cpu()], table.cpu())
