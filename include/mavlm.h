@@ -82,6 +82,31 @@ MAVLM_API int mavlm_gemm_bias_act_fwd(const void* A, int64_t lda, const void* W,
                             int64_t ldr, const void* addvec, void* C, int64_t ldc, int M, int N, int K, int act,
                             int dtype, int out_dtype, void* stream);
 
+/* ---- co-scheduled nn.Linear calls ("tail fill").  The recurrence (MemoryController.py:118-158) is a serial chain of
+ * GEMMs with 1568 rows, each of which leaves a third of the tile slots of its last wave empty, while other nn.Linear
+ * calls of the same step wait for nothing on that chain: the frame-side k_proj / v_proj of LATER chunks
+ * (MemoryController.py:49-50) and the memory_fuser of FINISHED states (llava_arch.py:545-546).  mavlm_gemm_fill_fwd
+ * runs one critical-path nn.Linear (`primary`, whole) and, in the SM time its last wave leaves idle, tiles
+ * [fill_begin, ...) of a second one (`filler`); mavlm_gemm_tiles_fwd runs a tile range of one problem on its own (the
+ * rest of a filler before its first consumer).  Tiles are 256 x 256 outputs in a fixed rasterised order
+ * (mavlm_gemm_num_tiles of them); results are bit-identical to mavlm_gemm_bias_act_fwd with the same tile.
+ * bf16 / fp16 tier only.  Same epilogue semantics as mavlm_gemm_bias_act_fwd / mavlm_gemm_bias_pe_fwd. */
+typedef struct mavlm_gemm_desc {
+  const void* A;        int64_t lda;   /* [M, K] */
+  const void* W;        int64_t ldw;   /* [N, K] (nn.Linear weight) */
+  const void* bias;                    /* [N] or NULL */
+  const void* resid;    int64_t ldr;   /* [M, N] or NULL */
+  const void* addvec;                  /* [N] or NULL */
+  const float* pe_table; const int64_t* frame_idx; int32_t tokens_per_frame;   /* fused temporal PE or NULL */
+  void* C;              int64_t ldc;   /* [M, N] */
+  int32_t M, N, K, act, out_dtype;
+} mavlm_gemm_desc;
+MAVLM_API int mavlm_gemm_num_tiles(const mavlm_gemm_desc* g);
+MAVLM_API int mavlm_gemm_tiles_fwd(const mavlm_gemm_desc* g, int tile_begin, int tile_end, int dtype, void* stream);
+/* *fill_done_end receives the first filler tile NOT computed (== fill_begin when nothing fitted). */
+MAVLM_API int mavlm_gemm_fill_fwd(const mavlm_gemm_desc* primary, const mavlm_gemm_desc* filler, int fill_begin,
+                                  int fill_avail_end, int* fill_done_end, int dtype, void* stream);
+
 /* ---- tensor.to(dtype) between the two tiers (fp32 <-> bf16), contiguous n elements. */
 MAVLM_API int mavlm_cast_fwd(const void* x, void* y, int64_t n, int src_dtype, int dst_dtype, void* stream);
 

@@ -18,6 +18,15 @@ POOL_BILINEAR, POOL_AVERAGE, POOL_MAX = 0, 1, 2
 E_INVALID, E_CUDA, E_ARCH, E_INDEX, E_WORKSPACE = -1, -2, -3, -4, -5
 
 
+class GemmDesc(ctypes.Structure):
+    """mavlm_gemm_desc of include/mavlm.h (one nn.Linear call as a tiled problem)."""
+    _fields_ = [("A", c_void_p), ("lda", c_int64), ("W", c_void_p), ("ldw", c_int64), ("bias", c_void_p),
+                ("resid", c_void_p), ("ldr", c_int64), ("addvec", c_void_p), ("pe_table", c_void_p),
+                ("frame_idx", c_void_p), ("tokens_per_frame", ctypes.c_int32), ("C", c_void_p), ("ldc", c_int64),
+                ("M", ctypes.c_int32), ("N", ctypes.c_int32), ("K", ctypes.c_int32), ("act", ctypes.c_int32),
+                ("out_dtype", ctypes.c_int32)]
+
+
 class MavlmError(RuntimeError):
     """Raised when a C-ABI call returns a negative status (shape errors surface as RuntimeError,
     like the reference's view/reshape failures)."""
@@ -38,6 +47,9 @@ PROTOTYPES = {
                                        c_int64, c_int, c_int, c_int, c_int, c_void_p]),
     "mavlm_gather_rows_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int,
                                       c_int, c_void_p]),
+    "mavlm_gemm_num_tiles": (c_int, [c_void_p]),
+    "mavlm_gemm_tiles_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
+    "mavlm_gemm_fill_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "mavlm_cast_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "mavlm_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_int,
                                     c_void_p]),

@@ -10,6 +10,10 @@ int gemm_bf16_tc(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, 
                  void* C, long long ldc, int M, int N, int K, int act, int out_f32, cudaStream_t st, int half = 0,
                  const float* pe_table = nullptr, const long long* pe_idx = nullptr, int pe_tokens = 0);
 void gemm_tc_force_bn(int bn);
+int gemm_fill_num_tiles(const mavlm_gemm_desc* d);
+int gemm_fill_range(const mavlm_gemm_desc* d, int t0, int t1, int half, cudaStream_t st);
+int gemm_fill_fwd(const mavlm_gemm_desc* prim, const mavlm_gemm_desc* fill, int fill_begin, int fill_avail_end,
+                  int* fill_done_end, int half, cudaStream_t st);
 int xattn_fp32(const float* Q, long long ldq, long long qb, const float* K, long long ldk, long long kb, const float* V,
                long long ldv, long long vb, float* O, long long ldo, long long ob, float* lse, float* col_scores,
                int batch, int heads, int lq, int lk, int dh, float scale, void* ws, size_t ws_bytes, cudaStream_t st);
@@ -59,6 +63,29 @@ int mavlm_gemm_bias_pe_fwd(const void* A, int64_t lda, const void* W, int64_t ld
                       static_cast<const __nv_bfloat16*>(bias), nullptr, 0, nullptr, C, ldc, M, N, K, MAVLM_ACT_NONE, 0,
                       static_cast<cudaStream_t>(stream), dtype == MAVLM_F16 ? 1 : 0, pe_table,
                       reinterpret_cast<const long long*>(frame_idx), tokens_per_frame);
+}
+
+int mavlm_gemm_num_tiles(const mavlm_gemm_desc* g) {
+  MAVLM_REQUIRE(g != nullptr && g->M > 0 && g->N > 0, MAVLM_E_INVALID, "gemm_num_tiles: bad problem");
+  return gemm_fill_num_tiles(g);
+}
+
+int mavlm_gemm_tiles_fwd(const mavlm_gemm_desc* g, int tile_begin, int tile_end, int dtype, void* stream) {
+  MAVLM_REQUIRE(g != nullptr, MAVLM_E_INVALID, "gemm_tiles: NULL problem");
+  MAVLM_REQUIRE(dtype == MAVLM_BF16 || dtype == MAVLM_F16, MAVLM_E_INVALID, "gemm_tiles: tensor-core tier only (bf16 / fp16)");
+  MAVLM_REQUIRE(g->out_dtype == dtype || g->out_dtype == MAVLM_F32, MAVLM_E_INVALID, "gemm_tiles: bad out_dtype %d", g->out_dtype);
+  return gemm_fill_range(g, tile_begin, tile_end, dtype == MAVLM_F16 ? 1 : 0, static_cast<cudaStream_t>(stream));
+}
+
+int mavlm_gemm_fill_fwd(const mavlm_gemm_desc* primary, const mavlm_gemm_desc* filler, int fill_begin, int fill_avail_end,
+                        int* fill_done_end, int dtype, void* stream) {
+  MAVLM_REQUIRE(primary != nullptr, MAVLM_E_INVALID, "gemm_fill: NULL primary");
+  MAVLM_REQUIRE(dtype == MAVLM_BF16 || dtype == MAVLM_F16, MAVLM_E_INVALID, "gemm_fill: tensor-core tier only (bf16 / fp16)");
+  MAVLM_REQUIRE(primary->out_dtype == dtype || primary->out_dtype == MAVLM_F32, MAVLM_E_INVALID, "gemm_fill: bad out_dtype");
+  if (filler != nullptr)
+    MAVLM_REQUIRE(filler->out_dtype == dtype || filler->out_dtype == MAVLM_F32, MAVLM_E_INVALID, "gemm_fill: bad filler out_dtype");
+  return gemm_fill_fwd(primary, filler, fill_begin, fill_avail_end, fill_done_end, dtype == MAVLM_F16 ? 1 : 0,
+                       static_cast<cudaStream_t>(stream));
 }
 
 size_t mavlm_xattn_workspace_bytes(int batch, int heads, int lq, int lk, int head_dim, int dtype) {

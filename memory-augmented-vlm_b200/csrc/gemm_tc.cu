@@ -43,6 +43,11 @@ struct GemmTcParams {
   long long c_outer, c_inner;
   int accumulate;  // C += result
   int tma_store;   // the epilogue stages C rows in shared memory and writes them with TMA stores (tmC)
+  // tile range of this launch: [tile_begin, tile_end) of the m_tiles * n_tiles * batches tiles (rasterised order)
+  int tile_begin, tile_end;
+  // tail fill (problem 2 of a launch only): the workers that would idle in the primary's last wave -- workers
+  // [fill_first_idle, workers) -- walk this problem's tiles tile_begin + (worker - fill_first_idle) + k * fill_n_idle
+  int fill_first_idle, fill_n_idle;
 };
 
 // CG = CTAs per MMA (tcgen05 cta_group): 1 = one CTA owns a 128 x BN tile; 2 = a CTA pair owns a 256 x BN
@@ -85,7 +90,9 @@ __device__ __forceinline__ void gemm_tile_coords(int tile, int m_tiles, int n_ti
 template <int BN, bool A_MN, bool B_MN, int CG, typename T = __nv_bfloat16>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, GemmTcParams p) {
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ GemmTcParams p,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+               const __grid_constant__ CUtensorMap tmC2, const __grid_constant__ GemmTcParams p2, const int has2) {
   static_assert(CG == 1 || CG == 2, "one CTA or a CTA pair per tile");
   static_assert(CG == 1 || !B_MN || (BN / CG) % 64 == 0, "an MN-major W half must be whole 64-column boxes");
   using Cfg = GemmCfg<BN, CG>;
@@ -103,9 +110,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_per_batch = p.m_tiles * p.n_tiles;
-  const int num_tiles = tiles_per_batch * p.batches;
-  const int kblocks = (p.K + GEMM_BK - 1) / GEMM_BK;
+  // A launch walks up to two problems with the same tile shape: the primary (all workers, round robin over its tile
+  // range) and, for TAIL FILL, a second problem whose tiles go only to the workers that would idle in the primary's
+  // last wave (GemmTcParams::fill_*).  Every role runs the same two loops, so the smem / TMEM pipelines just continue.
+#define MAVLM_GEMM_PROBLEM(pi)                                                                            \
+  const GemmTcParams& pp = (pi) ? p2 : p;                                                                 \
+  const CUtensorMap* ta = (pi) ? &tmA2 : &tmA;                                                            \
+  const CUtensorMap* tb = (pi) ? &tmB2 : &tmB;                                                            \
+  const CUtensorMap* tc = (pi) ? &tmC2 : &tmC;                                                            \
+  (void)ta; (void)tb; (void)tc;                                                                           \
+  if ((pi) && worker < pp.fill_first_idle) break;                                                         \
+  const int t_first = pp.tile_begin + ((pi) ? worker - pp.fill_first_idle : worker);                      \
+  const int t_step = (pi) ? pp.fill_n_idle : workers;                                                     \
+  const int tiles_per_batch = pp.m_tiles * pp.n_tiles;                                                    \
+  const int kblocks = (pp.K + GEMM_BK - 1) / GEMM_BK;                                                     \
+  (void)tiles_per_batch; (void)kblocks
   // CTA pair: rank 0 is the leader (issues the MMAs, owns the full / tempty barriers both CTAs signal)
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
   const int worker = CG == 2 ? blockIdx.x / 2 : blockIdx.x;       // persistent tile walker (CTA or pair)
@@ -115,6 +134,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     if (p.tma_store) prefetch_tmap(&tmC);
+    if (has2) {
+      prefetch_tmap(&tmA2);
+      prefetch_tmap(&tmB2);
+      if (p2.tma_store) prefetch_tmap(&tmC2);
+    }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -141,13 +165,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = worker; tile < num_tiles; tile += workers) {
+      for (int pi = 0; pi <= has2; ++pi) {
+      MAVLM_GEMM_PROBLEM(pi);
+      for (int tile = t_first; tile < pp.tile_end; tile += t_step) {
         int m_blk, n_blk;
         const int batch = tile / tiles_per_batch;
-        gemm_tile_coords(tile - batch * tiles_per_batch, p.m_tiles, p.n_tiles, p.group_m, m_blk, n_blk);
+        gemm_tile_coords(tile - batch * tiles_per_batch, pp.m_tiles, pp.n_tiles, pp.group_m, m_blk, n_blk);
         const int m0 = m_blk * TILE_M + static_cast<int>(rank) * GEMM_BM;
         const int n0 = n_blk * BN + static_cast<int>(rank) * Cfg::B_ROWS;
-        const int bi = batch % p.inner, bo = batch / p.inner;
+        const int bi = batch % pp.inner, bo = batch / pp.inner;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* a_dst = sA + stage * Cfg::A_BYTES;
@@ -157,38 +183,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (rank == 0) mbar_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
             const uint32_t bar = mapa_u32(smem_u32(&full[stage]), 0);
             if (!A_MN) {
-              tma_load_4d_pair(a_dst, &tmA, bar, kb * GEMM_BK, m0, bi, bo);
+              tma_load_4d_pair(a_dst, ta, bar, kb * GEMM_BK, m0, bi, bo);
             } else {
 #pragma unroll
               for (int i = 0; i < GEMM_BM / 64; ++i)
-                tma_load_4d_pair(a_dst + i * 8192, &tmA, bar, m0 + 64 * i, kb * GEMM_BK, bi, bo);
+                tma_load_4d_pair(a_dst + i * 8192, ta, bar, m0 + 64 * i, kb * GEMM_BK, bi, bo);
             }
             if (!B_MN) {
-              tma_load_4d_pair(b_dst, &tmB, bar, kb * GEMM_BK, n0, bi, bo);
+              tma_load_4d_pair(b_dst, tb, bar, kb * GEMM_BK, n0, bi, bo);
             } else {
 #pragma unroll
               for (int i = 0; i < Cfg::B_ROWS / 64; ++i)
-                tma_load_4d_pair(b_dst + i * 8192, &tmB, bar, n0 + 64 * i, kb * GEMM_BK, bi, bo);
+                tma_load_4d_pair(b_dst + i * 8192, tb, bar, n0 + 64 * i, kb * GEMM_BK, bi, bo);
             }
           } else {
             mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
             if (!A_MN) {
-              tma_load_4d(a_dst, &tmA, &full[stage], kb * GEMM_BK, m0, bi, bo);
+              tma_load_4d(a_dst, ta, &full[stage], kb * GEMM_BK, m0, bi, bo);
             } else {
 #pragma unroll
               for (int i = 0; i < GEMM_BM / 64; ++i)
-                tma_load_4d(a_dst + i * 8192, &tmA, &full[stage], m0 + 64 * i, kb * GEMM_BK, bi, bo);
+                tma_load_4d(a_dst + i * 8192, ta, &full[stage], m0 + 64 * i, kb * GEMM_BK, bi, bo);
             }
             if (!B_MN) {
-              tma_load_4d(b_dst, &tmB, &full[stage], kb * GEMM_BK, n0, bi, bo);
+              tma_load_4d(b_dst, tb, &full[stage], kb * GEMM_BK, n0, bi, bo);
             } else {
 #pragma unroll
               for (int i = 0; i < BN / 64; ++i)
-                tma_load_4d(b_dst + i * 8192, &tmB, &full[stage], n0 + 64 * i, kb * GEMM_BK, bi, bo);
+                tma_load_4d(b_dst + i * 8192, tb, &full[stage], n0 + 64 * i, kb * GEMM_BK, bi, bo);
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+      }
       }
     }
   } else if (warp == 1) {
@@ -198,7 +225,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = worker; tile < num_tiles; tile += workers) {
+      for (int pi = 0; pi <= has2; ++pi) {
+      MAVLM_GEMM_PROBLEM(pi);
+      for (int tile = t_first; tile < pp.tile_end; tile += t_step) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
@@ -223,6 +252,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         else umma_commit(&tfull[acc]);
         if ((acc ^= 1) == 0) acc_phase ^= 1;
       }
+      }
     }
   } else {
     const int q = warp & 3;                     // TMEM lane quadrant this warp may access
@@ -233,22 +263,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t acc_phase = 0;
     const uint32_t tempty_leader = CG == 2 ? mapa_u32(smem_u32(&tempty[0]), 0) : 0u;
     uint8_t* out_stage = sOut + (warp - 2) * Cfg::OUT_STAGE_BYTES;
-    for (int tile = worker; tile < num_tiles; tile += workers) {
+    for (int pi = 0; pi <= has2; ++pi) {
+      MAVLM_GEMM_PROBLEM(pi);
+      for (int tile = t_first; tile < pp.tile_end; tile += t_step) {
       int m_blk, n_blk;
       const int batch = tile / tiles_per_batch;
-      gemm_tile_coords(tile - batch * tiles_per_batch, p.m_tiles, p.n_tiles, p.group_m, m_blk, n_blk);
+      gemm_tile_coords(tile - batch * tiles_per_batch, pp.m_tiles, pp.n_tiles, pp.group_m, m_blk, n_blk);
       const int m0 = m_blk * TILE_M + static_cast<int>(rank) * GEMM_BM, n0 = n_blk * BN;
-      const long long c_off = (batch / p.inner) * p.c_outer + (batch % p.inner) * p.c_inner;
+      const long long c_off = (batch / pp.inner) * pp.c_outer + (batch % pp.inner) * pp.c_inner;
       const int row = m0 + row_in_tile;
-      const bool row_ok = row < p.M;
+      const bool row_ok = row < pp.M;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::ACC_STRIDE;
 
       // one 32-column chunk of this thread's row: + bias -> activation -> (+ resid) (+ addvec) -> store
       auto emit = [&](const uint32_t (&r)[32], int c) {
         const int nc = n0 + c * 32;
-        if (nc >= p.N) return;                      // warp-uniform
-        if (!row_ok && !p.tma_store) return;        // TMA-store mode keeps the whole warp in the protocol
-        const bool full_chunk = nc + 32 <= p.N;
+        if (nc >= pp.N) return;                      // warp-uniform
+        if (!row_ok && !pp.tma_store) return;        // TMA-store mode keeps the whole warp in the protocol
+        const bool full_chunk = nc + 32 <= pp.N;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -269,21 +301,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           } else {
             for (int j = 0; j < 32; ++j)
-              if (nc + j < p.N) v[j] += Elem16<T>::to_float(src[j]);
+              if (nc + j < pp.N) v[j] += Elem16<T>::to_float(src[j]);
           }
         };
-        if (p.bias != nullptr) add_vec32(static_cast<const T*>(p.bias) + nc, false);
-        if (p.act == MAVLM_ACT_GELU_ERF) {
+        if (pp.bias != nullptr) add_vec32(static_cast<const T*>(pp.bias) + nc, false);
+        if (pp.act == MAVLM_ACT_GELU_ERF) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
-        } else if (p.act == MAVLM_ACT_RELU) {
+        } else if (pp.act == MAVLM_ACT_RELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
-        if (p.resid != nullptr && row_ok) add_vec32(static_cast<const T*>(p.resid) + row * p.ldr + nc, true);
-        if (p.addvec != nullptr) add_vec32(static_cast<const T*>(p.addvec) + nc, false);
-        if (p.pe_table != nullptr && row_ok) {  // the frame's PE row (fp32, L2-resident: 196 rows share it)
-          const float* pe = p.pe_table + __ldg(p.pe_idx + row / p.pe_tokens) * p.N + nc;
+        if (pp.resid != nullptr && row_ok) add_vec32(static_cast<const T*>(pp.resid) + row * pp.ldr + nc, true);
+        if (pp.addvec != nullptr) add_vec32(static_cast<const T*>(pp.addvec) + nc, false);
+        if (pp.pe_table != nullptr && row_ok) {  // the frame's PE row (fp32, L2-resident: 196 rows share it)
+          const float* pe = pp.pe_table + __ldg(pp.pe_idx + row / pp.pe_tokens) * pp.N + nc;
           if (full_chunk) {
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
@@ -292,14 +324,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           } else {
             for (int j = 0; j < 32; ++j)
-              if (nc + j < p.N) v[j] += pe[j];
+              if (nc + j < pp.N) v[j] += pe[j];
           }
         }
-        if (p.tma_store) {
+        if (pp.tma_store) {
           // Coalesced output: the warp's 32 rows x 32 columns go to a swizzled shared-memory tile (thread = row,
           // conflict-free 16-byte writes) and leave as ONE TMA store, which also clips the M / N tails.  Direct
           // register stores (32 rows x 16 B per instruction, half sectors) cost 30 % of the K = 1152 projector GEMM.
-          if (p.out_f32) {
+          if (pp.out_f32) {
             if (lane == 0) bulk_wait_read<0>();
             __syncwarp();
             uint8_t* dst = out_stage + lane * 128;
@@ -310,7 +342,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(out_stage, &tmC, nc, m0 + q * 32);
+              tma_store_2d(out_stage, tc, nc, m0 + q * 32);
               bulk_commit();
             }
           } else {
@@ -330,17 +362,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(buf, &tmC, nc, m0 + q * 32);
+              tma_store_2d(buf, tc, nc, m0 + q * 32);
               bulk_commit();
             }
           }
           return;
         }
-        if (p.out_f32) {
-          float* cp = static_cast<float*>(p.C) + c_off + row * p.ldc + nc;
-          if (p.accumulate) {
+        if (pp.out_f32) {
+          float* cp = static_cast<float*>(pp.C) + c_off + row * pp.ldc + nc;
+          if (pp.accumulate) {
             for (int j = 0; j < 32; ++j)
-              if (nc + j < p.N) v[j] += cp[j];
+              if (nc + j < pp.N) v[j] += cp[j];
           }
           if (full_chunk) {
 #pragma unroll
@@ -348,13 +380,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               reinterpret_cast<float4*>(cp)[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
           } else {
             for (int j = 0; j < 32; ++j)
-              if (nc + j < p.N) cp[j] = v[j];
+              if (nc + j < pp.N) cp[j] = v[j];
           }
         } else {
-          T* cp = static_cast<T*>(p.C) + c_off + row * p.ldc + nc;
-          if (p.accumulate) {
+          T* cp = static_cast<T*>(pp.C) + c_off + row * pp.ldc + nc;
+          if (pp.accumulate) {
             for (int j = 0; j < 32; ++j)
-              if (nc + j < p.N) v[j] += Elem16<T>::to_float(cp[j]);
+              if (nc + j < pp.N) v[j] += Elem16<T>::to_float(cp[j]);
           }
           if (full_chunk) {
 #pragma unroll
@@ -368,7 +400,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           } else {
             for (int j = 0; j < 32; ++j)
-              if (nc + j < p.N) cp[j] = Elem16<T>::from_float(v[j]);
+              if (nc + j < pp.N) cp[j] = Elem16<T>::from_float(v[j]);
           }
         }
       };
@@ -406,7 +438,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if ((acc ^= 1) == 0) acc_phase ^= 1;
     }
-    if (p.tma_store && lane == 0) bulk_wait_all();  // every TMA store of this warp has completed
+    }
+    if (lane == 0) bulk_wait_all();  // every TMA store of this warp has completed (no-op without TMA stores)
   }
   tc_fence_before();
   if (CG == 2) cluster_sync_all();  // no CTA of the pair exits (or frees TMEM) while the other may still touch it
@@ -418,9 +451,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// m / n tile counts and the rasterisation group of a problem for a tile shape (depends on the problem only, so a
+// problem that is walked over several launches -- tail fill -- sees one consistent tile numbering)
+static void gemm_set_tiling(GemmTcParams& p, int bn, int cg) {
+  p.m_tiles = ceil_div(p.M, GEMM_BM * cg);
+  p.n_tiles = ceil_div(p.N, bn);
+  // a group's A rows (group * TILE_M * K bf16) should stay in L2 (126 MB, shared with the W slabs in flight and
+  // the streaming C writes) while N is swept: ~32 MB.  With the old fixed 16 x 128 rows the 12544 x 14336 x
+  // 3584 K/V projection read 1.06 GB from DRAM for 0.19 GB of operands (W re-read once per group).
+  const long long tile_bytes = static_cast<long long>(GEMM_BM) * cg * p.K * 2;
+  long long g = (40ll << 20) / (tile_bytes > 0 ? tile_bytes : 1);
+  if (tile_bytes * p.m_tiles <= (64ll << 20)) g = p.m_tiles;  // all of A fits: one group, W is read exactly once
+  if (g < 2) g = 2;
+  if (g > p.m_tiles) g = p.m_tiles;
+  p.group_m = static_cast<int>(g);
+  if (p.batches < 1) p.batches = 1;
+  if (p.inner < 1) p.inner = 1;
+}
+
+// One launch.  `p` must carry its tiling and tile range; `p2` (may be null) is the tail-fill problem with its range
+// and fill_* fields.  `full_grid`: launch every worker even if the primary has fewer tiles (the idle ones fill).
 template <int BN, bool A_MN, bool B_MN, int CG, typename T = __nv_bfloat16>
-static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, GemmTcParams p,
-                          cudaStream_t st) {
+static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmTcParams& p,
+                          cudaStream_t st, const CUtensorMap* tmA2 = nullptr, const CUtensorMap* tmB2 = nullptr,
+                          const CUtensorMap* tmC2 = nullptr, const GemmTcParams* p2 = nullptr, int workers_forced = 0) {
   using Cfg = GemmCfg<BN, CG>;
   static_assert(Cfg::SMEM_BYTES <= 232448, "gemm smem budget exceeded");
   static bool configured_dev[64] = {};  // the attribute is per device (one process may drive several GPUs)
@@ -432,27 +486,16 @@ static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  p.m_tiles = ceil_div(p.M, GEMM_BM * CG);
-  p.n_tiles = ceil_div(p.N, BN);
-  {
-    // a group's A rows (group * TILE_M * K bf16) should stay in L2 (126 MB, shared with the W slabs in flight and
-    // the streaming C writes) while N is swept: ~32 MB.  With the old fixed 16 x 128 rows the 12544 x 14336 x
-    // 3584 K/V projection read 1.06 GB from DRAM for 0.19 GB of operands (W re-read once per group).
-    const long long tile_bytes = static_cast<long long>(GEMM_BM) * CG * p.K * 2;
-    long long g = (40ll << 20) / (tile_bytes > 0 ? tile_bytes : 1);
-    if (tile_bytes * p.m_tiles <= (64ll << 20)) g = p.m_tiles;  // all of A fits: one group, W is read exactly once
-    if (g < 2) g = 2;
-    if (g > p.m_tiles) g = p.m_tiles;
-    p.group_m = static_cast<int>(g);
-  }
-  if (p.batches < 1) p.batches = 1;
-  if (p.inner < 1) p.inner = 1;
-  const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles * p.batches;
+  const long long tiles = static_cast<long long>(p.tile_end) - p.tile_begin;
   const int workers_max = sm_count() / CG;
-  const int workers = static_cast<int>(tiles < workers_max ? tiles : workers_max);
+  int workers = static_cast<int>(tiles < workers_max ? tiles : workers_max);
+  if (workers_forced > 0) workers = workers_forced;
+  if (workers < 1) return MAVLM_OK;
   LaunchCfg lc;
   make_launch(lc, dim3(workers * CG), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, st, CG, 1);
-  MAVLM_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, gemm_tc_kernel<BN, A_MN, B_MN, CG, T>, tmA, tmB, tmC, p));
+  const int has2 = p2 != nullptr ? 1 : 0;
+  MAVLM_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, gemm_tc_kernel<BN, A_MN, B_MN, CG, T>, tmA, tmB, tmC, p, has2 ? *tmA2 : tmA,
+                                   has2 ? *tmB2 : tmB, has2 ? *tmC2 : tmC, has2 ? *p2 : p, has2));
   MAVLM_LAUNCH_OK();
   return MAVLM_OK;
 }
@@ -605,6 +648,9 @@ int gemm_tc_general(const __nv_bfloat16* A, long long lda, bool a_mn, const __nv
     const uint32_t box[2] = {32, 32};
     if ((rc = make_tmap(&tmC, p.C, eb, p.out_f32 ? 128 : 64, 2, dims, str, box))) return rc;
   }
+  gemm_set_tiling(p, bn, cg);
+  p.tile_begin = 0;
+  p.tile_end = p.m_tiles * p.n_tiles * p.batches;
   if (a_mn)
     return b_mn ? dispatch_bn<true, true>(bn, cg, tmA, tmB, tmC, p, st)
                 : dispatch_bn<true, false>(bn, cg, tmA, tmB, tmC, p, st);
@@ -628,6 +674,118 @@ int gemm_bf16_tc(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, 
   p.bias = bias; p.resid = resid; p.ldr = ldr; p.addvec = addvec;
   p.C = C; p.ldc = ldc; p.act = act; p.out_f32 = out_f32;
   return gemm_tc_general(A, lda, false, W, ldw, false, p, 1, 1, nullptr, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Tail fill: co-scheduling an off-critical-path GEMM into the idle tail of a critical-path one.
+//
+// The recurrence is a serial chain of GEMMs with only 1568 rows: 7 x 14 = 98 CTA-pair tiles (256 x 256) on 74 pairs
+// is 1.32 waves, so 50 of the 148 tile slots of such a launch compute nothing (the 1568 x 3584 x 3584 launches ran at
+// 0.55 of the rate of the large GEMMs).  The step also contains GEMM work that nothing on the chain waits for yet: the
+// frame-side K/V projection of LATER chunks and the fuser MLP of FINISHED states.  A launch therefore takes TWO
+// problems of the same tile shape (CTA pair, 256 x 256): every worker walks the primary's tiles round-robin; the
+// workers that would idle in its last wave then take tiles [begin, end) of the fill problem -- as many per idle worker
+// as fit into one primary tile's time (K_primary / K_fill) -- so the chain's latency is unchanged and the fill work
+// costs nothing.  The host keeps a cursor per fill problem and finishes whatever is left with a plain range launch
+// before the first consumer.  Results are bit-identical to separate launches (same tiles, same k order).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int FILL_BN = 256;
+constexpr int FILL_CG = 2;
+
+static int fill_prepare(const mavlm_gemm_desc& d, int half, GemmTcParams& p, CUtensorMap& tmA, CUtensorMap& tmB,
+                        CUtensorMap& tmC) {
+  MAVLM_REQUIRE(d.A != nullptr && d.W != nullptr && d.C != nullptr, MAVLM_E_INVALID, "gemm fill: NULL operand");
+  MAVLM_REQUIRE(d.M > 0 && d.N > 0 && d.K > 0 && d.K % 8 == 0 && d.lda % 8 == 0 && d.ldw % 8 == 0, MAVLM_E_INVALID,
+                "gemm fill: bad shape / strides (M=%d N=%d K=%d)", d.M, d.N, d.K);
+  MAVLM_REQUIRE(d.act >= MAVLM_ACT_NONE && d.act <= MAVLM_ACT_RELU, MAVLM_E_INVALID, "gemm fill: bad activation %d", d.act);
+  const int out_f32 = d.out_dtype == MAVLM_F32 ? 1 : 0;
+  const int cvec = out_f32 ? 4 : 8;
+  MAVLM_REQUIRE(d.ldc % cvec == 0 && (reinterpret_cast<uintptr_t>(d.C) & 15) == 0, MAVLM_E_INVALID,
+                "gemm fill: C must be 16-byte aligned with ldc %% %d == 0", cvec);
+  if (d.resid != nullptr)
+    MAVLM_REQUIRE(d.ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(d.resid) & 15) == 0, MAVLM_E_INVALID,
+                  "gemm fill: resid must be 16-byte aligned with ldr %% 8 == 0");
+  p = GemmTcParams{};
+  p.half = half;
+  p.M = d.M; p.N = d.N; p.K = d.K;
+  p.bias = d.bias; p.resid = d.resid; p.ldr = d.ldr; p.addvec = d.addvec;
+  if (d.pe_table != nullptr) {
+    MAVLM_REQUIRE(d.frame_idx != nullptr && d.tokens_per_frame > 0 && d.N % 4 == 0, MAVLM_E_INVALID, "gemm fill: bad PE fusion");
+    p.pe_table = d.pe_table; p.pe_idx = reinterpret_cast<const long long*>(d.frame_idx); p.pe_tokens = d.tokens_per_frame;
+  }
+  p.C = d.C; p.ldc = d.ldc; p.act = d.act; p.out_f32 = out_f32;
+  p.batches = 1; p.inner = 1;
+  p.tma_store = 1;
+  gemm_set_tiling(p, FILL_BN, FILL_CG);
+  int rc;
+  if ((rc = make_operand_map(&tmA, d.A, d.lda, d.M, d.K, false, GEMM_BM, 1, 1, 0, 0))) return rc;
+  if ((rc = make_operand_map(&tmB, d.W, d.ldw, d.N, d.K, false, FILL_BN / FILL_CG, 1, 1, 0, 0))) return rc;
+  const int eb = out_f32 ? 4 : 2;
+  const uint64_t dims[2] = {static_cast<uint64_t>(d.N), static_cast<uint64_t>(d.M)};
+  const uint64_t str[1] = {static_cast<uint64_t>(d.ldc) * eb};
+  const uint32_t box[2] = {32, 32};
+  return make_tmap(&tmC, d.C, eb, out_f32 ? 128 : 64, 2, dims, str, box);
+}
+
+int gemm_fill_num_tiles(const mavlm_gemm_desc* d) {
+  return ceil_div(d->M, GEMM_BM * FILL_CG) * ceil_div(d->N, FILL_BN);
+}
+
+// tiles [t0, t1) of one problem as an ordinary launch (the flush of a fill problem, or a whole GEMM with t0 = 0)
+int gemm_fill_range(const mavlm_gemm_desc* d, int t0, int t1, int half, cudaStream_t st) {
+  GemmTcParams p;
+  CUtensorMap tmA, tmB, tmC;
+  int rc;
+  if ((rc = fill_prepare(*d, half, p, tmA, tmB, tmC))) return rc;
+  const int total = p.m_tiles * p.n_tiles;
+  MAVLM_REQUIRE(0 <= t0 && t0 <= t1 && t1 <= total, MAVLM_E_INVALID, "gemm fill: tile range [%d, %d) outside [0, %d)", t0, t1, total);
+  if (t0 == t1) return MAVLM_OK;
+  p.tile_begin = t0;
+  p.tile_end = t1;
+  if (half) return launch_gemm_tc<FILL_BN, false, false, FILL_CG, __half>(tmA, tmB, tmC, p, st);
+  return launch_gemm_tc<FILL_BN, false, false, FILL_CG>(tmA, tmB, tmC, p, st);
+}
+
+// primary (whole problem) + as many tiles of `fill` from `fill_begin` (at most up to fill_avail_end) as the primary's
+// last wave leaves room for; *fill_done_end receives the first fill tile NOT done
+int gemm_fill_fwd(const mavlm_gemm_desc* prim, const mavlm_gemm_desc* fill, int fill_begin, int fill_avail_end,
+                  int* fill_done_end, int half, cudaStream_t st) {
+  GemmTcParams p, p2;
+  CUtensorMap tmA, tmB, tmC, tmA2, tmB2, tmC2;
+  int rc;
+  if ((rc = fill_prepare(*prim, half, p, tmA, tmB, tmC))) return rc;
+  p.tile_begin = 0;
+  p.tile_end = p.m_tiles * p.n_tiles;
+  if (fill_done_end != nullptr) *fill_done_end = fill_begin;
+  const int workers = sm_count() / FILL_CG;
+  int n2 = 0, first_idle = 0, n_idle = 0;
+  if (fill != nullptr && fill_avail_end > fill_begin) {
+    if ((rc = fill_prepare(*fill, half, p2, tmA2, tmB2, tmC2))) return rc;
+    const int total2 = p2.m_tiles * p2.n_tiles;
+    MAVLM_REQUIRE(fill_begin >= 0 && fill_avail_end <= total2, MAVLM_E_INVALID, "gemm fill: range [%d, %d) outside [0, %d)",
+                  fill_begin, fill_avail_end, total2);
+    const int r = p.tile_end % workers;
+    first_idle = r;
+    n_idle = r == 0 ? 0 : workers - r;
+    // fill tiles per idle worker: what fits into the time of one primary tile (same tile shape: time ~ K)
+    int reps = 0;
+    if (p2.K <= p.K) reps = p.K / p2.K;
+    else if (p2.K * 4 <= p.K * 5) reps = 1;
+    n2 = n_idle * reps;
+    if (n2 > fill_avail_end - fill_begin) n2 = fill_avail_end - fill_begin;
+  }
+  if (n2 > 0) {
+    p2.tile_begin = fill_begin;
+    p2.tile_end = fill_begin + n2;
+    p2.fill_first_idle = first_idle;
+    p2.fill_n_idle = n_idle;
+    if (fill_done_end != nullptr) *fill_done_end = fill_begin + n2;
+    if (half)
+      return launch_gemm_tc<FILL_BN, false, false, FILL_CG, __half>(tmA, tmB, tmC, p, st, &tmA2, &tmB2, &tmC2, &p2, workers);
+    return launch_gemm_tc<FILL_BN, false, false, FILL_CG>(tmA, tmB, tmC, p, st, &tmA2, &tmB2, &tmC2, &p2, workers);
+  }
+  if (half) return launch_gemm_tc<FILL_BN, false, false, FILL_CG, __half>(tmA, tmB, tmC, p, st);
+  return launch_gemm_tc<FILL_BN, false, false, FILL_CG>(tmA, tmB, tmC, p, st);
 }
 
 // Backward-pass entry (mavlm_gemm_ex, bf16): trans_a = 1 -> A stored [K,M]; trans_b = 0 -> B stored [K,N].

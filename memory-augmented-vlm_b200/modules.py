@@ -62,9 +62,14 @@ class Residual(nn.Module):
         self.dense = nn.Linear(input_size, output_size, dtype=dt)
         self.layernorm = nn.LayerNorm(output_size, eps=config.mm_layer_norm_eps, dtype=dt)
 
-    def forward(self, hidden_states: torch.Tensor, input_tensor: torch.Tensor, *, weight=None, out=None) -> torch.Tensor:
+    def forward(self, hidden_states: torch.Tensor, input_tensor: torch.Tensor, *, weight=None, out=None,
+                fillers=()) -> torch.Tensor:
         w = self.dense.weight if weight is None else weight
-        pre = ops.linear(hidden_states, w, self.dense.bias, resid=input_tensor, out_dtype=torch.float32)
+        if fillers:     # tail fill (ops.linear_fill): off-critical-path GEMM tiles ride in this launch's idle tile slots
+            pre = ops.linear_fill(hidden_states, w, self.dense.bias, resid=input_tensor, out_dtype=torch.float32,
+                                  fillers=fillers)
+        else:
+            pre = ops.linear(hidden_states, w, self.dense.bias, resid=input_tensor, out_dtype=torch.float32)
         return ops.layernorm(pre, self.layernorm.weight, self.layernorm.bias, self.layernorm.eps,
                              out_dtype=input_tensor.dtype, out=out)
 

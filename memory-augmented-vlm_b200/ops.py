@@ -4,6 +4,7 @@ streams); every computation below runs in libmavlm.so.  No fallback: CPU tensors
 """
 from __future__ import annotations
 
+import ctypes
 import math
 from typing import Optional, Tuple
 
@@ -108,6 +109,125 @@ def _linear_raw(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tens
                                      0 if r2 is None else r2.stride(0), _ptr(addvec), _ptr(out2), out2.stride(0), m, n,
                                      k, act, dtype_code(x), _DTYPES[odt], _stream())
     _lib.check(st, "gemm_bias_act_fwd")
+    if out is not None:
+        return out
+    return out2.reshape(*lead, n)
+
+
+class GemmWork:
+    """One nn.Linear call y = act(x W^T + b) (+ resid) (+ addvec) as a TILED problem (256 x 256 output tiles in a fixed
+    order) that can be computed in pieces: as the FILLER of critical-path GEMMs (`linear_fill`) and / or by `run()`
+    for whatever is left before the first consumer reads y.  bf16 / fp16 tier.  Holds references to its operands."""
+
+    def __init__(self, x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, *,
+                 act: int = ACT_NONE, resid: Optional[torch.Tensor] = None, addvec: Optional[torch.Tensor] = None,
+                 after: Optional["GemmWork"] = None):
+        _need_cuda(x, weight, bias, resid, addvec, out)
+        if x.dtype not in (torch.bfloat16, torch.float16):
+            raise TypeError("mavlm.GemmWork: tensor-core tier only (bfloat16 / float16)")
+        for t in (weight, bias, resid, addvec):
+            if t is not None and t.dtype != x.dtype:
+                raise TypeError(f"mavlm.GemmWork: operand dtype {t.dtype} != input dtype {x.dtype}")
+        _rowmajor2d(x, "x")
+        _rowmajor2d(weight, "weight")
+        _rowmajor2d(out, "out")
+        m, k = x.shape
+        n = weight.shape[0]
+        if weight.shape[1] != k or tuple(out.shape) != (m, n) or out.dtype not in (x.dtype, torch.float32):
+            raise RuntimeError("mavlm.GemmWork: shape / dtype mismatch")
+        if resid is not None:
+            _rowmajor2d(resid, "resid")
+            if tuple(resid.shape) != (m, n):
+                raise RuntimeError("mavlm.GemmWork: resid shape mismatch")
+        self.keep = (x, weight, bias, resid, addvec, out)
+        self.code = dtype_code(x)
+        d = _lib.GemmDesc()
+        d.A, d.lda, d.W, d.ldw = x.data_ptr(), x.stride(0), weight.data_ptr(), weight.stride(0)
+        d.bias = _ptr(bias)
+        d.resid, d.ldr = _ptr(resid), (0 if resid is None else resid.stride(0))
+        d.addvec = _ptr(addvec)
+        d.pe_table, d.frame_idx, d.tokens_per_frame = None, None, 0
+        d.C, d.ldc = out.data_ptr(), out.stride(0)
+        d.M, d.N, d.K, d.act, d.out_dtype = m, n, k, act, _DTYPES[out.dtype]
+        self.desc = d
+        self.out = out
+        self.device = x.device
+        self.after = after                       # a work whose output this one reads: it must be complete first
+        self.total = _lib.load().mavlm_gemm_num_tiles(ctypes.byref(d))
+        if self.total <= 0:
+            raise _lib.MavlmError("mavlm.GemmWork: " + _lib.load().mavlm_last_error_string().decode())
+        self.cursor = 0
+
+    @property
+    def done(self) -> bool:
+        return self.cursor >= self.total
+
+    @property
+    def ready(self) -> bool:
+        return self.after is None or self.after.done
+
+    def run(self, fillers=()) -> torch.Tensor:
+        """Compute every tile that is still missing and return the output: a plain launch over the missing range, or --
+        when nothing of this problem has been computed yet -- a launch that takes a ready filler along."""
+        if self.after is not None and not self.after.done:
+            self.after.run()
+        if self.done:
+            return self.out
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            other = _pick_filler(fillers, self.desc.K, exclude=self) if self.cursor == 0 else None
+            if other is not None:
+                done_end = ctypes.c_int(other.cursor)
+                st = lib.mavlm_gemm_fill_fwd(ctypes.byref(self.desc), ctypes.byref(other.desc), other.cursor, other.total,
+                                             ctypes.byref(done_end), self.code, _stream())
+                _lib.check(st, "gemm_fill_fwd")
+                other.cursor = done_end.value
+            else:
+                st = lib.mavlm_gemm_tiles_fwd(ctypes.byref(self.desc), self.cursor, self.total, self.code, _stream())
+                _lib.check(st, "gemm_tiles_fwd")
+        self.cursor = self.total
+        return self.out
+
+
+def _pick_filler(fillers, k_primary: int, exclude=None):
+    """First filler that is unfinished, whose input is complete, and whose tiles are not longer than the primary's
+    (a longer tile in the last wave would stretch the critical path): K_fill <= 1.25 K_primary."""
+    for w_ in fillers:
+        if w_ is exclude or w_.done or not w_.ready:
+            continue
+        if w_.desc.K * 4 > k_primary * 5:
+            continue
+        return w_
+    return None
+
+
+def linear_fill(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: int = ACT_NONE,
+                resid: Optional[torch.Tensor] = None, addvec: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
+                fillers=()) -> torch.Tensor:
+    """`linear` on the critical path with TAIL FILL: the tile slots its last wave would leave idle compute tiles of the
+    first unfinished, ready GemmWork in `fillers` (include/mavlm.h: mavlm_gemm_fill_fwd).  Without a usable filler (or
+    in the fp32 tier) this is `linear`."""
+    work = _pick_filler(fillers, x.shape[-1]) if x.dtype in (torch.bfloat16, torch.float16) else None
+    if work is None:
+        return linear(x, weight, bias, act=act, resid=resid, addvec=addvec, out=out, out_dtype=out_dtype)
+    lead = x.shape[:-1]
+    k = x.shape[-1]
+    x2 = x.reshape(-1, k)
+    m, n = x2.shape[0], weight.shape[0]
+    if out is None:
+        out2 = torch.empty((m, n), dtype=out_dtype or x.dtype, device=x.device)
+    else:
+        out2 = out.reshape(-1, n) if out.dim() != 2 else out
+        if out2.data_ptr() != out.data_ptr():
+            raise RuntimeError("mavlm.linear_fill: out must be a row-major [M, N] view")
+    prim = GemmWork(x2, weight, bias, out2, act=act, resid=None if resid is None else resid.reshape(-1, n), addvec=addvec)
+    done_end = ctypes.c_int(work.cursor)
+    with torch.cuda.device(x.device):
+        st = _lib.load().mavlm_gemm_fill_fwd(ctypes.byref(prim.desc), ctypes.byref(work.desc), work.cursor, work.total,
+                                             ctypes.byref(done_end), prim.code, _stream())
+    _lib.check(st, "gemm_fill_fwd")
+    work.cursor = done_end.value
     if out is not None:
         return out
     return out2.reshape(*lead, n)

@@ -41,7 +41,8 @@ class VisualMemoryPipeline(nn.Module):
                  memory_fuser: "MemoryFuserMLP | MemoryFuser", positional_encoding: TemporalPositionalEncoding,
                  token_type_embedding: nn.Embedding, image_newline: torch.Tensor, embed_tokens: nn.Embedding,
                  chunk_size: int = 32, max_fine_frames: int = 32, num_patches_per_side: int = 27,
-                 pool_stride: int = 2, projector_frames_per_pass: int = 64, pool_before_w2: bool = True):
+                 pool_stride: int = 2, projector_frames_per_pass: int = 64, pool_before_w2: bool = True,
+                 tail_fill: bool = True):
         super().__init__()
         self.mm_projector = mm_projector
         self.recurrent_memory_transformer = recurrent_memory_transformer
@@ -57,6 +58,10 @@ class VisualMemoryPipeline(nn.Module):
         self.projector_frames_per_pass = projector_frames_per_pass
         self.pool_before_w2 = pool_before_w2
         self.pool_mode = "bilinear"
+        # one video, tensor-core tier: the frame-side K/V projection of chunk t+1 and the fuser MLP of finished states
+        # are computed in the idle tile slots of chunk t's 1568-row GEMMs (ops.linear_fill) instead of in launches of
+        # their own; same results bit for bit
+        self.tail_fill = tail_fill
         self._consts: Dict = {}
 
     # ------------------------------------------------------------------------------------------
@@ -154,7 +159,14 @@ class VisualMemoryPipeline(nn.Module):
         dhp = packs[0]["dhp"]
         hd = heads * dhp
         wf, bf = self._formation_kv_weights()
-        if piece_frames is None:
+        fz = self.memory_fuser
+        fill = (self.tail_fill and b == 1 and dtype != torch.float32 and piece_frames is None
+                and not isinstance(fz, MemoryFuser) and d % 8 == 0)
+        kv_work: List = []
+        fillers: List = []                                              # GemmWork in the order they should be picked
+        if fill:
+            kvf = torch.empty((b, f * p, wf.shape[0]), dtype=dtype, device=dev)
+        elif piece_frames is None:
             kvf = ops.linear(z2, wf, bf)                                # [B, F*P, depth*2*hd]
         else:
             if b != 1 or boundaries is not None or piece_frames % self.chunk_size != 0:
@@ -169,6 +181,17 @@ class VisualMemoryPipeline(nn.Module):
                 raise ValueError(f"mavlm: chunk boundaries must rise from 0 to the frame count {f}, got {bounds}")
         n_chunks = len(bounds) - 1
         n_keep = min(n_chunks, cap)
+        first = n_chunks - n_keep
+        if fill:
+            kv_work = [ops.GemmWork(z2[0, bounds[t] * p: bounds[t + 1] * p], wf, bf, kvf[0, bounds[t] * p: bounds[t + 1] * p])
+                       for t in range(n_chunks)]
+            kv_work[0].run()
+            n_fine = min(self.max_fine_frames, f)
+            if seq_out is None:
+                seq_out = torch.empty((b, self.sequence_length(n_keep, n_fine, drop_frames), d), dtype=dtype, device=dev)
+            fuse_hidden = torch.empty((n_keep, lq, fz[0].weight.shape[0]), dtype=dtype, device=dev)
+            fuse_work: List = []
+        lin = ops.linear_fill if fill else (lambda *a, fillers=(), **k: ops.linear(*a, **k))
         evo = rmt.memory_update_attention
         evo_p = evo.packed()
         ring_states = torch.empty((b, cap, lq, d), dtype=dtype, device=dev)
@@ -195,7 +218,12 @@ class VisualMemoryPipeline(nn.Module):
                 q = ring_qkv[:, prev * lq:(prev + 1) * lq, :hd]
                 kv = ring_qkv[:, : n * lq]
                 ctx, _, _ = ops.xattn(q, kv[..., hd:2 * hd], kv[..., 2 * hd:], heads, head_dim=dhp, scale=scale)
-                mem = evo.residual(ctx, mem, weight=evo_p["wo"])
+                mem = evo.residual(ctx, mem, weight=evo_p["wo"], fillers=fillers)
+            if fill:
+                # what may ride in this chunk's GEMM tails: what is left of THIS chunk's frame K/V (needed by the first
+                # attention below), then the NEXT chunk's, then the fuser MLP of finished states (up; down once its up
+                # is complete)
+                fillers = kv_work[t:t + 2] + [w_ for w_ in fuse_work if not w_.done]
             r0, r1 = bounds[t] * p, bounds[t + 1] * p
             if piece_frames is not None and bounds[t] % piece_frames == 0:   # first chunk of a piece: its frames' K/V
                 j = bounds[t] // piece_frames
@@ -206,24 +234,36 @@ class VisualMemoryPipeline(nn.Module):
             for li, layer in enumerate(rmt.layers):
                 pk = packs[li]
                 att = layer.memory_segment_fusion_attention
-                q = ops.linear(mem, pk["wq"], pk["bq"])
+                q = lin(mem, pk["wq"], pk["bq"], fillers=fillers)
+                if fill and li == 0:
+                    kv_work[t].run()                                    # this chunk's frame K/V: whatever the tails left
                 kcol = li * 2 * hd
                 ctx, _, _ = ops.xattn(q, kvf[:, r0:r1, kcol:kcol + hd], kvf[:, r0:r1, kcol + hd:kcol + 2 * hd], heads,
                                       head_dim=dhp, scale=scale)
-                a = att.residual(ctx, mem, weight=pk["wo"])
-                up = ops.linear(a, layer.mlp[0].weight, layer.mlp[0].bias, act=layer._act)
+                a = att.residual(ctx, mem, weight=pk["wo"], fillers=fillers)
+                up = lin(a, layer.mlp[0].weight, layer.mlp[0].bias, act=layer._act, fillers=fillers)
                 if li == last_layer and b == 1:                         # the new state is normalised straight into its ring slot
-                    mem = layer.residual(up, a, out=ring_states[:, slot])
+                    mem = layer.residual(up, a, out=ring_states[:, slot], fillers=fillers)
                 else:
-                    mem = layer.residual(up, a)
+                    mem = layer.residual(up, a, fillers=fillers)
             if b != 1:
                 ring_states[:, slot].copy_(mem)
+            if fill and t >= first:
+                # the state just written stays in its ring slot to the end (t + cap >= n_chunks): its fuser MLP
+                # (llava_arch.py:545-546) becomes filler for the chunks that follow; rows land at their final position
+                i_seq = t - first
+                npm_ = len(MEMORY_PROMPT_IDS)
+                up_w = ops.GemmWork(ring_states[0, slot], fz[0].weight, fz[0].bias, fuse_hidden[i_seq], act=ACT_GELU_ERF)
+                dn_w = ops.GemmWork(fuse_hidden[i_seq], fz[2].weight, fz[2].bias,
+                                    seq_out[0, npm_ + i_seq * lq: npm_ + (i_seq + 1) * lq],
+                                    addvec=self.token_type_embedding.weight.detach()[0], after=up_w)
+                fuse_work += [up_w, dn_w]
             if t + 1 < n_chunks:                                        # project the new state once for later chunks
                 for bi in range(b):
-                    ops.linear(mem[bi], w_evo, b_evo, out=ring_qkv[bi, slot * lq:(slot + 1) * lq])
+                    lin(mem[bi], w_evo, b_evo, out=ring_qkv[bi, slot * lq:(slot + 1) * lq],
+                        fillers=[w_ for w_ in fuse_work if not w_.done] if fill else ())
 
         # fuser + assembly: state written at chunk t sits in slot t % cap; reference order is oldest first
-        first = n_chunks - n_keep
         n_fine = min(self.max_fine_frames, f)
         fkey = ("fine", f, str(dev))
         if fkey not in self._consts:                                    # cached: no H2D copy on the hot path / in graphs
@@ -235,7 +275,20 @@ class VisualMemoryPipeline(nn.Module):
         pm_ids, pf_ids = self._const_ids(dev)
         emb = self.token_type_embedding.weight.detach()
         npm = len(MEMORY_PROMPT_IDS)
-        fz = self.memory_fuser
+        if fill:
+            # whatever the tails did not absorb: the remaining fuser tiles (each launch takes a ready filler along)
+            for w_ in fuse_work:
+                w_.run(fillers=[o_ for o_ in fuse_work if not o_.done])
+            ops.assemble(seq_out[0], None, n_keep * lq, z[0], fine_idx, p, emb, self.image_newline.detach(),
+                         self.embed_tokens.weight.detach(), pm_ids, pf_ids, drop_frames)
+            out = {"sequence": seq_out}
+            if return_states:
+                if first == 0:
+                    out["states"] = ring_states[:, :n_keep]
+                else:
+                    order = [(first + i) % cap for i in range(n_keep)]
+                    out["states"] = torch.cat([ring_states[:, s_:s_ + 1] for s_ in order], dim=1)
+            return out
         if isinstance(fz, MemoryFuser):
             # encoder-variant fuser (MemoryFuser.py; the mode llava_arch.py:137-143 keeps commented out): self-attention
             # inside each 196-token memory slot, over the cached states oldest first (llava_arch.py:545-546)

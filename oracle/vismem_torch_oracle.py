@@ -163,7 +163,10 @@ def path_gradients(z_np: np.ndarray, w_np: Dict[str, np.ndarray], *, chunk: int,
         n_el += seq.numel()
     loss = total / n_el
     loss.backward()
-    grads = {k: v.grad.detach().numpy() for k, v in w.items() if v.grad is not None}
-    grads["embed.prompt_mem"] = pm.grad.numpy()
-    grads["embed.prompt_frm"] = pf.grad.numpy()
-    return float(loss.detach()), grads, torch.stack(seqs).numpy()
+    def _np(t):                                                             # bf16 (noise-floor runs) has no numpy dtype
+        return t.detach().numpy() if t.dtype in (torch.float32, torch.float64) else t.detach().double().numpy()
+
+    grads = {k: _np(v.grad) for k, v in w.items() if v.grad is not None}
+    grads["embed.prompt_mem"] = _np(pm.grad)
+    grads["embed.prompt_frm"] = _np(pf.grad)
+    return float(loss.detach()), grads, _np(torch.stack(seqs))
