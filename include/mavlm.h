@@ -119,12 +119,22 @@ MAVLM_API int mavlm_layernorm_fwd(const void* x, const void* gamma, const void* 
  * probs never materialised in the bf16 tier.  Q [B, Lq, H*dh] (row stride ldq), K/V [B, Lk, H*dh]
  * (row strides ldk/ldv, batch strides in elements), O [B, Lq, H*dh].  lse (fp32 [B,H,Lq], natural log) may be
  * NULL.  col_scores (fp32 [B, Lk]) if non-NULL receives sum over heads and queries of the normalised
- * probabilities (MemoryController.py:135; fp32 tier only). workspace: see mavlm_xattn_workspace_bytes. */
+ * probabilities (MemoryController.py:135; fp32 tier only -- the bf16 / fp16 tier gets them from mavlm_xattn_colsum).
+ * workspace: see mavlm_xattn_workspace_bytes. */
 MAVLM_API size_t mavlm_xattn_workspace_bytes(int batch, int heads, int lq, int lk, int head_dim, int dtype);
 MAVLM_API int mavlm_xattn_fwd(const void* Q, int64_t ldq, int64_t q_batch_stride, const void* K, int64_t ldk,
                     int64_t k_batch_stride, const void* V, int64_t ldv, int64_t v_batch_stride, void* O, int64_t ldo,
                     int64_t o_batch_stride, float* lse, float* col_scores, int batch, int heads, int lq, int lk,
                     int head_dim, float scale, int dtype, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- frame scores of TransformerProjector.forward (MemoryController.py:135-139: attn_probs.sum(heads).sum(queries)) in
+ * the bf16 / fp16 tier, where the fused attention never forms the probabilities: a second pass over K with the LSE that
+ * mavlm_xattn_fwd saved.  col_scores fp32 [B, Lk] = sum over heads h and queries q of exp(q.k * scale - lse[b,h,q]); every
+ * row of it sums to heads * lq.  One batched tcgen05 GEMM (keys x queries per head) with an exp2 + row-sum epilogue:
+ * half the MMA work of the attention call itself. */
+MAVLM_API int mavlm_xattn_colsum(const void* Q, int64_t ldq, int64_t q_batch_stride, const void* K, int64_t ldk,
+                                 int64_t k_batch_stride, const float* lse, float* col_scores, int batch, int heads, int lq,
+                                 int lk, int head_dim, float scale, int dtype, void* stream);
 
 /* ---- a14 + a15: type embeddings + token assembly (llava_arch.py:548-554, 620-629, 708-731).
  * Writes seq [10 + n_mem_rows + 1 + 9 + n_fine*tokens + 1, D]:

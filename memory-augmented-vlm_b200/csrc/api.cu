@@ -23,6 +23,9 @@ int xattn_bf16_tc(const __nv_bfloat16* Q, long long ldq, long long qb, const __n
                   size_t ws_bytes, cudaStream_t st, int half = 0);
 size_t xattn_bf16_workspace_bytes(int batch, int heads, int lq, int lk, int dh);
 void attn_force_groups(int n);
+int xattn_colsum_tc(const __nv_bfloat16* Q, long long ldq, long long qb, const __nv_bfloat16* K, long long ldk,
+                    long long kb, const float* lse, float* out, int batch, int heads, int lq, int lk, int dh, float scale,
+                    int half, cudaStream_t st);
 }  // namespace mavlm
 
 using namespace mavlm;
@@ -113,6 +116,22 @@ int mavlm_xattn_fwd(const void* Q, int64_t ldq, int64_t q_batch_stride, const vo
                        static_cast<const __nv_bfloat16*>(V), ldv, v_batch_stride, static_cast<__nv_bfloat16*>(O), ldo,
                        o_batch_stride, lse, batch, heads, lq, lk, head_dim, scale, workspace, workspace_bytes, st,
                        dtype == MAVLM_F16 ? 1 : 0);
+}
+
+int mavlm_xattn_colsum(const void* Q, int64_t ldq, int64_t q_batch_stride, const void* K, int64_t ldk,
+                       int64_t k_batch_stride, const float* lse, float* col_scores, int batch, int heads, int lq, int lk,
+                       int head_dim, float scale, int dtype, void* stream) {
+  MAVLM_REQUIRE(batch >= 0 && heads > 0 && lq >= 0 && lk >= 0 && head_dim > 0, MAVLM_E_INVALID, "xattn_colsum: bad shape");
+  MAVLM_REQUIRE(dtype == MAVLM_BF16 || dtype == MAVLM_F16, MAVLM_E_INVALID,
+                "xattn_colsum is the tensor-core tier's second pass; the fp32 tier returns col_scores from mavlm_xattn_fwd");
+  if (batch == 0 || lk == 0) return MAVLM_OK;
+  if (lq == 0) {
+    MAVLM_CUDA_OK(cudaMemsetAsync(col_scores, 0, static_cast<size_t>(batch) * lk * sizeof(float), static_cast<cudaStream_t>(stream)));
+    return MAVLM_OK;
+  }
+  return xattn_colsum_tc(static_cast<const __nv_bfloat16*>(Q), ldq, q_batch_stride, static_cast<const __nv_bfloat16*>(K),
+                         ldk, k_batch_stride, lse, col_scores, batch, heads, lq, lk, head_dim, scale,
+                         dtype == MAVLM_F16 ? 1 : 0, static_cast<cudaStream_t>(stream));
 }
 
 /* development knob (not part of the reference-facing surface): force the GEMM tile (0 = heuristic).

@@ -48,6 +48,12 @@ struct GemmTcParams {
   // tail fill (problem 2 of a launch only): the workers that would idle in the primary's last wave -- workers
   // [fill_first_idle, workers) -- walk this problem's tiles tile_begin + (worker - fill_first_idle) + k * fill_n_idle
   int fill_first_idle, fill_n_idle;
+  // EPI = 1 (probability column sums, MemoryController.py:135): rows = keys, columns = queries of one (batch, head)
+  // problem; the epilogue adds sum_q exp2(c * cs_scale_log2 - lse[q] * log2 e) of its columns to cs_out[b][key]
+  const float* cs_lse;   // [batches][N] natural-log LSE of the attention forward
+  float* cs_out;         // [outer][cs_out_stride] (summed over the inner = head problems and all query tiles)
+  float cs_scale_log2;
+  long long cs_out_stride;
 };
 
 // CG = CTAs per MMA (tcgen05 cta_group): 1 = one CTA owns a 128 x BN tile; 2 = a CTA pair owns a 256 x BN
@@ -87,7 +93,7 @@ __device__ __forceinline__ void gemm_tile_coords(int tile, int m_tiles, int n_ti
 // A_MN / B_MN: the operand is stored with its M (resp. N) index contiguous ([K, M] / [K, N] row-major: the
 // transposed operands of dgrad / wgrad / attention backward).  Such a tile is loaded as 64x64 boxes
 // [64 k-rows x 64 m] and consumed as an MN-major UMMA operand (8-k-row atoms of 1 KB, 64-wide M groups 8 KB apart).
-template <int BN, bool A_MN, bool B_MN, int CG, typename T = __nv_bfloat16>
+template <int BN, bool A_MN, bool B_MN, int CG, typename T = __nv_bfloat16, int EPI = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ GemmTcParams p,
@@ -275,6 +281,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool row_ok = row < pp.M;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::ACC_STRIDE;
 
+      float cs_acc = 0.f;  // EPI == 1: this thread's row (key) sum over the tile's columns (queries)
       // one 32-column chunk of this thread's row: + bias -> activation -> (+ resid) (+ addvec) -> store
       auto emit = [&](const uint32_t (&r)[32], int c) {
         const int nc = n0 + c * 32;
@@ -284,6 +291,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if constexpr (EPI == 1) {
+          // this thread's key against 32 queries: normalised probabilities from the forward's LSE, summed over queries
+          if (row_ok) {
+            const float* l = pp.cs_lse + static_cast<long long>(batch) * pp.N + nc;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (full_chunk || nc + j < pp.N) {
+                float e;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(v[j], pp.cs_scale_log2, -1.44269504088896340736f * __ldg(l + j))));
+                cs_acc += e;
+              }
+            }
+          }
+          return;
+        }
         // v += src[0..32).  `dep`: src was written by the previous kernel (resid) -> ordered load, see ld_dep_u4
         auto add_vec32 = [&](const T* src, bool dep) {
           if (full_chunk) {
@@ -436,6 +458,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           emit(rb, cb + i + 1);
         }
       }
+      if constexpr (EPI == 1) {
+        if (row_ok) atomicAdd(pp.cs_out + (batch / pp.inner) * pp.cs_out_stride + row, cs_acc);
+      }
       if ((acc ^= 1) == 0) acc_phase ^= 1;
     }
     }
@@ -471,7 +496,7 @@ static void gemm_set_tiling(GemmTcParams& p, int bn, int cg) {
 
 // One launch.  `p` must carry its tiling and tile range; `p2` (may be null) is the tail-fill problem with its range
 // and fill_* fields.  `full_grid`: launch every worker even if the primary has fewer tiles (the idle ones fill).
-template <int BN, bool A_MN, bool B_MN, int CG, typename T = __nv_bfloat16>
+template <int BN, bool A_MN, bool B_MN, int CG, typename T = __nv_bfloat16, int EPI = 0>
 static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmTcParams& p,
                           cudaStream_t st, const CUtensorMap* tmA2 = nullptr, const CUtensorMap* tmB2 = nullptr,
                           const CUtensorMap* tmC2 = nullptr, const GemmTcParams* p2 = nullptr, int workers_forced = 0) {
@@ -482,7 +507,7 @@ static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   MAVLM_CUDA_OK(cudaGetDevice(&dev_id));
   bool& configured = configured_dev[dev_id & 63];
   if (!configured) {
-    MAVLM_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN, CG, T>,
+    MAVLM_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN, CG, T, EPI>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
@@ -494,7 +519,7 @@ static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   LaunchCfg lc;
   make_launch(lc, dim3(workers * CG), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, st, CG, 1);
   const int has2 = p2 != nullptr ? 1 : 0;
-  MAVLM_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, gemm_tc_kernel<BN, A_MN, B_MN, CG, T>, tmA, tmB, tmC, p, has2 ? *tmA2 : tmA,
+  MAVLM_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, gemm_tc_kernel<BN, A_MN, B_MN, CG, T, EPI>, tmA, tmB, tmC, p, has2 ? *tmA2 : tmA,
                                    has2 ? *tmB2 : tmB, has2 ? *tmC2 : tmC, has2 ? *p2 : p, has2));
   MAVLM_LAUNCH_OK();
   return MAVLM_OK;
@@ -786,6 +811,37 @@ int gemm_fill_fwd(const mavlm_gemm_desc* prim, const mavlm_gemm_desc* fill, int 
   }
   if (half) return launch_gemm_tc<FILL_BN, false, false, FILL_CG, __half>(tmA, tmB, tmC, p, st);
   return launch_gemm_tc<FILL_BN, false, false, FILL_CG>(tmA, tmB, tmC, p, st);
+}
+
+// Frame scores in the tensor-core tier (MemoryController.py:135-139): out[b][key] = sum over heads and queries of the
+// NORMALISED attention probabilities, from a second pass over K with the forward's LSE -- a batched (b, h) GEMM
+// S^T = K_h Q_h^T (rows = keys on the TMEM lanes, columns = queries) whose epilogue turns every accumulator into
+// exp2(s * scale * log2 e - lse[q] * log2 e) and adds the row sums to out.  Half the MMA work of one attention call, at
+// GEMM efficiency (N = 256 score tiles: the O accumulator that forces 64-key tiles on the attention kernel is absent).
+int xattn_colsum_tc(const __nv_bfloat16* Q, long long ldq, long long qb, const __nv_bfloat16* K, long long ldk,
+                    long long kb, const float* lse, float* out, int batch, int heads, int lq, int lk, int dh, float scale,
+                    int half, cudaStream_t st) {
+  MAVLM_REQUIRE(lq > 0 && lk > 0 && dh > 0 && dh % 8 == 0 && ldq % 8 == 0 && ldk % 8 == 0 && qb % 8 == 0 && kb % 8 == 0,
+                MAVLM_E_INVALID, "xattn_colsum: head_dim and strides must be multiples of 8");
+  MAVLM_REQUIRE(lse != nullptr && out != nullptr && scale > 0.f, MAVLM_E_INVALID, "xattn_colsum: needs the forward's LSE");
+  MAVLM_CUDA_OK(cudaMemsetAsync(out, 0, static_cast<size_t>(batch) * lk * sizeof(float), st));
+  GemmTcParams p{};
+  p.half = half;
+  p.M = lk; p.N = lq; p.K = dh;
+  p.C = out; p.ldc = 4; p.out_f32 = 1;
+  p.batches = batch * heads;
+  p.inner = heads;
+  p.cs_lse = lse; p.cs_out = out; p.cs_scale_log2 = scale * 1.44269504088896340736f; p.cs_out_stride = lk;
+  constexpr int BN = 256;
+  gemm_set_tiling(p, BN, 1);
+  p.tile_begin = 0;
+  p.tile_end = p.m_tiles * p.n_tiles * p.batches;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = make_operand_map(&tmA, K, ldk, lk, dh, false, GEMM_BM, heads, batch, dh, kb))) return rc;
+  if ((rc = make_operand_map(&tmB, Q, ldq, lq, dh, false, BN, heads, batch, dh, qb))) return rc;
+  if (half) return launch_gemm_tc<BN, false, false, 1, __half, 1>(tmA, tmB, tmA, p, st);
+  return launch_gemm_tc<BN, false, false, 1, __nv_bfloat16, 1>(tmA, tmB, tmA, p, st);
 }
 
 // Backward-pass entry (mavlm_gemm_ex, bf16): trans_a = 1 -> A stored [K,M]; trans_b = 0 -> B stored [K,N].

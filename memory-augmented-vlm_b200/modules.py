@@ -90,7 +90,7 @@ class Attention(nn.Module):
     forward returns (output, probs) like the reference; probs is None here because the fused kernel
     never materialises them (the reference's [1,8,Lq,Lk] tensor is 157 MB per layer at 7B).  Column
     sums of the probabilities (all the reference ever derives from them, :135) are available through
-    `col_scores=True` in the fp32 tier."""
+    `col_scores=True` (fp32 tier: fused into the attention; bf16 / fp16 tier: a second tensor-core pass with the LSE)."""
 
     def __init__(self, config):
         super().__init__()
@@ -169,14 +169,21 @@ class Attention(nn.Module):
         k_, v_ = kv_projected[..., :hd], kv_projected[..., hd:]
         grad = torch.is_grad_enabled() and (q.requires_grad or kv_projected.requires_grad)
         fused_scores = col_scores and fp32 and not grad
-        ctx, _, cs = ops.xattn(q, k_, v_, h, head_dim=dhp, scale=scale, want_col_scores=fused_scores)
-        if col_scores and not fused_scores:
-            # frame scores (MemoryController.py:135, detached at :157) need normalised probabilities, which neither
-            # the fused bf16 kernel nor the autograd path forms: diagnostics-only extra pass through the fp32 tier.
+        tc_scores = col_scores and not fp32 and not grad
+        ctx, lse, cs = ops.xattn(q, k_, v_, h, head_dim=dhp, scale=scale, want_col_scores=fused_scores, want_lse=tc_scores)
+        if tc_scores:
+            # frame scores (MemoryController.py:135, detached at :157) need normalised probabilities, which the fused
+            # kernel never forms: a second tensor-core pass over K with the saved LSE (half the attention's MMA work)
+            cs = ops.xattn_colsum(q, k_, lse, h, head_dim=dhp, scale=scale)
+        elif col_scores and not fused_scores:
+            # under autograd (diagnostics only, detached): the same second pass on detached operands
             with torch.no_grad():
-                qf = ops.cast(q.detach(), torch.float32)
-                kf = ops.cast(k_.detach().contiguous(), torch.float32)
-                _, _, cs = ops.xattn(qf, kf, kf, h, head_dim=dhp, scale=scale, want_col_scores=True)
+                qd, kd, vd = q.detach(), k_.detach(), v_.detach()
+                if fp32:
+                    _, _, cs = ops.xattn(qd, kd, vd, h, head_dim=dhp, scale=scale, want_col_scores=True)
+                else:
+                    _, lse_d, _ = ops.xattn(qd, kd, vd, h, head_dim=dhp, scale=scale, want_lse=True)
+                    cs = ops.xattn_colsum(qd, kd, lse_d, h, head_dim=dhp, scale=scale)
         self.last_col_scores = cs
         out = self.residual(ctx, x, weight=p["wo"])
         return out.reshape(hidden_states.shape), None

@@ -366,6 +366,28 @@ def _xattn_raw(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, *,
 
 
 @on_tensor_device
+def xattn_colsum(q: torch.Tensor, k: torch.Tensor, lse: torch.Tensor, heads: int, *, head_dim: Optional[int] = None,
+                 scale: Optional[float] = None) -> torch.Tensor:
+    """Column sums of the normalised attention probabilities over heads and queries -> fp32 [B, Lk]
+    (MemoryController.py:135), tensor-core tier: second pass over K with the LSE of `xattn(..., want_lse=True)`."""
+    _need_cuda(q, k, lse)
+    if q.dim() != 3 or k.dim() != 3 or q.stride(2) != 1 or k.stride(2) != 1:
+        raise RuntimeError("mavlm.xattn_colsum: q, k must be [B, L, H*dh] with a contiguous last dim")
+    b, lq, hd = q.shape
+    lk = k.shape[1]
+    dh = head_dim or hd // heads
+    if scale is None:
+        scale = 1.0 / math.sqrt(dh)
+    if lse.dtype != torch.float32 or tuple(lse.shape) != (b, heads, lq) or not lse.is_contiguous():
+        raise RuntimeError("mavlm.xattn_colsum: lse must be contiguous fp32 [B, H, Lq]")
+    out = torch.empty((b, lk), dtype=torch.float32, device=q.device)
+    st = _lib.load().mavlm_xattn_colsum(_ptr(q), q.stride(1), q.stride(0), _ptr(k), k.stride(1), k.stride(0), _ptr(lse),
+                                        _ptr(out), b, heads, lq, lk, dh, float(scale), dtype_code(q), _stream())
+    _lib.check(st, "xattn_colsum")
+    return out
+
+
+@on_tensor_device
 def pool_pe(x: torch.Tensor, *, side: int, stride: int = 2, mode: str = "bilinear",
             pe_table: Optional[torch.Tensor] = None, frame_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
     """[F, side*side, D] -> [F, out*out, D] (+ pe_table[frame_idx] when given)."""

@@ -42,7 +42,7 @@ class VisualMemoryPipeline(nn.Module):
                  token_type_embedding: nn.Embedding, image_newline: torch.Tensor, embed_tokens: nn.Embedding,
                  chunk_size: int = 32, max_fine_frames: int = 32, num_patches_per_side: int = 27,
                  pool_stride: int = 2, projector_frames_per_pass: int = 64, pool_before_w2: bool = True,
-                 tail_fill: bool = True):
+                 tail_fill: bool = False):
         super().__init__()
         self.mm_projector = mm_projector
         self.recurrent_memory_transformer = recurrent_memory_transformer
@@ -60,7 +60,9 @@ class VisualMemoryPipeline(nn.Module):
         self.pool_mode = "bilinear"
         # one video, tensor-core tier: the frame-side K/V projection of chunk t+1 and the fuser MLP of finished states
         # are computed in the idle tile slots of chunk t's 1568-row GEMMs (ops.linear_fill) instead of in launches of
-        # their own; same results bit for bit
+        # their own; same results bit for bit.  OFF by default: measured at parity on B200 (profiles/r2_fill_bench.json:
+        # the fill tiles take L2 bandwidth the last wave's own tiles were using, and the forced 256 x 256 pair tile costs
+        # the critical GEMM 8 us against the 256 x 192 one the heuristic picks) -- kept as a switch, tested bitwise
         self.tail_fill = tail_fill
         self._consts: Dict = {}
 

@@ -451,23 +451,68 @@ def test_fused_pipeline_with_the_encoder_variant_fuser():
 
 
 def test_frame_scores_bf16_tier():
-    """K9 (MemoryController.py:135-139) in the bf16 tier: frame scores sum to H*Lq/P = 64 and match the oracle."""
-    cfg = M.Config()
-    cfg.mm_hidden_size, cfg.mm_intermediate_size, cfg.depth, cfg.mm_dtype = 896, 3584, 2, torch.float32
-    cfg.frame_scores = True
-    torch.manual_seed(0)
-    rmt = M.TransformerProjector(cfg)
-    w = {"recurrent_memory_transformer." + k: v.detach().bfloat16().double().numpy() for k, v in rmt.state_dict().items()}
-    rmt = rmt.to(DEV).bfloat16()
-    x = torch.randn(6, 196, 896).bfloat16()
-    rmt.memory_cache = []
-    cache, scores = rmt(x.to(DEV))
-    ref_cache, ref_score = O.rmt_chunk(x.double().numpy(), [], w, want_scores=True)
-    assert len(scores) == 1 and scores[0].shape == (6,)
-    assert abs(float(scores[0].sum()) - 64.0) < 0.05
-    assert err(scores[0], ref_score) < BF16_TOL
-    rmt.memory_cache = []
-    assert rmt.frame_attn_scores == []
+    """K9 (MemoryController.py:135-139) in the bf16 tier -- a second tensor-core pass over K with the forward's LSE
+    (mavlm_xattn_colsum): frame scores sum to H*Lq/P = 64 and match the oracle, at OV-0.5B dims (padded heads) and at
+    OV-7B dims (dh 448, one 16-frame chunk)."""
+    for hidden, frames in ((896, 6), (3584, 16)):
+        cfg = M.Config()
+        cfg.mm_hidden_size, cfg.mm_intermediate_size, cfg.depth, cfg.mm_dtype = hidden, 4 * hidden, 2, torch.float32
+        cfg.frame_scores = True
+        torch.manual_seed(0)
+        rmt = M.TransformerProjector(cfg)
+        w = {"recurrent_memory_transformer." + k: v.detach().bfloat16().double().numpy() for k, v in rmt.state_dict().items()}
+        rmt = rmt.to(DEV).bfloat16()
+        x = torch.randn(frames, 196, hidden).bfloat16()
+        rmt.memory_cache = []
+        cache, scores = rmt(x.to(DEV))
+        ref_cache, ref_score = O.rmt_chunk(x.double().numpy(), [], w, want_scores=True)
+        assert len(scores) == 1 and scores[0].shape == (frames,)
+        assert abs(float(scores[0].sum()) - 64.0) < 0.05
+        assert err(scores[0], ref_score) < BF16_TOL, hidden
+        assert err(cache[-1], ref_cache[-1]) < BF16_TOL
+        rmt.memory_cache = []
+        assert rmt.frame_attn_scores == []
+
+
+def test_xattn_colsum_op_sharp_softmax_and_cost():
+    """mavlm_xattn_colsum against the oracle's probabilities on the same bf16 operands (logits x8: peaked rows; ragged
+    key and query tails; batch 2), and its cost: at the OV-7B chunk shape it is a fraction of the attention call."""
+    torch.manual_seed(11)
+    h = 8
+    for dh, lq, lk in ((448, 300, 1568 + 72), (128, 1568, 520)):
+        q = (torch.randn(2, lq, h * dh) * 8.0).bfloat16()
+        k = torch.randn(2, lk, h * dh).bfloat16()
+        v = torch.randn(2, lk, h * dh).bfloat16()
+        _, lse, _ = ops.xattn(q.to(DEV), k.to(DEV), v.to(DEV), h, want_lse=True)
+        cs = ops.xattn_colsum(q.to(DEV), k.to(DEV), lse, h)
+        assert cs.shape == (2, lk) and cs.dtype == torch.float32
+        for b in range(2):
+            qd, kd = (t[b].double().numpy().reshape(-1, h, dh).transpose(1, 0, 2) for t in (q, k))
+            pr = O.softmax_lastdim(qd @ kd.transpose(0, 2, 1) / np.sqrt(dh))
+            ref = pr.sum(axis=0).sum(axis=0)
+            assert err(cs[b], ref) < BF16_TOL, (dh, b)
+            assert abs(float(cs[b].sum()) - h * lq) < 1e-3 * h * lq
+    dh, lq, lk = 448, 1568, 6272
+    q = torch.randn(1, lq, h * dh, device=DEV).bfloat16()
+    k = torch.randn(1, lk, h * dh, device=DEV).bfloat16()
+    v = torch.randn(1, lk, h * dh, device=DEV).bfloat16()
+    _, lse, _ = ops.xattn(q, k, v, h, want_lse=True)
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 10
+
+    t_attn = timed(lambda: ops.xattn(q, k, v, h, want_lse=True))
+    t_cs = timed(lambda: ops.xattn_colsum(q, k, lse, h))
+    print(f"attention {t_attn * 1e3:.0f} us, column-sum pass {t_cs * 1e3:.0f} us ({t_cs / t_attn:.2f}x)")
+    assert t_cs < 1.3 * t_attn
 
 
 # ---- fp16: the reference inference loader's default dtype (builder.py:27), SURVEY.md §8f-2 ----
@@ -573,3 +618,41 @@ def test_tensors_on_a_non_current_device_run_on_their_own_device():
     assert err(res["sequence"][0], ref["sequence"]) < FP32_TOL
     with pytest.raises(RuntimeError, match="different CUDA devices"):
         ops.linear(torch.zeros(4, 8, device="cuda:0"), torch.zeros(16, 8, device="cuda:1"))
+
+
+def test_tail_fill_is_bitwise_equal_to_separate_launches():
+    """mavlm_gemm_fill_fwd / mavlm_gemm_tiles_fwd: a GEMM walked as the filler of several critical-path launches plus a
+    final range launch equals one plain launch bit for bit, the primaries too; and the whole pipeline with
+    tail_fill=True (next chunk's frame K/V and finished states' fuser MLP riding in the 1568-row GEMMs' tails) equals
+    the default path bit for bit."""
+    torch.manual_seed(0)
+    lib = M._lib.load()
+    x = torch.randn(1568, 896, device=DEV).bfloat16()
+    w = (torch.randn(1024, 896, device=DEV) / 30).bfloat16()
+    b = torch.randn(1024, device=DEV).bfloat16()
+    zf = torch.randn(3000, 896, device=DEV).bfloat16()                           # ragged: 12 row tiles, the last one partial
+    wk = (torch.randn(2056, 896, device=DEV) / 30).bfloat16()                    # ragged N
+    bk = torch.randn(2056, device=DEV).bfloat16()
+    lib.mavlm_debug_force_gemm_bn(1256)
+    ref_y = ops.linear(x, w, b, act=2)
+    ref_kv = ops.linear(zf, wk, bk)
+    lib.mavlm_debug_force_gemm_bn(0)
+    out = torch.zeros_like(ref_kv)
+    work = ops.GemmWork(zf, wk, bk, out)
+    assert work.total == 12 * 9 and not work.done
+    n = 0
+    while not work.done and n < 3:
+        y = ops.linear_fill(x, w, b, act=2, fillers=[work])
+        assert torch.equal(y, ref_y)
+        n += 1
+    assert 0 < work.cursor <= work.total
+    work.run()
+    assert work.done and torch.equal(out, ref_kv)
+    assert float((ops.linear(zf, wk, bk).float() - ref_kv.float()).abs().max()) == 0.0   # heuristic tile: same k order
+    pipe, _ = synthetic.build_pipeline(896, 1152, dtype=torch.bfloat16, chunk_size=8, device=DEV, cache_size=3)
+    xs = synthetic.synthetic_tower_tokens(1, 40, 1152).to(DEV)                   # 5 chunks, ring of 3 wraps
+    idx = torch.arange(40)[None]
+    plain = pipe(xs, idx)
+    pipe.tail_fill = True
+    filled = pipe(xs, idx)
+    assert torch.equal(plain["sequence"], filled["sequence"]) and torch.equal(plain["states"], filled["states"])
