@@ -23,6 +23,9 @@ int xattn_bf16_tc(const __nv_bfloat16* Q, long long ldq, long long qb, const __n
                   size_t ws_bytes, cudaStream_t st, int half = 0);
 size_t xattn_bf16_workspace_bytes(int batch, int heads, int lq, int lk, int dh);
 void attn_force_groups(int n);
+void attn_pair_force_groups(int n);
+void attn_use_pair_kernel(bool on);
+void attn_pair_set_trace(unsigned long long* buf);
 int xattn_colsum_tc(const __nv_bfloat16* Q, long long ldq, long long qb, const __nv_bfloat16* K, long long ldk,
                     long long kb, const float* lse, float* out, int batch, int heads, int lq, int lk, int dh, float scale,
                     int half, cudaStream_t st);
@@ -143,16 +146,26 @@ MAVLM_API int mavlm_debug_force_gemm_bn(int bn) {
   return MAVLM_OK;
 }
 
-/* development knob: bit 4 (16) turns programmatic dependent launch off (A/B timing of the launch overlap).  No flag
+/* development knob: bit 4 (16) turns programmatic dependent launch off (A/B timing of the launch overlap); bit 6 (64)
+   runs head_dim 448 attention on the CTA-pair kernel (attn_pair.cu: correct, measured slower, kept for A/B).  No flag
    changes what a kernel computes or stores. */
 MAVLM_API int mavlm_debug_set_flags(int flags) {
   pdl_force_off((flags & 16) != 0);
+  attn_use_pair_kernel((flags & 64) != 0);
+  return MAVLM_OK;
+}
+
+/* development knob: event trace of the first CTA pair of the head_dim 448 attention kernel: a DEVICE buffer of
+   2 CTAs x 3 roles x 256 uint64 ((clock64 << 8) | event code), zero-filled by the caller; NULL switches it off */
+MAVLM_API int mavlm_debug_attn_trace(void* device_buffer) {
+  attn_pair_set_trace(static_cast<unsigned long long*>(device_buffer));
   return MAVLM_OK;
 }
 
 /* development knob: force the number of attention CTA groups (0 = as many as fit on the SMs) */
 MAVLM_API int mavlm_debug_force_attn_groups(int n) {
   attn_force_groups(n);
+  attn_pair_force_groups(n);
   return MAVLM_OK;
 }
 

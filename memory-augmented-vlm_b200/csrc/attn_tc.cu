@@ -510,11 +510,27 @@ static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUt
   return MAVLM_OK;
 }
 
+// head_dim 448 can run on the CTA-pair kernel (attn_pair.cu; mavlm_debug_set_flags bit 6).  OFF by default: it is
+// correct (tests/test_gpu_parity.py) but 1.5-1.9x SLOWER than this kernel -- the P tile it ships between the two CTAs
+// (32 KB per 128-key block) moves at ~8 B/cycle over DSMEM stores (profiles/r2_attn_pair_trace.md)
+size_t xattn_pair_workspace_bytes(int batch, int heads, int lq, int lk);
+int xattn_bf16_pair(const __nv_bfloat16* Q, long long ldq, long long qb, const __nv_bfloat16* K, long long ldk, long long kb,
+                    const __nv_bfloat16* V, long long ldv, long long vb, __nv_bfloat16* O, long long ldo, long long ob,
+                    float* lse, int batch, int heads, int lq, int lk, float scale, void* ws, size_t ws_bytes,
+                    cudaStream_t st, int half);
+static bool g_use_pair = false;
+void attn_use_pair_kernel(bool on) { g_use_pair = on; }
+
 size_t xattn_bf16_workspace_bytes(int batch, int heads, int lq, int lk, int dh) {
   const AttnGeom g = attn_geometry(batch, heads, lq, lk);
   const long long slot = static_cast<long long>(ATT_BQ) * dh + 2 * ATT_BQ;
   const size_t ctas = static_cast<size_t>(g.groups) * g.gs;
-  return ctas * slot * sizeof(float) + ctas * sizeof(unsigned int);  // one partial slot + one flag per CTA
+  size_t need = ctas * slot * sizeof(float) + ctas * sizeof(unsigned int);  // one partial slot + one flag per CTA
+  if (dh == 448) {
+    const size_t pair = xattn_pair_workspace_bytes(batch, heads, lq, lk);
+    if (pair > need) need = pair;
+  }
+  return need;
 }
 
 int xattn_bf16_tc(const __nv_bfloat16* Q, long long ldq, long long qb, const __nv_bfloat16* K, long long ldk,
@@ -522,6 +538,9 @@ int xattn_bf16_tc(const __nv_bfloat16* Q, long long ldq, long long qb, const __n
                   long long ob, float* lse, int batch, int heads, int lq, int lk, int dh, float scale, void* ws,
                   size_t ws_bytes, cudaStream_t st, int half) {
   if (batch == 0 || lq == 0) return MAVLM_OK;
+  if (dh == 448 && g_use_pair)
+    return xattn_bf16_pair(Q, ldq, qb, K, ldk, kb, V, ldv, vb, O, ldo, ob, lse, batch, heads, lq, lk, scale, ws, ws_bytes, st,
+                           half);
   MAVLM_REQUIRE(dh == 128 || dh == 448, MAVLM_E_INVALID,
                 "bf16 xattn: head_dim %d not supported by the tcgen05 kernel (128 or 448; 112 is padded to 128 by "
                 "the host packing)", dh);
