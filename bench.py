@@ -407,130 +407,27 @@ def run_ours(args):
     ms_copy = timed(step_copy_only, steps, after=drain_copies)
 
     # ---- instrumented pass: per-launch CUDA-event timing of every op, INSIDE a CUDA graph of the step ----
-    # The step is captured a second time with an external timing event recorded before and after every library
-    # call (event-record nodes on the capture stream), so the intervals are device times of back-to-back
-    # kernels exactly as the timed graph replays run them: no host launch gaps, no allocator stalls.
-    recs = []                                               # (family, work, bytes, e0, e1, tag)
-    orig = {name: getattr(ops, name) for name in ("linear", "linear_pe", "xattn", "layernorm", "pool_pe", "add_pe",
-                                                  "add_rows", "assemble")}
-
-    def _events():
-        return (torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True))
-
-    def _nbytes(t):
-        return 0 if t is None else t.numel() * t.element_size()
-
-    def wrap(name, meter):
-        fn0 = orig[name]
-
-        def fn(*a, **kw):
-            if not torch.cuda.is_current_stream_capturing():
-                return fn0(*a, **kw)
-            e0, e1 = _events()
-            e0.record()
-            y = fn0(*a, **kw)
-            e1.record()
-            fam, flops, nbytes, tag = meter(y, *a, **kw)
-            recs.append((fam, flops, nbytes, e0, e1, tag))
-            return y
-        return fn
-
-    def m_linear(y, x, w, b=None, **kw):
-        m = x.numel() // x.shape[-1]
-        return "gemm", 2.0 * m * w.shape[0] * w.shape[1], 0, f"{m}x{w.shape[0]}x{w.shape[1]}"
-
-    def m_linear_pe(y, x, w, b, table, fidx, **kw):
-        m = x.numel() // x.shape[-1]
-        return "gemm", 2.0 * m * w.shape[0] * w.shape[1], 0, f"{m}x{w.shape[0]}x{w.shape[1]}"
-
-    def m_xattn(y, q, k, v, heads, **kw):
-        bq, lq, hd = q.shape
-        lk = k.shape[1]
-        return "xattn", 4.0 * bq * lq * lk * hd, 0, f"B{bq} Lq{lq} Lk{lk} dh{hd // heads}"
-
-    def m_layernorm(y, x, *a, **kw):
-        out = kw.get("out")
-        return "layernorm", 0.0, _nbytes(x) + (_nbytes(out) if out is not None else _nbytes(y)), f"{x.numel() // x.shape[-1]}x{x.shape[-1]}"
-
-    def m_pool(y, x, **kw):
-        return "pool_pe", 0.0, _nbytes(x) + _nbytes(y), f"{x.shape[0]} frames"
-
-    def m_add_pe(y, x, *a, **kw):
-        return "add_pe", 0.0, 2 * _nbytes(x), ""
-
-    def m_assemble(y, seq, mem, n_mem_rows, frames, fine_idx, tokens, *a, **kw):
-        rows = seq.shape[0] - (0 if mem is not None else n_mem_rows)      # rows this launch writes (each read once too)
-        return "assemble", 0.0, 2 * rows * seq.shape[-1] * seq.element_size(), f"{rows} rows"
-
-    meters = {"linear": m_linear, "linear_pe": m_linear_pe, "xattn": m_xattn, "layernorm": m_layernorm,
-              "pool_pe": m_pool, "add_pe": m_add_pe, "add_rows": m_add_pe, "assemble": m_assemble}
-    for name, meter in meters.items():
-        setattr(ops, name, wrap(name, meter))
-    try:
+    # (mavlm_b200.meter: the step is captured a second time with an external timing event around every library call;
+    # medians over >= 100 replays)
+    from mavlm_b200.meter import KERNEL_NAMES, KernelMeter
+    with KernelMeter() as km:
         prof_graph = M.GraphedPipeline(pipe, 1, FRAMES)
-    finally:
-        for name, fn in orig.items():
-            setattr(ops, name, fn)
     prof_graph(x_dev, idx)
     torch.cuda.synchronize()
     prof_steps = max(100, min(steps, 200))
-    per_rec = [[] for _ in recs]
-    prof_ms = []
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for _ in range(prof_steps):
-        e0.record()
-        prof_graph(None, None)
-        e1.record()
-        torch.cuda.synchronize()
-        prof_ms.append(e0.elapsed_time(e1))
-        for i, (_, _, _, a, b, _) in enumerate(recs):
-            per_rec[i].append(a.elapsed_time(b))
-    rec_ms = [_median(v) for v in per_rec]                  # median duration of each launch over the replays
-    step_ms_prof = _median(prof_ms)
+    km.collect(lambda: prof_graph(None, None), prof_steps)
+    step_ms_prof = km.step_ms
     peaks = measured_peaks()
     timed_region_s = ms_total * 1e-3
     burst_applies = timed_region_s < 1.0                    # a sub-second timed region runs at burst clocks
     tpeak = peaks["tflops_burst"] if burst_applies else peaks["tflops_sustained"]
     tpeak_name = "burst" if burst_applies else "sustained"
-    fams = {}
-    for (fam, flops, nbytes, _, _, tag), ms in zip(recs, rec_ms):
-        f = fams.setdefault(fam, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
-        f["launches"] += 1
-        f["ms"] += ms
-        f["flops"] += flops
-        f["bytes"] += nbytes
-    kernel_names = {"gemm": "gemm_tc_kernel (tcgen05 bf16 GEMM, all epilogues)", "xattn": "attn_tc_kernel<448> (tcgen05 flash cross-attention)",
-                    "layernorm": "layernorm_kernel", "pool_pe": "pool_pe_kernel", "add_pe": "add_pe_kernel",
-                    "assemble": "assemble_kernel"}
-    roofline_kernels = []
-    for fam, f in fams.items():
-        if f["ms"] <= 0:
-            continue
-        ent = {"kernel": kernel_names.get(fam, fam), "launches_per_step": f["launches"], "ms_per_step": f["ms"],
-               "share_of_step": f["ms"] / step_ms_prof if step_ms_prof > 0 else None}
-        if f["flops"] > 0:
-            ach = f["flops"] / (f["ms"] * 1e-3) / 1e12
-            ent.update({"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak,
-                        "frac_of_burst": ach / peaks["tflops_burst"], "frac_of_sustained": ach / peaks["tflops_sustained"],
-                        "gflop_per_step": f["flops"] / 1e9})
-        else:
-            ach = f["bytes"] / (f["ms"] * 1e-3) / 1e9
-            ent.update({"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": ach / peaks["hbm_gbs"], "mbytes_per_step": f["bytes"] / 1e6})
-        roofline_kernels.append(ent)
-    roofline_kernels.sort(key=lambda e: -e["ms_per_step"])
+    fams = km.families()
+    kernel_names = KERNEL_NAMES
+    roofline_kernels = km.roofline_kernels(tpeak, peaks)
     breakdown = {fam: {"ms_per_step": f["ms"], "share": f["ms"] / step_ms_prof} for fam, f in fams.items()}
-    by_shape = {}
-    for (fam, flops, _, _, _, tag), ms in zip(recs, rec_ms):
-        if fam not in ("gemm", "xattn"):
-            continue
-        t = by_shape.setdefault((fam, tag), [0, 0.0, flops])
-        t[0] += 1
-        t[1] += ms
-    gemm_shapes = {tag: {"launches_per_step": c, "us": 1e3 * ms / c, "tflops": fl / (ms / c * 1e-3) / 1e12}
-                   for (fam, tag), (c, ms, fl) in by_shape.items() if fam == "gemm"}
-    attn_shapes = {tag: {"launches_per_step": c, "us": 1e3 * ms / c, "tflops": fl / (ms / c * 1e-3) / 1e12}
-                   for (fam, tag), (c, ms, fl) in by_shape.items() if fam == "xattn"}
+    gemm_shapes = km.shapes("gemm")
+    attn_shapes = km.shapes("xattn")
     g = fams.get("gemm", {"launches": 0, "ms": 0.0, "flops": 0.0})
     achieved = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
     traffic = None
