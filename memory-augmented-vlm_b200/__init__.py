@@ -18,12 +18,13 @@ from . import preprocess  # noqa: F401
 from . import legacy  # noqa: F401  (Flash-VStream-style memories, scene segmentation)
 from .preprocess import SigLipImageProcessor, frames_preprocess
 from .splice import IGNORE_INDEX, IMAGE_TOKEN_INDEX, splice_text_and_vision
-from .pipeline import (FRAME_PROMPT_IDS, MEMORY_PROMPT_IDS, GraphedPipeline, HostStreamEncoder,
+from .pipeline import (FRAME_PROMPT_IDS, MEMORY_PROMPT_IDS, GraphedPipeline, GraphedTrainStep, HostStreamEncoder,
                        VisualMemoryPipeline)
+from . import dist  # noqa: F401  (video sharding, frame-sharded pre-pass)
 
 __all__ = [
     "Attention", "Config", "MemoryFuser", "MemoryFuserMLP", "Residual", "TemporalPositionalEncoding", "TransformerLayer",
     "TransformerProjector", "VisionProjector", "build_memory_fuser", "build_vision_projector", "fine_frame_indices",
-    "get_2dPool", "sample_frame_indices", "uniform_segment_variant", "VisualMemoryPipeline", "GraphedPipeline", "HostStreamEncoder", "MEMORY_PROMPT_IDS",
+    "get_2dPool", "sample_frame_indices", "uniform_segment_variant", "VisualMemoryPipeline", "GraphedPipeline", "GraphedTrainStep", "HostStreamEncoder", "MEMORY_PROMPT_IDS",
     "FRAME_PROMPT_IDS", "SigLipImageProcessor", "frames_preprocess", "patch_llava", "convert_rmt", "splice_text_and_vision", "IGNORE_INDEX", "IMAGE_TOKEN_INDEX",
 ]

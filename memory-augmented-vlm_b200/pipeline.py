@@ -74,6 +74,15 @@ class VisualMemoryPipeline(nn.Module):
                                  torch.tensor(FRAME_PROMPT_IDS, dtype=torch.int64, device=device))
         return self._consts[key]
 
+    def prepare_constants(self, frames: int, device) -> None:
+        """Fill the small index caches (prompt ids, fine-frame pick) for videos of `frames` frames on `device`, so that a
+        later CUDA-graph capture of memory_forward at that length contains no host-to-device copy."""
+        dev = torch.device(device)
+        self._const_ids(dev)
+        fkey = ("fine", frames, str(dev))
+        if fkey not in self._consts:
+            self._consts[fkey] = fine_frame_indices(frames, self.max_fine_frames).to(dev)
+
     def sequence_length(self, n_states: int, n_fine: int, drop_frames: bool = False) -> int:
         rmt = self.recurrent_memory_transformer
         lq = rmt.num_memory_tokens * rmt.patch_size
@@ -412,6 +421,10 @@ class VisualMemoryPipeline(nn.Module):
         return {"sequence": seq,
                 "states": torch.stack([s_.reshape(b, m_slots, p, d) for s_ in states], dim=1)}
 
+    def graphed_train(self, batch: int, frames: int, loss_fn=None) -> "GraphedTrainStep":
+        """CUDA-graph replay of one training step (forward + loss + backward) for a fixed (batch, frames)."""
+        return GraphedTrainStep(self, batch, frames, loss_fn)
+
     def graphed(self, batch: int, frames: int, *, return_states: bool = False) -> "GraphedPipeline":
         """CUDA-graph replay of forward() for a fixed (batch, frames): the ~45 dependent launches of a step
         become one graph launch (the recurrence is launch-latency sensitive: ~25 kernels per chunk)."""
@@ -419,6 +432,54 @@ class VisualMemoryPipeline(nn.Module):
         if key not in self._consts:
             self._consts[key] = GraphedPipeline(self, batch, frames, return_states=return_states)
         return self._consts[key]
+
+
+class GraphedTrainStep:
+    """One TRAINING step of the path -- memory_forward_train, the loss and the whole backward (BPTT through the chunks)
+    -- captured into ONE CUDA graph (BASELINE config[3]; the reference runs this step under PyTorch autograd,
+    train.py:1694-1728).  The ~600 launches of a step are issued by the autograd engine from Python otherwise, which
+    leaves host gaps between kernels.  Static input buffer `z` [B, F, P, D] (pooled + PE'd frames, detached as in
+    llava_arch.py:302); gradients land in the parameters' .grad (static tensors, overwritten by every replay);
+    `loss_fn(sequence) -> scalar` defaults to the mean square the parity tests use."""
+
+    def __init__(self, pipe: VisualMemoryPipeline, batch: int, frames: int, loss_fn=None, warmup: int = 3):
+        rmt = pipe.recurrent_memory_transformer
+        p0 = rmt.initial_memory
+        dev = p0.device
+        dtype = pipe.memory_fuser[0].weight.dtype
+        self.pipe, self.dev = pipe, dev
+        self.loss_fn = loss_fn or (lambda seq: (seq.float() ** 2).mean())
+        self.z = torch.zeros((batch, frames, rmt.patch_size, rmt.hidden_size), dtype=dtype, device=dev)
+        self.params = [p_ for p_ in pipe.parameters() if p_.requires_grad]
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    self._zero()
+                    self.loss_fn(pipe.memory_forward_train(self.z)["sequence"]).backward()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self._zero()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                out = pipe.memory_forward_train(self.z)
+                self.sequence = out["sequence"]
+                self.loss = self.loss_fn(self.sequence)
+                self.loss.backward()
+
+    def _zero(self):
+        for p_ in self.params:
+            p_.grad = None
+
+    def __call__(self, z: Optional[torch.Tensor] = None):
+        """Replay on z (copied into the static buffer; None = keep its contents).  Returns (loss, sequence): device
+        tensors that the next replay overwrites."""
+        with torch.cuda.device(self.dev):
+            if z is not None and z is not self.z:
+                self.z.copy_(z.reshape(self.z.shape), non_blocking=True)
+            self.graph.replay()
+        return self.loss, self.sequence
 
 
 class GraphedPipeline:

@@ -50,6 +50,7 @@ def run_point(batch, frames, chunk, slots, iters=3, peaks=None):
         pipe.memory_forward(z[:, : 2 * chunk], return_states=False)
         pipe.memory_forward(z[:, : 2 * chunk], return_states=False)
     torch.cuda.current_stream().wait_stream(side)
+    pipe.prepare_constants(frames, z.device)
     torch.cuda.synchronize()
     with KernelMeter() as km:
         graph = torch.cuda.CUDAGraph()

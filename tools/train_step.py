@@ -61,10 +61,26 @@ def main():
         for _ in range(args.iters):
             loss = step()
         torch.cuda.synchronize()
-        ms = (time.perf_counter() - t0) / args.iters * 1e3
+        ms_eager = (time.perf_counter() - t0) / args.iters * 1e3
+        eager_grads = {n_: p_.grad.detach().clone() for n_, p_ in pipe.named_parameters() if p_.grad is not None}
+        # the same step as ONE CUDA graph (forward + loss + backward), device-timed
+        gstep = pipe.graphed_train(args.batch, frames)
+        gstep(z)
+        torch.cuda.synchronize()
+        same = all(torch.equal(p_.grad, eager_grads[n_]) for n_, p_ in pipe.named_parameters() if p_.grad is not None)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(max(args.iters, 5)):
+            gstep(None)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / max(args.iters, 5)
+        loss = float(gstep.loss)
+        del gstep
         gf = 3.0 * args.batch * fwd_gflop(frames, 32, d)
         n_grads = sum(p_.grad is not None for p_ in pipe.parameters())
         rec = {"dims": args.dims, "batch": args.batch, "frames": frames, "ms_per_step": ms,
+               "ms_per_step_eager_autograd": ms_eager, "graph_grads_equal_eager_bitwise": same,
                "frames_per_s": args.batch * frames / ms * 1e3, "algorithmic_tflops_fwd_bwd": gf / ms,
                "params_with_grad": n_grads, "loss": loss,
                "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
