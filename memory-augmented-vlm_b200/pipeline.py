@@ -368,7 +368,8 @@ class VisualMemoryPipeline(nn.Module):
         scale = 1.0 / math.sqrt(d // heads)
         cap = rmt.cache_size
         pm_ids, pf_ids = self._const_ids(dev)
-        fine_idx = fine_frame_indices(f, self.max_fine_frames).to(dev)
+        self.prepare_constants(f, dev)                                  # cached: no H2D copy inside a captured step
+        fine_idx = self._consts[("fine", f, str(dev))]
         emb = self.token_type_embedding.weight
         newline = self.image_newline
         fz = self.memory_fuser
