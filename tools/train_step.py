@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--frames", type=int, nargs="+", default=[32, 64])
     ap.add_argument("--iters", type=int, default=2)
+    ap.add_argument("--no-graph", action="store_true", help="eager autograd only (the run that is put under ncu)")
     args = ap.parse_args()
     d = synthetic.OV_DIMS[args.dims]
     pipe, _ = synthetic.build_pipeline(d, 1152, dtype=torch.bfloat16, chunk_size=32, device="cuda:0")
@@ -63,24 +64,28 @@ def main():
         torch.cuda.synchronize()
         ms_eager = (time.perf_counter() - t0) / args.iters * 1e3
         eager_grads = {n_: p_.grad.detach().clone() for n_, p_ in pipe.named_parameters() if p_.grad is not None}
-        # the same step as ONE CUDA graph (forward + loss + backward), device-timed
-        gstep = pipe.graphed_train(args.batch, frames)
-        gstep(z)
-        torch.cuda.synchronize()
-        same = all(torch.equal(p_.grad, eager_grads[n_]) for n_, p_ in pipe.named_parameters() if p_.grad is not None)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(max(args.iters, 5)):
-            gstep(None)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / max(args.iters, 5)
-        loss = float(gstep.loss)
-        del gstep
+        ms, same = ms_eager, None
+        if not args.no_graph:
+            # the same step as ONE CUDA graph (forward + loss + backward), device-timed
+            gstep = pipe.graphed_train(args.batch, frames)
+            gstep(z)
+            torch.cuda.synchronize()
+            # (not bitwise: bias / LayerNorm gradient sums use atomics) worst normalised difference over the tensors
+            same = max(float((p_.grad.float() - eager_grads[n_].float()).abs().max() / eager_grads[n_].float().abs().max().clamp_min(1e-30))
+                       for n_, p_ in pipe.named_parameters() if p_.grad is not None and not n_.endswith("k_proj.bias"))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(max(args.iters, 5)):
+                gstep(None)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / max(args.iters, 5)
+            loss = float(gstep.loss)
+            del gstep
         gf = 3.0 * args.batch * fwd_gflop(frames, 32, d)
         n_grads = sum(p_.grad is not None for p_ in pipe.parameters())
         rec = {"dims": args.dims, "batch": args.batch, "frames": frames, "ms_per_step": ms,
-               "ms_per_step_eager_autograd": ms_eager, "graph_grads_equal_eager_bitwise": same,
+               "ms_per_step_eager_autograd": ms_eager, "graph_vs_eager_worst_grad_diff": same,
                "frames_per_s": args.batch * frames / ms * 1e3, "algorithmic_tflops_fwd_bwd": gf / ms,
                "params_with_grad": n_grads, "loss": loss,
                "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
