@@ -47,6 +47,42 @@ __global__ void __launch_bounds__(256) colsum_t_kernel(const T* __restrict__ x, 
   }
 }
 
+// bf16, N % 8 == 0, 16-byte aligned rows: a warp reads 512 contiguous bytes of a row (8 columns per lane); the eight
+// warps of a block stride the rows.  (The scalar kernel above moves 64 bytes per warp load: 1.7 ms of a 50 ms training
+// step went into bias-gradient sums.)
+__global__ void __launch_bounds__(256) colsum_bf16_vec_kernel(const __nv_bfloat16* __restrict__ x, long long ld,
+                                                              float* __restrict__ out, int M, int N, int rows_per_block) {
+  __shared__ float red[8][256 + 8];
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + lane * 8;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(r0 + rows_per_block, M);
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col < N) {
+#pragma unroll 4
+    for (int r = r0 + wy; r < r1; r += 8) {
+      const uint4 t = __ldg(reinterpret_cast<const uint4*>(x + static_cast<long long>(r) * ld + col));
+      const uint32_t* h = reinterpret_cast<const uint32_t*>(&t);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h[e]));
+        s[2 * e] += f.x;
+        s[2 * e + 1] += f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[wy][lane * 8 + e] = s[e];
+  __syncthreads();
+  const int c = threadIdx.x;  // one column of the block's 256 per thread
+  if (blockIdx.x * 256 + c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][c];
+    atomicAdd(out + blockIdx.x * 256 + c, t);
+  }
+}
+
 __device__ __forceinline__ float block_sum_b(float v, float* red) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -281,6 +317,16 @@ int mavlm_colsum(const void* x, int64_t ld, float* out, int M, int N, int accumu
   if (N == 0) return MAVLM_OK;
   if (!accumulate) MAVLM_CUDA_OK(cudaMemsetAsync(out, 0, static_cast<size_t>(N) * sizeof(float), st));
   if (M == 0) return MAVLM_OK;
+  if (dtype == MAVLM_BF16 && N % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    // enough row blocks to fill the SMs a few times over
+    const int col_blocks = ceil_div(N, 256);
+    int rpb_v = 512;
+    while (rpb_v > 64 && static_cast<long long>(col_blocks) * ceil_div(M, rpb_v) < 4ll * sm_count()) rpb_v >>= 1;
+    colsum_bf16_vec_kernel<<<dim3(col_blocks, ceil_div(M, rpb_v)), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ld, out,
+                                                                                 M, N, rpb_v);
+    MAVLM_LAUNCH_OK();
+    return MAVLM_OK;
+  }
   const int rpb = 256;
   dim3 grid(ceil_div(N, 32), ceil_div(M, rpb));
   dim3 block(32, 8);

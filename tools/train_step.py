@@ -33,6 +33,20 @@ def fwd_gflop(frames, chunk, d, lq=1568, p=196, depth=2, cap=10):
     return fl / 1e9
 
 
+class UpstreamGrad(torch.autograd.Function):
+    """A scalar whose gradient w.r.t. `seq` is the given `dseq` (stands in for the LLM's backward); no extra kernels."""
+
+    @staticmethod
+    def forward(ctx, seq, dseq):
+        ctx.save_for_backward(dseq)
+        return seq.new_zeros(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (dseq,) = ctx.saved_tensors
+        return dseq, None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--dims", default="7b")
@@ -40,6 +54,9 @@ def main():
     ap.add_argument("--frames", type=int, nargs="+", default=[32, 64])
     ap.add_argument("--iters", type=int, default=2)
     ap.add_argument("--no-graph", action="store_true", help="eager autograd only (the run that is put under ncu)")
+    ap.add_argument("--upstream-grad", action="store_true",
+                    help="backward from a fixed d(sequence) as the LLM would hand it over (no loss kernels in the step) "
+                         "instead of the parity tests' mean-square loss")
     args = ap.parse_args()
     d = synthetic.OV_DIMS[args.dims]
     pipe, _ = synthetic.build_pipeline(d, 1152, dtype=torch.bfloat16, chunk_size=32, device="cuda:0")
@@ -48,11 +65,24 @@ def main():
         g = torch.Generator(device="cuda:0").manual_seed(1234)
         z = torch.randn(args.batch, frames, 196, d, device="cuda:0", generator=g).bfloat16()
 
+        dseq = None
+
+        def loss_fn(seq):
+            # --upstream-grad: sum(seq * dseq) has d(loss)/d(seq) = dseq, i.e. the backward starts from a given upstream
+            # gradient (one fused multiply-reduce instead of the three fp32 passes of the mean-square loss)
+            nonlocal dseq
+            if not args.upstream_grad:
+                return (seq.float() ** 2).mean()
+            if dseq is None:
+                gd = torch.Generator(device="cuda:0").manual_seed(77)
+                dseq = (torch.randn(seq.shape, device="cuda:0", generator=gd) * 1e-4).to(seq.dtype)
+            return UpstreamGrad.apply(seq, dseq)
+
         def step():
             for p_ in pipe.parameters():
                 p_.grad = None
             res = pipe.memory_forward_train(z)
-            loss = (res["sequence"].float() ** 2).mean()
+            loss = loss_fn(res["sequence"])
             loss.backward()
             return float(loss)
 
@@ -67,7 +97,7 @@ def main():
         ms, same = ms_eager, None
         if not args.no_graph:
             # the same step as ONE CUDA graph (forward + loss + backward), device-timed
-            gstep = pipe.graphed_train(args.batch, frames)
+            gstep = pipe.graphed_train(args.batch, frames, loss_fn=loss_fn)
             gstep(z)
             torch.cuda.synchronize()
             # (not bitwise: bias / LayerNorm gradient sums use atomics) worst normalised difference over the tensors
@@ -87,7 +117,7 @@ def main():
         rec = {"dims": args.dims, "batch": args.batch, "frames": frames, "ms_per_step": ms,
                "ms_per_step_eager_autograd": ms_eager, "graph_vs_eager_worst_grad_diff": same,
                "frames_per_s": args.batch * frames / ms * 1e3, "algorithmic_tflops_fwd_bwd": gf / ms,
-               "params_with_grad": n_grads, "loss": loss,
+               "params_with_grad": n_grads, "loss": loss, "upstream_grad": bool(args.upstream_grad),
                "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
         out.append(rec)
         print(json.dumps(rec), flush=True)
