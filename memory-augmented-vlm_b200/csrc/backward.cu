@@ -9,6 +9,9 @@ namespace mavlm {
 int gemm_ex_fp32(const float* A, long long lda, int trans_a, const float* B, long long ldb, int trans_b, float* C,
                  long long ldc, int M, int N, int K, float alpha, int accumulate, int outer, int inner,
                  const long long* strides, cudaStream_t st);
+int attn_bwd_scores_gemm(int mode, const __nv_bfloat16* A, long long lda, long long a_batch, const __nv_bfloat16* B,
+                         long long ldb, long long b_batch, __nv_bfloat16* out, const float* vec, int batch, int heads, int M,
+                         int N, int dh, float scale, cudaStream_t st);
 int gemm_ex_bf16(const __nv_bfloat16* A, long long lda, int trans_a, const __nv_bfloat16* B, long long ldb, int trans_b,
                  void* C, long long ldc, int M, int N, int K, int accumulate, int out_f32, int outer, int inner,
                  const long long* s6, cudaStream_t st, int half = 0);
@@ -391,8 +394,8 @@ int mavlm_act_bwd(const void* dy, const void* ref, void* dx, int64_t n, int act,
 size_t mavlm_xattn_bwd_workspace_bytes(int batch, int heads, int lq, int lk, int head_dim, int dtype) {
   (void)head_dim;
   const size_t rows = static_cast<size_t>(batch) * heads * lq;
-  if (dtype == MAVLM_BF16)  // S/dP fp32, P/dS bf16, D fp32
-    return rows * static_cast<size_t>(lk) * (sizeof(float) + 2) + rows * sizeof(float);
+  if (dtype == MAVLM_BF16)  // P / dS bf16 (the fp32 scores and dP live only in TMEM accumulators), D fp32
+    return rows * static_cast<size_t>(lk) * 2 + rows * sizeof(float) + 16;
   return (2 * rows * static_cast<size_t>(lk) + rows) * sizeof(float);  // P, dP/dS, D
 }
 
@@ -410,12 +413,12 @@ int mavlm_xattn_bwd(const void* Q, int64_t ldq, int64_t qb, const void* K, int64
   const long long rows = static_cast<long long>(batch) * heads * lq;
   const long long hs = static_cast<long long>(lq) * lk;
   if (dtype == MAVLM_BF16) {
-    // Unfused tensor-core backward: five batched tcgen05 GEMMs (transposed operands as MN-major UMMA operands)
-    // around three elementwise passes.  Scores and dP are kept in fp32; only P and dS are rounded to bf16.
+    // Tensor-core backward: five batched tcgen05 GEMMs (transposed operands as MN-major UMMA operands); the two
+    // elementwise steps ride in GEMM epilogues -- scores -> P (exp with the forward's LSE) and dP -> dS (in place over P)
+    // are formed from the fp32 accumulators, only P and dS (bf16 GEMM operands) ever reach memory.
     MAVLM_REQUIRE(lk % 8 == 0 && head_dim % 8 == 0, MAVLM_E_INVALID, "xattn_bwd bf16: lk and head_dim must be multiples of 8");
-    float* X = static_cast<float*>(workspace);                                  // S, then dP
-    __nv_bfloat16* Pb = reinterpret_cast<__nv_bfloat16*>(X + rows * lk);        // P, then dS
-    float* Dv = reinterpret_cast<float*>(Pb + rows * lk);
+    __nv_bfloat16* Pb = static_cast<__nv_bfloat16*>(workspace);                 // P, then dS   [B*H, Lq, Lk]
+    float* Dv = reinterpret_cast<float*>(Pb + rows * lk);                       // D = rowsum(dO * O)   [B*H, Lq]
     const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(Q);
     const __nv_bfloat16* k = static_cast<const __nv_bfloat16*>(K);
     const __nv_bfloat16* v = static_cast<const __nv_bfloat16*>(V);
@@ -423,24 +426,16 @@ int mavlm_xattn_bwd(const void* Q, int64_t ldq, int64_t qb, const void* K, int64
     const __nv_bfloat16* go = static_cast<const __nv_bfloat16*>(dO);
     const int dh = head_dim;
     int rc;
-    {  // S = Q K^T (fp32)
-      const long long s6[6] = {qb, dh, kb, dh, hs * heads, hs};
-      if ((rc = gemm_ex_bf16(q, ldq, 0, k, ldk, 1, X, lk, lq, lk, dh, 0, 1, batch, heads, s6, st))) return rc;
-    }
-    probs_bf16_kernel<<<static_cast<unsigned>(rows), 256, 0, st>>>(X, lse, Pb, lk, scale);
-    MAVLM_LAUNCH_OK();
+    // P = exp(Q K^T * scale - lse)
+    if ((rc = attn_bwd_scores_gemm(2, q, ldq, qb, k, ldk, kb, Pb, lse, batch, heads, lq, lk, dh, scale, st))) return rc;
     {  // dV = P^T dO
       const long long s6[6] = {hs * heads, hs, dob, dh, dvb, dh};
       if ((rc = gemm_ex_bf16(Pb, lk, 1, go, lddo, 0, dV, lddv, lk, dh, lq, 0, 0, batch, heads, s6, st))) return rc;
     }
-    {  // dP = dO V^T (fp32, over S)
-      const long long s6[6] = {dob, dh, vb, dh, hs * heads, hs};
-      if ((rc = gemm_ex_bf16(go, lddo, 0, v, ldv, 1, X, lk, lq, lk, dh, 0, 1, batch, heads, s6, st))) return rc;
-    }
     rowdot_bf16_kernel<<<dim3(lq, heads, batch), 128, 0, st>>>(go, lddo, dob, o, ldo, ob, Dv, heads, lq, dh);
     MAVLM_LAUNCH_OK();
-    ds_bf16_kernel<<<static_cast<unsigned>(rows), 256, 0, st>>>(Pb, X, Dv, lk, scale);
-    MAVLM_LAUNCH_OK();
+    // dS = P * (dO V^T - D) * scale, over P
+    if ((rc = attn_bwd_scores_gemm(3, go, lddo, dob, v, ldv, vb, Pb, Dv, batch, heads, lq, lk, dh, scale, st))) return rc;
     {  // dQ = dS K
       const long long s6[6] = {hs * heads, hs, kb, dh, dqb, dh};
       if ((rc = gemm_ex_bf16(Pb, lk, 0, k, ldk, 0, dQ, lddq, lq, dh, lk, 0, 0, batch, heads, s6, st))) return rc;

@@ -306,6 +306,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           return;
         }
+        if constexpr (EPI == 2) {
+          // attention backward, scores -> probabilities: P = exp2(s * scale * log2 e - lse[row] * log2 e), stored in T
+          // (the unfused form wrote the fp32 scores and re-read them in a separate pass)
+          const float l2 = row_ok ? -1.44269504088896340736f * __ldg(pp.cs_lse + static_cast<long long>(batch) * pp.M + row) : 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float e;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(v[j], pp.cs_scale_log2, l2)));
+            v[j] = e;
+          }
+        }
+        if constexpr (EPI == 3) {
+          // attention backward, dP -> dS IN PLACE over P: dS = P * (dP - D[row]) * scale  (cs_lse holds D = rowsum(dO * O),
+          // cs_scale_log2 the plain softmax scale; C holds P on entry and dS on exit -- same thread, same addresses)
+          if (row_ok) {
+            const float dsum = __ldg(pp.cs_lse + static_cast<long long>(batch) * pp.M + row);
+            const T* pr = static_cast<const T*>(pp.C) + c_off + row * pp.ldc + nc;
+            if (full_chunk) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint4 t = ld_dep_u4(reinterpret_cast<const uint4*>(pr) + g);
+                const uint32_t* h = reinterpret_cast<const uint32_t*>(&t);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = Elem16<T>::unpack2(h[e]);
+                  v[g * 8 + 2 * e] = f.x * (v[g * 8 + 2 * e] - dsum) * pp.cs_scale_log2;
+                  v[g * 8 + 2 * e + 1] = f.y * (v[g * 8 + 2 * e + 1] - dsum) * pp.cs_scale_log2;
+                }
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (nc + j < pp.N) v[j] = Elem16<T>::to_float(pr[j]) * (v[j] - dsum) * pp.cs_scale_log2;
+            }
+          }
+        }
         // v += src[0..32).  `dep`: src was written by the previous kernel (resid) -> ordered load, see ld_dep_u4
         auto add_vec32 = [&](const T* src, bool dep) {
           if (full_chunk) {
@@ -842,6 +877,38 @@ int xattn_colsum_tc(const __nv_bfloat16* Q, long long ldq, long long qb, const _
   if ((rc = make_operand_map(&tmB, Q, ldq, lq, dh, false, BN, heads, batch, dh, qb))) return rc;
   if (half) return launch_gemm_tc<BN, false, false, 1, __half, 1>(tmA, tmB, tmA, p, st);
   return launch_gemm_tc<BN, false, false, 1, __nv_bfloat16, 1>(tmA, tmB, tmA, p, st);
+}
+
+// Attention backward with the elementwise passes fused into GEMM epilogues (bf16):
+//   mode 2:  P[b,h] = exp(Q_h K_h^T * scale - lse)                      (bf16 out; was: fp32 scores + a pass over them)
+//   mode 3:  dS[b,h] = P * (dO_h V_h^T - D) * scale, in place over P    (was: fp32 dP + a pass over P and dP)
+// A [rows_a x dh] and B [rows_b x dh] are K-major column slices of [B, L, H*dh] tensors (batch stride, head offset dh);
+// out [batch*heads][M][N] bf16 contiguous; vec [batch*heads][M] fp32 (LSE, natural log, or D).
+int attn_bwd_scores_gemm(int mode, const __nv_bfloat16* A, long long lda, long long a_batch, const __nv_bfloat16* B,
+                         long long ldb, long long b_batch, __nv_bfloat16* out, const float* vec, int batch, int heads, int M,
+                         int N, int dh, float scale, cudaStream_t st) {
+  MAVLM_REQUIRE(mode == 2 || mode == 3, MAVLM_E_INVALID, "attn_bwd_scores_gemm: bad mode");
+  MAVLM_REQUIRE(dh % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && a_batch % 8 == 0 && b_batch % 8 == 0 && N % 8 == 0,
+                MAVLM_E_INVALID, "attention backward: head_dim, key count and strides must be multiples of 8");
+  GemmTcParams p{};
+  p.M = M; p.N = N; p.K = dh;
+  p.C = out; p.ldc = N; p.out_f32 = 0;
+  p.batches = batch * heads;
+  p.inner = heads;
+  p.c_outer = static_cast<long long>(heads) * M * N;
+  p.c_inner = static_cast<long long>(M) * N;
+  p.cs_lse = vec;
+  p.cs_scale_log2 = mode == 2 ? scale * 1.44269504088896340736f : scale;
+  constexpr int BN = 256;
+  gemm_set_tiling(p, BN, 1);
+  p.tile_begin = 0;
+  p.tile_end = p.m_tiles * p.n_tiles * p.batches;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = make_operand_map(&tmA, A, lda, M, dh, false, GEMM_BM, heads, batch, dh, a_batch))) return rc;
+  if ((rc = make_operand_map(&tmB, B, ldb, N, dh, false, BN, heads, batch, dh, b_batch))) return rc;
+  if (mode == 2) return launch_gemm_tc<BN, false, false, 1, __nv_bfloat16, 2>(tmA, tmB, tmA, p, st);
+  return launch_gemm_tc<BN, false, false, 1, __nv_bfloat16, 3>(tmA, tmB, tmA, p, st);
 }
 
 // Backward-pass entry (mavlm_gemm_ex, bf16): trans_a = 1 -> A stored [K,M]; trans_b = 0 -> B stored [K,N].
