@@ -686,3 +686,21 @@ def test_cta_pair_attention_kernel_matches_the_oracle():
                 assert err(lse[bi], ref_lse) < 1e-3 and err(lse1[bi], ref_lse) < 1e-3
     finally:
         lib.mavlm_debug_set_flags(0)
+
+
+def test_frame_sharded_encoder_single_process_equals_the_plain_path():
+    """dist.FrameShardedEncoder without a process group (world 1): the piece-wise schedule (per-piece pre-pass into the
+    gather buffer, per-piece frame K/V projection, ragged last piece) gives the plain pipeline's bits."""
+    from mavlm_b200 import dist as D
+    pipe, _ = synthetic.build_pipeline(896, 1152, dtype=torch.bfloat16, chunk_size=4, device=DEV, cache_size=3)
+    x = synthetic.synthetic_tower_tokens(1, 18, 1152)[0].to(DEV)            # 5 chunks (the last one of 2 frames), ring wraps
+    idx = torch.arange(18) * 7
+    plain = pipe(x[None], idx[None], return_states=True)
+    enc = D.FrameShardedEncoder(pipe, 18)
+    assert enc.world == 1 and enc.piece == 4 and len(enc.sched) == 5
+    got = enc(x, idx, return_states=True)
+    assert torch.equal(got["sequence"], plain["sequence"]) and torch.equal(got["states"], plain["states"])
+    again = enc(x, idx, overlap=False)
+    assert torch.equal(again["sequence"], plain["sequence"])
+    with pytest.raises(ValueError):
+        enc(x, torch.full((18,), 600))                                           # PE index check survives
