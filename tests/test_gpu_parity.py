@@ -492,6 +492,11 @@ def test_xattn_colsum_op_sharp_softmax_and_cost():
             ref = pr.sum(axis=0).sum(axis=0)
             assert err(cs[b], ref) < BF16_TOL, (dh, b)
             assert abs(float(cs[b].sum()) - h * lq) < 1e-3 * h * lq
+    qh, kh, vh = (torch.randn(1, n_, h * 448, device=DEV).half() for n_ in (200, 456, 456))       # fp16: same kernels, F16 operands
+    _, lse_h, _ = ops.xattn(qh, kh, vh, h, want_lse=True)
+    cs_h = ops.xattn_colsum(qh, kh, lse_h, h)
+    s_h = (qh.float().view(200, h, 448).transpose(0, 1) @ kh.float().view(456, h, 448).transpose(0, 1).transpose(1, 2)) / 448 ** 0.5
+    assert err(cs_h[0], s_h.softmax(-1).sum(dim=(0, 1)).double().cpu().numpy()) < FP16_TOL * 4
     dh, lq, lk = 448, 1568, 6272
     q = torch.randn(1, lq, h * dh, device=DEV).bfloat16()
     k = torch.randn(1, lk, h * dh, device=DEV).bfloat16()

@@ -84,7 +84,7 @@ def main():
             res = pipe.memory_forward_train(z)
             loss = loss_fn(res["sequence"])
             loss.backward()
-            return float(loss)
+            return float(loss.detach())
 
         step()
         torch.cuda.synchronize()
