@@ -99,15 +99,23 @@ class KernelMeter:
             return y
         return fn
 
-    def collect(self, replay: Callable[[], None], n: int) -> None:
-        """Replay the metered graph n times; keep the MEDIAN duration of every launch and of the whole step."""
+    def collect(self, replay: Callable[[], None], n: int, burst: int = 0, pause_s: float = 0.0, on_burst=None) -> None:
+        """Replay the metered graph n times; keep the MEDIAN duration of every launch and of the whole step.
+        `burst` > 0: the replays run in bursts of that many with `pause_s` seconds of idle time in between, so that a
+        pass of >= 100 replays stays in the clock regime of a short timed region instead of running into the power cap
+        half-way; `on_burst()` is called at the end of every burst (e.g. to read the SM clock while still loaded)."""
+        import time
         per = [[] for _ in self.recs]
         steps = []
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for _ in range(n):
+        for it in range(n):
+            if burst > 0 and it > 0 and it % burst == 0 and pause_s > 0:
+                time.sleep(pause_s)
             e0.record()
             replay()
             e1.record()
+            if on_burst is not None and burst > 0 and (it + 1) % burst == 0:
+                on_burst()                                              # the burst's last replay is still running
             torch.cuda.synchronize()
             steps.append(e0.elapsed_time(e1))
             for i, (_, _, _, a, b, _) in enumerate(self.recs):
