@@ -91,15 +91,41 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region.
+
+    Two sources feed the same sample list: an in-process NVML poll every 5 ms (the counters nvidia-smi itself prints;
+    it cannot miss a timed region of a few tens of milliseconds) and `nvidia-smi -lms 50` (the recipe's clocks line),
+    whose start-up can take longer than a short timed region on a fresh box."""
     Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, device_index: int):
-        self.lines = []
+        self.samples = []          # (time, sm_mhz, sm_max_mhz, [reasons], source)
         self.proc = None
         self.t0 = self.t1 = None
+        self._run = True
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = device_index
+            if visible:
+                ids = [v.strip() for v in visible.split(",") if v.strip()]
+                if device_index < len(ids) and ids[device_index].isdigit():
+                    phys = int(ids[device_index])
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": getattr(pynvml, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                    "hw_thermal_slowdown": getattr(pynvml, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(pynvml, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                    "sw_power_cap": getattr(pynvml, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            self._nvml = (pynvml, h, mx, bits)
+            threading.Thread(target=self._poll, daemon=True).start()
+        except Exception:
+            self._nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "50", "-i", str(device_index)], stdout=subprocess.PIPE,
@@ -108,9 +134,28 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        pynvml, h, mx, bits = self._nvml
+        while self._run:
+            try:
+                sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.samples.append((time.time(), sm, mx, [n for n, b in bits.items() if mask & b], "nvml"))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append((time.time(), line.strip()))
+            f = [x.strip() for x in line.strip().split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm, mx = float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            self.samples.append((time.time(), sm, mx,
+                                 [n for n, v in zip(self.NAMES, f[4:8]) if v.lower().startswith("active")], "nvidia-smi"))
 
     def mark_start(self):
         self.t0 = time.time()
@@ -122,24 +167,22 @@ class ClockSampler:
         if self.proc is not None:
             time.sleep(0.08)
             self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for t, line in self.lines:
-            if self.t0 is None or not (self.t0 - 0.03 <= t <= (self.t1 or t) + 0.08):
+        self._run = False
+        sm, mx, reasons, src = [], [], set(), set()
+        for t, s, m, r, source in list(self.samples):
+            in_region = self.t0 is not None and self.t0 <= t <= (self.t1 or t)
+            # nvidia-smi reports the previous 50 ms window: accept its line up to one period after the region
+            late_smi = source == "nvidia-smi" and self.t0 is not None and self.t0 <= t <= (self.t1 or t) + 0.08
+            if not (in_region or late_smi):
                 continue
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 8:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+            sm.append(s)
+            mx.append(m)
+            reasons.update(r)
+            src.add(source)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm), "source": "+".join(sorted(src))}
 
 
 def oracle_pass(frames: int, chunk: int, weights32, x32, pe_table):
