@@ -99,6 +99,7 @@ PROTOTYPES = {
     "mavlm_debug_set_flags": (c_int, [c_int]),
     "mavlm_debug_force_attn_groups": (c_int, [c_int]),
     "mavlm_debug_attn_trace": (c_int, [c_void_p]),
+    "mavlm_debug_attn_tc_trace": (c_int, [c_void_p]),
 }
 
 _lib = None

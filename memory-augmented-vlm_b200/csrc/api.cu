@@ -26,6 +26,7 @@ void attn_force_groups(int n);
 void attn_pair_force_groups(int n);
 void attn_use_pair_kernel(bool on);
 void attn_pair_set_trace(unsigned long long* buf);
+void attn_tc_set_trace(unsigned long long* buf);
 int xattn_colsum_tc(const __nv_bfloat16* Q, long long ldq, long long qb, const __nv_bfloat16* K, long long ldk,
                     long long kb, const float* lse, float* out, int batch, int heads, int lq, int lk, int dh, float scale,
                     int half, cudaStream_t st);
@@ -159,6 +160,13 @@ MAVLM_API int mavlm_debug_set_flags(int flags) {
    2 CTAs x 3 roles x 256 uint64 ((clock64 << 8) | event code), zero-filled by the caller; NULL switches it off */
 MAVLM_API int mavlm_debug_attn_trace(void* device_buffer) {
   attn_pair_set_trace(static_cast<unsigned long long*>(device_buffer));
+  return MAVLM_OK;
+}
+
+/* development knob: event trace of the single-CTA attention kernel (attn_tc.cu): a DEVICE buffer of
+   grid x 2 roles x 64 uint64 ((clock64 << 8) | event code), zero-filled by the caller; NULL switches it off */
+MAVLM_API int mavlm_debug_attn_tc_trace(void* device_buffer) {
+  attn_tc_set_trace(static_cast<unsigned long long*>(device_buffer));
   return MAVLM_OK;
 }
 

@@ -64,7 +64,17 @@ struct AttnTcParams {
   long long units;      // batch * heads * ngq * kv_blocks  (group-level units)
   float* ws;            // partial slots: [grid] x { O fp32 [DH/32][32][128], m [128], l [128] }
   unsigned int* flags;  // [grid] "this CTA's partial slot is complete" (zeroed by the host before the launch)
+  unsigned long long* trace;  // development: per CTA 2 roles x 64 event stamps (NULL in production)
 };
+
+// development trace: role 0 = MMA issuer, role 1 = lane 0 of the first softmax warp; (clock64 << 8) | code
+#define AT_TR(role, code)                                                                                        \
+  do {                                                                                                           \
+    if (p.trace != nullptr && tr_n < 64) {                                                                       \
+      p.trace[(blockIdx.x * 2 + (role)) * 64 + tr_n] = (static_cast<unsigned long long>(clock64()) << 8) | (code); \
+      ++tr_n;                                                                                                    \
+    }                                                                                                            \
+  } while (0)
 
 template <int DH>
 __host__ __device__ constexpr long long attn_slot_floats() { return static_cast<long long>(ATT_BQ) * DH + 2 * ATT_BQ; }
@@ -97,7 +107,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 template <int DH, typename T = __nv_bfloat16>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-               const __grid_constant__ CUtensorMap tmV, AttnTcParams p) {
+               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, AttnTcParams p) {
   using Cfg = AttnCfg<DH>;
   constexpr int NS = Cfg::NS;
   constexpr int NPS = Cfg::NPS;
@@ -132,6 +142,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     prefetch_tmap(&tmQ);
     prefetch_tmap(&tmK);
     prefetch_tmap(&tmV);
+    prefetch_tmap(&tmO);
     for (int s = 0; s < RING; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
@@ -220,11 +231,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         umma_commit(&o_done[nn & 1]);
       };
       int seg = 0;
+      int tr_n = 0;
+      AT_TR(0, 1);
       for (long long u = u_begin; u < u_end; ++seg) {
         const int item = static_cast<int>(u / J), j0 = static_cast<int>(u - static_cast<long long>(item) * J);
         const int j1 = static_cast<int>(min(static_cast<long long>(J), j0 + (u_end - u)));
         mbar_wait(q_full, seg & 1);
         tc_fence_after();
+        AT_TR(0, 20);
         for (int j = j0; j < j1; ++j, ++n) {
           if (n > 0) {
             mbar_wait(s_free, (n - 1) & 1);
@@ -260,6 +274,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           tc_fence_after();
         }
         issue_pv(n - 1, j1 - j0 == 1);
+        AT_TR(0, 21);
         u += j1 - j0;
       }
     }
@@ -270,14 +285,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
     constexpr int OCH = DH / 64;         // 32-column O chunks per half
     int n = 0;  // key blocks processed by this CTA so far (all segments)
+    int tr_n = (warp == 2 && lane == 0) ? 0 : 64;
+    AT_TR(1, 1);
     for (long long u = u_begin; u < u_end;) {
       const int item = static_cast<int>(u / J), j0 = static_cast<int>(u - static_cast<long long>(item) * J);
       const int j1 = static_cast<int>(min(static_cast<long long>(J), j0 + (u_end - u)));
       const int qt = (item % p.ngq) * p.gs + grp_r, h = (item / p.ngq) % p.heads, b = item / (p.ngq * p.heads);
       float m_used = -INFINITY, l = 0.f;
+      AT_TR(1, 10);
       for (int j = j0; j < j1; ++j, ++n) {
         mbar_wait(s_full, n & 1);
         tc_fence_after();
+        if (j == j0) AT_TR(1, 11);
         uint32_t r[32];
         tmem_ld32(tmem_base + lane_off + Cfg::S_COL + 32 * half, r);
         tmem_ld_wait();
@@ -350,6 +369,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
       // ---- segment epilogue.  row sum = the two halves' partial sums (both used the same m_used)
       // (exchange through the buffer the NEXT key block will not use, so a fast thread cannot overwrite it)
+      AT_TR(1, 12);
       float* xl = xchg + ((n & 1) ^ 1) * (2 * ATT_BQ);
       named_bar_sync(1, 32 * ATT_SM_WARPS);
       xl[half * ATT_BQ + row] = l;
@@ -357,6 +377,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       l += xl[(half ^ 1) * ATT_BQ + row];
       mbar_wait(&o_done[(n - 1) & 1], ((n - 1) >> 1) & 1);  // PV(n-3) known complete (s_full(n-1)): exact as above
       tc_fence_after();
+      AT_TR(1, 13);
       const int q = qt * ATT_BQ + row;
       if (j0 > 0) {
         // ---- later part of an item that starts in an earlier group: unnormalised fp32 O + (m, l) into this CTA's
@@ -378,6 +399,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         __threadfence();
         named_bar_sync(1, 32 * ATT_SM_WARPS);
         if (warp == 2 && lane == 0) st_release_gpu(p.flags + blockIdx.x, 1u);
+        AT_TR(1, 14);
       } else {
         // ---- the part that starts at key block 0 owns the item's result.  If the item continues in later groups
         // (j1 < J) their parts were those groups' first segments: wait for them and fold them in.
@@ -398,6 +420,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             for (int i = 0; i < np; ++i) wait_flag_gpu(p.flags + static_cast<long long>(g_part[i]) * p.gs + grp_r);
           named_bar_sync(1, 32 * ATT_SM_WARPS);
           __threadfence();
+          AT_TR(1, 15);
           for (int i = 0; i < np; ++i) {
             const float* sl = p.ws + (static_cast<long long>(g_part[i]) * p.gs + grp_r) * attn_slot_floats<DH>();
             w_part[i] = ld_cg_f32(sl + static_cast<long long>(ATT_BQ) * DH + row);  // m of that part
@@ -414,7 +437,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
         const float inv = 1.f / l;
         const float own_scale = w_own * inv;
-        T* orow = static_cast<T*>(p.O) + b * p.o_batch + static_cast<long long>(q) * p.ldo + h * DH;
+        // Output rows leave through shared memory and TMA stores (which clip rows >= lq): the warp's 32 rows x 32
+        // columns go to a 64B-swizzled 2 KB tile (thread = row, conflict-free 16-byte writes), double-buffered in
+        // this warp's 4 KB of the two P buffers -- every P V has completed (o_done above) and no warp writes P again
+        // before the next key block's named barrier, which every warp reaches after its last wait_read below.
+        // Direct register stores (32 rows x 16 B per instruction) took ~14 k cycles per segment.
+        uint8_t* out_stage = sP + (warp - 2) * 4096;
 #pragma unroll 1
         for (int c = half * OCH; c < (half + 1) * OCH; ++c) {
           uint32_t o[32];
@@ -430,26 +458,39 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaf(wk, ld_cg_f32(sl + i * ATT_BQ), v[i]);
           }
-          if (q < p.lq) {
+          uint8_t* buf = out_stage + (c & 1) * 2048;
+          if (lane == 0) bulk_wait_read<1>();  // the store issued two chunks ago has read this buffer
+          __syncwarp();
+          uint8_t* dst = buf + lane * 64;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 t;
-              t.x = Elem16<T>::pack2(v[8 * g], v[8 * g + 1]);
-              t.y = Elem16<T>::pack2(v[8 * g + 2], v[8 * g + 3]);
-              t.z = Elem16<T>::pack2(v[8 * g + 4], v[8 * g + 5]);
-              t.w = Elem16<T>::pack2(v[8 * g + 6], v[8 * g + 7]);
-              reinterpret_cast<uint4*>(orow + c * 32)[g] = t;
-            }
+          for (int g = 0; g < 4; ++g) {
+            uint4 t;
+            t.x = Elem16<T>::pack2(v[8 * g], v[8 * g + 1]);
+            t.y = Elem16<T>::pack2(v[8 * g + 2], v[8 * g + 3]);
+            t.z = Elem16<T>::pack2(v[8 * g + 4], v[8 * g + 5]);
+            t.w = Elem16<T>::pack2(v[8 * g + 6], v[8 * g + 7]);
+            *reinterpret_cast<uint4*>(dst + ((g ^ ((lane >> 1) & 3)) << 4)) = t;  // 64B swizzle
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(buf, &tmO, h * DH + c * 32, qt * ATT_BQ + qd * 32, b);
+            bulk_commit();
           }
         }
+        if (lane == 0) bulk_wait_read<0>();
+        __syncwarp();
         if (half == 0 && p.lse != nullptr && q < p.lq)
           p.lse[(static_cast<long long>(b) * p.heads + h) * p.lq + q] = (m_used + log2f(l)) * 0.69314718055994530942f;
       }
       tc_fence_before();
       __syncwarp();
+      AT_TR(1, 16);
       if (lane == 0) mbar_arrive(o_free);
       u += j1 - j0;
     }
+    if (lane == 0) bulk_wait_all();  // every TMA store of this warp has completed
+    AT_TR(1, 2);
   }
   __syncthreads();
   if (warp == 1) {
@@ -488,8 +529,8 @@ static AttnGeom attn_geometry(int batch, int heads, int lq, int lk) {
 }
 
 template <int DH, typename T = __nv_bfloat16>
-static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnTcParams& p,
-                       cudaStream_t st) {
+static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const CUtensorMap& tmO,
+                       const AttnTcParams& p, cudaStream_t st) {
   using Cfg = AttnCfg<DH>;
   static_assert(Cfg::SMEM_BYTES <= 232448, "attention smem budget exceeded");
   static bool configured_dev[64] = {};  // the attribute is per device (one process may drive several GPUs)
@@ -505,7 +546,7 @@ static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUt
     MAVLM_CUDA_OK(cudaMemsetAsync(p.flags, 0, static_cast<size_t>(p.groups) * p.gs * sizeof(unsigned int), st));
   LaunchCfg lc;  // (after a memset node the PDL attribute is inert: the edge is then a full dependency)
   make_launch(lc, dim3(p.groups * p.gs), dim3(ATT_THREADS), Cfg::SMEM_BYTES, st, 1, 2);
-  MAVLM_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, attn_tc_kernel<DH, T>, tmQ, tmK, tmV, p));
+  MAVLM_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, attn_tc_kernel<DH, T>, tmQ, tmK, tmV, tmO, p));
   MAVLM_LAUNCH_OK();
   return MAVLM_OK;
 }
@@ -520,6 +561,8 @@ int xattn_bf16_pair(const __nv_bfloat16* Q, long long ldq, long long qb, const _
                     cudaStream_t st, int half);
 static bool g_use_pair = false;
 void attn_use_pair_kernel(bool on) { g_use_pair = on; }
+static unsigned long long* g_attn_trace = nullptr;
+void attn_tc_set_trace(unsigned long long* buf) { g_attn_trace = buf; }
 
 size_t xattn_bf16_workspace_bytes(int batch, int heads, int lq, int lk, int dh) {
   const AttnGeom g = attn_geometry(batch, heads, lq, lk);
@@ -548,7 +591,7 @@ int xattn_bf16_tc(const __nv_bfloat16* Q, long long ldq, long long qb, const __n
   MAVLM_REQUIRE(scale > 0.f, MAVLM_E_INVALID, "xattn: scale must be positive");
   MAVLM_REQUIRE(ldo % 8 == 0 && ob % 8 == 0 && (reinterpret_cast<uintptr_t>(O) & 15) == 0, MAVLM_E_INVALID,
                 "bf16 xattn: O must be 16-byte aligned with ldo %% 8 == 0");
-  CUtensorMap tmQ, tmK, tmV;
+  CUtensorMap tmQ, tmK, tmV, tmO;
   const uint64_t cols = static_cast<uint64_t>(heads) * dh;
   auto mk = [&](CUtensorMap* tm, const void* base, long long ld, long long bs, int rows, uint32_t box_rows) {
     const uint64_t dims[3] = {cols, static_cast<uint64_t>(rows), static_cast<uint64_t>(batch)};
@@ -562,6 +605,13 @@ int xattn_bf16_tc(const __nv_bfloat16* Q, long long ldq, long long qb, const __n
   if ((rc = mk(&tmQ, Q, ldq, qb, lq, ATT_BQ))) return rc;
   if ((rc = mk(&tmK, K, ldk, kb, lk, ATT_BKV))) return rc;
   if ((rc = mk(&tmV, V, ldv, vb, lk, ATT_BKV))) return rc;
+  {  // O leaves through TMA stores of 32 x 32 tiles (64B swizzle); rows >= lq are clipped by the hardware
+    const uint64_t dims[3] = {cols, static_cast<uint64_t>(lq), static_cast<uint64_t>(batch)};
+    const uint64_t bstride = batch > 1 ? static_cast<uint64_t>(ob) * 2 : static_cast<uint64_t>(ldo) * 2 * lq;
+    const uint64_t str[2] = {static_cast<uint64_t>(ldo) * 2, bstride};
+    const uint32_t box[3] = {32, 32, 1};
+    if ((rc = make_tmap(&tmO, O, 2, 64, 3, dims, str, box))) return rc;
+  }
   const size_t need = xattn_bf16_workspace_bytes(batch, heads, lq, lk, dh);
   MAVLM_REQUIRE(ws != nullptr && ws_bytes >= need && (reinterpret_cast<uintptr_t>(ws) & 15) == 0, MAVLM_E_WORKSPACE,
                 "bf16 xattn: 16-byte aligned workspace of %zu bytes needed, %zu given", need, ws_bytes);
@@ -573,10 +623,12 @@ int xattn_bf16_tc(const __nv_bfloat16* Q, long long ldq, long long qb, const __n
   p.qtiles = geo.qtiles; p.ngq = geo.ngq; p.gs = geo.gs; p.groups = geo.groups; p.units = geo.units;
   p.items = batch * heads * p.qtiles;
   p.ws = static_cast<float*>(ws);
+  p.trace = g_attn_trace;
   p.flags = reinterpret_cast<unsigned int*>(p.ws + static_cast<long long>(p.groups) * p.gs * (static_cast<long long>(ATT_BQ) * dh + 2 * ATT_BQ));
   if (half)
-    return dh == 448 ? launch_attn<448, __half>(tmQ, tmK, tmV, p, st) : launch_attn<128, __half>(tmQ, tmK, tmV, p, st);
-  return dh == 448 ? launch_attn<448>(tmQ, tmK, tmV, p, st) : launch_attn<128>(tmQ, tmK, tmV, p, st);
+    return dh == 448 ? launch_attn<448, __half>(tmQ, tmK, tmV, tmO, p, st)
+                     : launch_attn<128, __half>(tmQ, tmK, tmV, tmO, p, st);
+  return dh == 448 ? launch_attn<448>(tmQ, tmK, tmV, tmO, p, st) : launch_attn<128>(tmQ, tmK, tmV, tmO, p, st);
 }
 
 }  // namespace mavlm
