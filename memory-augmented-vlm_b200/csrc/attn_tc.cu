@@ -443,6 +443,35 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         // before the next key block's named barrier, which every warp reaches after its last wait_read below.
         // Direct register stores (32 rows x 16 B per instruction) took ~14 k cycles per segment.
         uint8_t* out_stage = sP + (warp - 2) * 4096;
+        // The other parts' partial O tiles (this warp's 32 rows x 32 columns of one chunk = 32 pieces of 128 bytes)
+        // are prefetched with cp.async into a ring of PF 4 KB buffers per warp: a merging segment is its CTA's last one
+        // (the item continues in the next group, so this CTA's unit range ends here) and every MMA has completed, so
+        // the Q tile and the K/V ring are free.  Plain L2 loads (32 in flight per thread and chunk) added ~11 k cycles.
+        constexpr int PF_Q = Cfg::Q_BYTES / (ATT_SM_WARPS * 4096);
+        constexpr int PF_R = (RING * ATT_SLOT_BYTES) / (ATT_SM_WARPS * 4096);
+        constexpr int PF = PF_Q + PF_R;
+        auto pf_buf = [&](int r) -> uint8_t* {
+          return r < PF_Q ? sQ + ((warp - 2) * PF_Q + r) * 4096 : sKV + ((warp - 2) * PF_R + (r - PF_Q)) * 4096;
+        };
+        const int pf_items = OCH * np;
+        auto pf_issue = [&](int t) {
+          const int c = half * OCH + t / np, k = t - (t / np) * np;
+          const float* src = p.ws + (static_cast<long long>(g_part[k]) * p.gs + grp_r) * attn_slot_floats<DH>() +
+                             static_cast<long long>(c) * 32 * ATT_BQ + qd * 32 + (lane & 7) * 4;
+          uint8_t* dst = pf_buf(t % PF) + (lane & 7) * 16;
+#pragma unroll
+          for (int tt = 0; tt < 8; ++tt) {
+            const int i = tt * 4 + (lane >> 3);
+            cp_async_cg16(dst + i * 128, src + i * ATT_BQ);
+          }
+        };
+        if (np > 0) {
+          for (int t = 0; t < PF; ++t) {
+            if (t < pf_items) pf_issue(t);
+            cp_async_commit();
+          }
+        }
+        int pf_t = 0;
 #pragma unroll 1
         for (int c = half * OCH; c < (half + 1) * OCH; ++c) {
           uint32_t o[32];
@@ -451,12 +480,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(o[i]) * own_scale;
-          for (int k = 0; k < np; ++k) {
-            const float* sl = p.ws + (static_cast<long long>(g_part[k]) * p.gs + grp_r) * attn_slot_floats<DH>() +
-                              static_cast<long long>(c) * 32 * ATT_BQ + row;
+          for (int k = 0; k < np; ++k, ++pf_t) {
+            cp_async_wait<PF - 1>();  // item pf_t has landed (one group is committed per item, empty ones included)
+            __syncwarp();
+            const float* sl = reinterpret_cast<const float*>(pf_buf(pf_t % PF)) + lane;
             const float wk = w_part[k] * inv;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaf(wk, ld_cg_f32(sl + i * ATT_BQ), v[i]);
+            for (int i = 0; i < 32; ++i) v[i] = fmaf(wk, sl[i * 32], v[i]);
+            __syncwarp();
+            if (pf_t + PF < pf_items) pf_issue(pf_t + PF);
+            cp_async_commit();
           }
           uint8_t* buf = out_stage + (c & 1) * 2048;
           if (lane == 0) bulk_wait_read<1>();  // the store issued two chunks ago has read this buffer

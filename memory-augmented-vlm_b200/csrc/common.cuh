@@ -406,6 +406,14 @@ __device__ __forceinline__ float ld_cg_f32(const float* p) {  // L2 load: data w
   return v;
 }
 
+// Ampere-style asynchronous copy, 16 bytes, L2 only (data written by another CTA of this grid)
+__device__ __forceinline__ void cp_async_cg16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
