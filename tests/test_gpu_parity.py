@@ -228,6 +228,38 @@ def test_bf16_attention_kernel_sharp_softmax():
         assert err(lse[0], ref_lse) < 1e-4, dh
 
 
+def test_bf16_attention_strided_output_and_ragged_rows_through_the_c_abi():
+    """The output leaves the kernel through TMA stores of 32 x 32 tiles: a strided O (column slice of a wider buffer,
+    padded batch stride) with Lq not a multiple of 32 must receive exactly the rows / columns of the contiguous call
+    and nothing else (sentinel around it), for both head dims, a batch > 1 and a split-merged B = 1 case."""
+    from mavlm_b200 import _lib
+    from mavlm_b200.ops import _ptr, _stream, dtype_code
+    lib = _lib.load()
+    torch.manual_seed(11)
+    for dh, h, b, lq, lk in ((128, 7, 3, 77, 333), (448, 8, 2, 161, 700), (448, 8, 1, 1568, 3000)):
+        hd = h * dh
+        q = torch.randn(b, lq, hd, device=DEV).bfloat16()
+        k = torch.randn(b, lk, hd, device=DEV).bfloat16()
+        v = torch.randn(b, lk, hd, device=DEV).bfloat16()
+        ref, ref_lse, _ = ops.xattn(q, k, v, h, head_dim=dh, want_lse=True)
+        wide = torch.full((b, lq + 5, 2 * hd + 64), 7.0, device=DEV).bfloat16()  # rows lq.. and columns outside stay 7
+        o = wide[:, :lq, 64:64 + hd]
+        lse = torch.empty(b, h, lq, dtype=torch.float32, device=DEV)
+        code = dtype_code(q)
+        ws_bytes = lib.mavlm_xattn_workspace_bytes(b, h, lq, lk, dh, code)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=DEV)
+        st = lib.mavlm_xattn_fwd(_ptr(q), q.stride(1), q.stride(0), _ptr(k), k.stride(1), k.stride(0), _ptr(v),
+                                 v.stride(1), v.stride(0), _ptr(o), o.stride(1), o.stride(0), _ptr(lse), None, b, h,
+                                 lq, lk, dh, 1.0 / np.sqrt(dh), code, _ptr(ws), ws_bytes, _stream())
+        _lib.check(st, "xattn_fwd")
+        torch.cuda.synchronize()
+        assert torch.equal(o, ref), (dh, b, lq)
+        assert torch.equal(lse, ref_lse)
+        mask = torch.ones_like(wide, dtype=torch.bool)
+        mask[:, :lq, 64:64 + hd] = False
+        assert bool((wide[mask] == 7.0).all()), "the kernel wrote outside its output window"
+
+
 def test_bf16_tier_stress_sharp_softmax():
     """q_proj x8 and inputs x4 through the recurrence.  In this regime bf16 rounding is
     amplified chaotically: the REFERENCE's own bf16-vs-fp32 drift is 16 % (first state) / 81 % (second)
