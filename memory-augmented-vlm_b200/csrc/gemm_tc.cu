@@ -59,6 +59,9 @@ struct GemmTcParams {
 // CG = CTAs per MMA (tcgen05 cta_group): 1 = one CTA owns a 128 x BN tile; 2 = a CTA pair owns a 256 x BN
 // tile, each CTA staging its own 128 rows of A and HALF of the W slab (BN/2 rows), so the shared-memory
 // bytes read per MMA cycle drop by a third and a stage is 32 KB instead of 48 KB (deeper ring).
+// bf16 / fp16 TMA stores use 32 x 64-column boxes when every epilogue warp converts an even number of 32-column chunks
+__host__ __device__ constexpr bool gemm_wide_store(int bn) { return ((bn / 32) / 2) % 2 == 0; }
+
 template <int BN, int CG = 1>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
@@ -402,6 +405,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_store_2d(out_stage, tc, nc, m0 + q * 32);
               bulk_commit();
             }
+          } else if constexpr (gemm_wide_store(BN)) {
+            // an even number of chunks per warp: two chunks share one 32 x 128 B tile (128B swizzle) and leave as ONE
+            // TMA store of whole 128-byte lines -- half as many stores as 32 x 64 B tiles, which bound the epilogue of
+            // the short-K projector GEMM (64 stores per 128 x 256 tile and CTA)
+            const int sub = c & 1;                                   // this warp's first chunk index is even
+            const bool closes = sub == 1 || nc + 32 >= pp.N;         // the odd chunk would be past N: store now
+            if (sub == 0) {
+              if (lane == 0) bulk_wait_read<0>();                    // the previous store has read the tile
+              __syncwarp();
+            }
+            uint8_t* dst = out_stage + lane * 128;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 t;
+              t.x = Elem16<T>::pack2(v[8 * g], v[8 * g + 1]);
+              t.y = Elem16<T>::pack2(v[8 * g + 2], v[8 * g + 3]);
+              t.z = Elem16<T>::pack2(v[8 * g + 4], v[8 * g + 5]);
+              t.w = Elem16<T>::pack2(v[8 * g + 6], v[8 * g + 7]);
+              *reinterpret_cast<uint4*>(dst + (((4 * sub + g) ^ (lane & 7)) << 4)) = t;  // 128B swizzle
+            }
+            if (closes) {
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(out_stage, tc, nc - 32 * sub, m0 + q * 32);
+                bulk_commit();
+              }
+            }
           } else {
             uint8_t* buf = out_stage + (c & 1) * 2048;
             if (lane == 0) bulk_wait_read<1>();  // the store issued two chunks ago has read this buffer
@@ -689,7 +720,12 @@ int gemm_tc_general(const __nv_bfloat16* A, long long lda, bool a_mn, const __nv
   p.c_inner = s6[5];
   const bool pair_ok = p.batches == 1;
   const int choice = gemm_tc_pick_tile(p.M, p.N, p.batches, pair_ok);
-  const int cg = choice >= 1000 ? 2 : 1, bn = choice % 1000;
+  const int cg = choice >= 1000 ? 2 : 1;
+  int bn = choice % 1000;
+  // CTA-pair kernels with a transposed operand exist for 256 x 256 and 256 x 128 tiles only (dispatch_bn): the tiling
+  // and the output boxes below must describe the tile the kernel really walks
+  if (cg == 2 && (a_mn || b_mn)) bn = bn >= 192 ? 256 : 128;
+  else if (cg == 2 && bn < 128) bn = 128;
   CUtensorMap tmA, tmB;
   int rc;
   if ((rc = make_operand_map(&tmA, A, lda, a_mn ? p.K : p.M, a_mn ? p.M : p.K, a_mn, GEMM_BM, inner, outer, s6[1],
@@ -705,8 +741,9 @@ int gemm_tc_general(const __nv_bfloat16* A, long long lda, bool a_mn, const __nv
     const int eb = p.out_f32 ? 4 : 2;
     const uint64_t dims[2] = {static_cast<uint64_t>(p.N), static_cast<uint64_t>(p.M)};
     const uint64_t str[1] = {static_cast<uint64_t>(p.ldc) * eb};
-    const uint32_t box[2] = {32, 32};
-    if ((rc = make_tmap(&tmC, p.C, eb, p.out_f32 ? 128 : 64, 2, dims, str, box))) return rc;
+    const bool wide = !p.out_f32 && gemm_wide_store(bn);
+    const uint32_t box[2] = {wide ? 64u : 32u, 32};
+    if ((rc = make_tmap(&tmC, p.C, eb, (p.out_f32 || wide) ? 128 : 64, 2, dims, str, box))) return rc;
   }
   gemm_set_tiling(p, bn, cg);
   p.tile_begin = 0;
@@ -783,8 +820,9 @@ static int fill_prepare(const mavlm_gemm_desc& d, int half, GemmTcParams& p, CUt
   const int eb = out_f32 ? 4 : 2;
   const uint64_t dims[2] = {static_cast<uint64_t>(d.N), static_cast<uint64_t>(d.M)};
   const uint64_t str[1] = {static_cast<uint64_t>(d.ldc) * eb};
-  const uint32_t box[2] = {32, 32};
-  return make_tmap(&tmC, d.C, eb, out_f32 ? 128 : 64, 2, dims, str, box);
+  const bool wide = !out_f32 && gemm_wide_store(FILL_BN);
+  const uint32_t box[2] = {wide ? 64u : 32u, 32};
+  return make_tmap(&tmC, d.C, eb, (out_f32 || wide) ? 128 : 64, 2, dims, str, box);
 }
 
 int gemm_fill_num_tiles(const mavlm_gemm_desc* d) {
