@@ -77,7 +77,12 @@ MAVLM_API int mavlm_add_pe_fwd(const void* x, void* y, const float* pe_table, co
  * projections (MemoryController.py:23,37-39), the RMT MLP (:63-67) and the fuser (llava_arch.py:132-136):
  *   C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]) (+ resid[M,N]) (+ addvec[N])
  * A, W, resid in `dtype`; bias/addvec in `dtype`; C in out_dtype (MAVLM_F32 allowed with bf16 inputs:
- * used for the pre-LayerNorm sum).  ld* are row strides in elements.  bias/resid/addvec may be NULL. */
+ * used for the pre-LayerNorm sum).  ld* are row strides in elements.  bias/resid/addvec may be NULL.
+ * W is a module PARAMETER (an nn.Linear weight): the bf16 / fp16 kernel requests the first W slabs of each worker's
+ * first tile before it waits for the kernel ahead of it on the stream (programmatic dependent launch), so W must not be
+ * the output of one of this library's own launches still in flight on `stream` (a tensor torch or a memcpy produced is
+ * fine: those complete before a dependent launch starts).  mavlm_gemm_ex is the entry for computed operands.  The
+ * same holds for gamma / beta of mavlm_layernorm_fwd. */
 MAVLM_API int mavlm_gemm_bias_act_fwd(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* resid,
                             int64_t ldr, const void* addvec, void* C, int64_t ldc, int M, int N, int K, int act,
                             int dtype, int out_dtype, void* stream);

@@ -127,6 +127,15 @@ __global__ void __launch_bounds__(32 * LN_WARPS, 3) layernorm_kernel(const TI* _
   const long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
   const bool active = row < rows;
   pdl_trigger();
+  {  // gamma | beta -> shared memory (16-byte vectors).  They are module parameters, not outputs of the kernel ahead on
+     // the stream, so they are fetched BEFORE griddepcontrol.wait: their L2 / HBM round trip hides under that kernel's tail
+    constexpr int EV = 16 / sizeof(TO);
+    const int nv = dim / EV;
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+      reinterpret_cast<uint4*>(sg)[i] = __ldg(reinterpret_cast<const uint4*>(gamma) + i);
+      reinterpret_cast<uint4*>(sb)[i] = __ldg(reinterpret_cast<const uint4*>(beta) + i);
+    }
+  }
   pdl_wait();
   const TI* xr = x + (active ? row : 0) * dim;
   TO* yr = y + (active ? row : 0) * dim;
@@ -149,14 +158,6 @@ __global__ void __launch_bounds__(32 * LN_WARPS, 3) layernorm_kernel(const TI* _
       s += (v[c][0] + v[c][1]) + (v[c][2] + v[c][3]);
     } else {
       v[c][0] = v[c][1] = v[c][2] = v[c][3] = 0.f;
-    }
-  }
-  {  // gamma | beta -> shared memory (16-byte vectors), overlapping the row loads above
-    constexpr int EV = 16 / sizeof(TO);
-    const int nv = dim / EV;
-    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
-      reinterpret_cast<uint4*>(sg)[i] = __ldg(reinterpret_cast<const uint4*>(gamma) + i);
-      reinterpret_cast<uint4*>(sb)[i] = __ldg(reinterpret_cast<const uint4*>(beta) + i);
     }
   }
   const float mean = warp_sum(s) / static_cast<float>(dim);
@@ -210,7 +211,9 @@ __global__ void __launch_bounds__(32 * LN_WARPS, 3) layernorm_kernel(const TI* _
 }
 
 // ---------------------------------------------------------------------------------------
-// K12 + K13: token assembly.  One CTA per output row; the row kind is decoded from its index.
+// K12 + K13: token assembly.  One CTA per output row that this launch writes; the row kind is decoded from its index.
+// When the memory-token rows are already in place (mem == nullptr: the fuser GEMM's epilogue stored them) the grid
+// does not cover them.  A thread issues all of its (up to 4) 16-byte row loads before the first store.
 // ---------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(128) assemble_kernel(T* __restrict__ seq, const T* __restrict__ mem, long long n_mem,
@@ -221,16 +224,18 @@ __global__ void __launch_bounds__(128) assemble_kernel(T* __restrict__ seq, cons
                                                        const int64_t* __restrict__ pm_ids, int n_pm,
                                                        const int64_t* __restrict__ pf_ids, int n_pf, int dim) {
   constexpr int V = Vec<T>::N;
+  constexpr int U = 4;
   pdl_trigger();
   pdl_wait();
-  long long r = blockIdx.x;
+  long long out_row = blockIdx.x;
+  if (mem == nullptr && out_row >= n_pm) out_row += n_mem;  // rows [n_pm, n_pm + n_mem) are not part of this grid
+  long long r = out_row;
   const T* src = nullptr;
   const T* add = nullptr;
   const long long n_fine_rows = static_cast<long long>(n_fine) * tokens;
   if (r < n_pm) {
     src = table + pm_ids[r] * dim;
   } else if ((r -= n_pm) < n_mem) {
-    if (mem == nullptr) return;  // written in place by the fuser GEMM epilogue
     src = mem + r * dim;
     add = type_emb;
   } else if ((r -= n_mem) < 1) {
@@ -244,17 +249,32 @@ __global__ void __launch_bounds__(128) assemble_kernel(T* __restrict__ seq, cons
   } else {
     src = newline;
   }
-  T* dst = seq + static_cast<long long>(blockIdx.x) * dim;
-  for (int i = threadIdx.x * V; i < dim; i += blockDim.x * V) {
-    float v[V];
-    Vec<T>::load_plain(src + i, v);
-    if (add != nullptr) {
-      float a[V];
-      Vec<T>::load(add + i, a);
+  T* dst = seq + out_row * dim;
+  const int nvec = dim / V;
+  for (int base = threadIdx.x; base < nvec; base += blockDim.x * U) {
+    float v[U][V];
 #pragma unroll
-      for (int k = 0; k < V; ++k) v[k] += a[k];
+    for (int u = 0; u < U; ++u) {
+      const int j = base + u * blockDim.x;
+      if (j < nvec) Vec<T>::load_plain(src + j * V, v[u]);
     }
-    Vec<T>::store(dst + i, v);
+    if (add != nullptr) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = base + u * blockDim.x;
+        if (j < nvec) {
+          float a[V];
+          Vec<T>::load(add + j * V, a);
+#pragma unroll
+          for (int k = 0; k < V; ++k) v[u][k] += a[k];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int j = base + u * blockDim.x;
+      if (j < nvec) Vec<T>::store(dst + j * V, v[u]);
+    }
   }
 }
 
@@ -477,6 +497,7 @@ int mavlm_assemble_fwd(void* seq, const void* mem, int64_t n_mem_rows, const voi
   MAVLM_REQUIRE(dim > 0 && dim % vec == 0, MAVLM_E_INVALID, "assemble: dim %d must be a multiple of %d", dim, vec);
   long long rows = n_prompt_mem + n_mem_rows + 1;
   if (!drop_frames) rows += n_prompt_frm + static_cast<long long>(n_fine) * tokens + 1;
+  if (mem == nullptr) rows -= n_mem_rows;  // already in place: the grid skips them
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MAVLM_DISPATCH_DTYPE(dtype, (assemble_kernel<T><<<static_cast<unsigned>(rows), 128, 0, st>>>(
                                   static_cast<T*>(seq), static_cast<const T*>(mem), n_mem_rows,

@@ -456,12 +456,13 @@ def fam_ab():
         return e0.elapsed_time(e1) / n
 
     variants = {}
-    for name, flags in (("pdl", 0), ("no-pdl", 16)):
+    for name, flags in (("pdl", 0), ("no-early-w", 32), ("no-pdl", 16)):
         lib.mavlm_debug_set_flags(flags)
         variants[name] = GraphedPipeline(pipe, 1, 64)       # the launch attributes are baked in at capture time
     lib.mavlm_debug_set_flags(0)
     for rnd in range(5):
-        print(f"round {rnd}:  " + "   ".join(f"{name}: {graph_ms(gp):.3f} ms" for name, gp in variants.items()), flush=True)
+        print(f"round {rnd}:  " + "   ".join(f"{name}: {graph_ms(gp, 20):.3f} ms" for name, gp in variants.items()), flush=True)
+        time.sleep(0.5)
     ref = variants["no-pdl"](x, idx)["sequence"].float().clone()
     out = variants["pdl"](x, idx)["sequence"].float()
     torch.cuda.synchronize()
