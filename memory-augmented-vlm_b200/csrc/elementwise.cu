@@ -100,12 +100,15 @@ __global__ void __launch_bounds__(256) add_pe_kernel(const T* x, T* y,  // y may
 }
 
 // ---------------------------------------------------------------------------------------
-// LayerNorm: one WARP per row (4 rows per CTA), the row cached in registers as 16-byte vectors, exact
-// two-pass statistics in fp32 (eps = 1e-12 in the RMT makes the one-pass E[x^2]-E[x]^2 form unsafe).
-// A lane issues all of its row loads back to back (28 independent 16-byte loads for D = 3584), the
-// reductions are warp shuffles; gamma / beta are staged once per CTA in shared memory while the row loads
-// are in flight (reading them from global inside the output loop serialised 28 dependent L2 round trips per
-// row: 20 us for the 1568 x 3584 rows of a memory state, 4x the HBM time).
+// LayerNorm: persistent CTAs (one per SM, 12 warps), one WARP per row, rows staged through shared memory by the
+// bulk-copy engine.  Every warp owns a one-row buffer and an mbarrier: lane 0 requests the row with ONE
+// cp.async.bulk (14 KB for D = 3584 fp32), the warp pulls it into registers as 16-byte vectors and immediately
+// requests its NEXT row into the same buffer, so a row's statistics / normalisation / stores overlap the next row's
+// fetch and ~170 KB per SM stay in flight for the whole kernel (the register-only version had its loads in flight only
+// during the load phase of each 4-row CTA and re-staged gamma / beta per CTA: 0.35-0.63 of the copy bandwidth even at
+// 50 k rows).  Exact two-pass statistics in fp32 (eps = 1e-12 in the RMT makes the one-pass E[x^2]-E[x]^2 form unsafe).
+// gamma / beta are module parameters: staged once per CTA BEFORE griddepcontrol.wait (under the previous kernel's tail).
+// Rows are dealt round-robin over (warp, CTA) so that a single-wave launch (1568 rows of a memory state) spreads evenly.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -113,22 +116,36 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-constexpr int LN_WARPS = 4;
+constexpr int LN_WARPS = 12;
+
+// global -> shared bulk copy completing on an mbarrier; `after` is an unused operand that orders the request behind
+// the value's computation (the warp reduction that consumed every lane's reads of the buffer being overwritten)
+__device__ __forceinline__ void ln_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, float after) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];  // %4"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "f"(after)
+               : "memory");
+}
 
 template <typename TI, typename TO, int CACHE>  // CACHE = 4-float vectors per lane: dim <= 128 * CACHE
-__global__ void __launch_bounds__(32 * LN_WARPS, 3) layernorm_kernel(const TI* __restrict__ x,
+__global__ void __launch_bounds__(32 * LN_WARPS, 1) layernorm_kernel(const TI* __restrict__ x,
                                                                   const TO* __restrict__ gamma,
                                                                   const TO* __restrict__ beta, TO* __restrict__ y,
                                                                   int rows, int dim, float eps) {
-  extern __shared__ __align__(16) uint8_t ln_smem[];
+  extern __shared__ __align__(128) uint8_t ln_smem[];
   TO* sg = reinterpret_cast<TO*>(ln_smem);
   TO* sb = sg + dim;
   const int lane = threadIdx.x & 31;
-  const long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
-  const bool active = row < rows;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t row_bytes = static_cast<uint32_t>(dim) * sizeof(TI);
+  uint8_t* bufs = ln_smem + 2 * static_cast<size_t>(dim) * sizeof(TO);
+  const TI* buf = reinterpret_cast<const TI*>(bufs + static_cast<size_t>(warp) * row_bytes);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(bufs + static_cast<size_t>(LN_WARPS) * row_bytes) + warp;
   pdl_trigger();
-  {  // gamma | beta -> shared memory (16-byte vectors).  They are module parameters, not outputs of the kernel ahead on
-     // the stream, so they are fetched BEFORE griddepcontrol.wait: their L2 / HBM round trip hides under that kernel's tail
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  {
     constexpr int EV = 16 / sizeof(TO);
     const int nv = dim / EV;
     for (int i = threadIdx.x; i < nv; i += blockDim.x) {
@@ -136,75 +153,89 @@ __global__ void __launch_bounds__(32 * LN_WARPS, 3) layernorm_kernel(const TI* _
       reinterpret_cast<uint4*>(sb)[i] = __ldg(reinterpret_cast<const uint4*>(beta) + i);
     }
   }
-  pdl_wait();
-  const TI* xr = x + (active ? row : 0) * dim;
-  TO* yr = y + (active ? row : 0) * dim;
-  float v[CACHE][4];
-  float s = 0.f;
-#pragma unroll
-  for (int c = 0; c < CACHE; ++c) {
-    const int i = (c * 32 + lane) * 4;
-    if (active && i < dim) {
-      if constexpr (sizeof(TI) == 4) {
-        const uint4 t = ld_dep_u4(reinterpret_cast<const float*>(xr) + i);
-        v[c][0] = __uint_as_float(t.x); v[c][1] = __uint_as_float(t.y);
-        v[c][2] = __uint_as_float(t.z); v[c][3] = __uint_as_float(t.w);
-      } else {
-        uint2 t = ld_dep_u2(reinterpret_cast<const uint16_t*>(xr) + i);
-        float2 a = Elem16<TO>::unpack2(t.x);   // a 16-bit input has the output's type
-        float2 b = Elem16<TO>::unpack2(t.y);
-        v[c][0] = a.x; v[c][1] = a.y; v[c][2] = b.x; v[c][3] = b.y;
-      }
-      s += (v[c][0] + v[c][1]) + (v[c][2] + v[c][3]);
-    } else {
-      v[c][0] = v[c][1] = v[c][2] = v[c][3] = 0.f;
-    }
-  }
-  const float mean = warp_sum(s) / static_cast<float>(dim);
-  float q = 0.f;
-#pragma unroll
-  for (int c = 0; c < CACHE; ++c) {
-    const int i = (c * 32 + lane) * 4;
-    if (i < dim) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float d = v[c][k] - mean;
-        q += d * d;
-      }
-    }
-  }
-  const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(dim) + eps);
   __syncthreads();
-  if (!active) return;
+  pdl_wait();  // x is the previous kernel's output
+  const long long stride = static_cast<long long>(gridDim.x) * LN_WARPS;
+  long long row = static_cast<long long>(warp) * gridDim.x + blockIdx.x;
+  if (row < rows && lane == 0) {
+    mbar_expect_tx(bar, row_bytes);
+    ln_bulk_load(const_cast<TI*>(buf), x + row * dim, row_bytes, bar, 0.f);
+  }
+  uint32_t phase = 0;
+  for (; row < rows; row += stride) {
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    float v[CACHE][4];
+    float s = 0.f;
 #pragma unroll
-  for (int c = 0; c < CACHE; ++c) {
-    const int i = (c * 32 + lane) * 4;
-    if (i < dim) {
-      float g[4], b[4], o[4];
-      if constexpr (sizeof(TO) == 4) {
-        const float4 tg = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sg) + i);
-        const float4 tb = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sb) + i);
-        g[0] = tg.x; g[1] = tg.y; g[2] = tg.z; g[3] = tg.w;
-        b[0] = tb.x; b[1] = tb.y; b[2] = tb.z; b[3] = tb.w;
+    for (int c = 0; c < CACHE; ++c) {
+      const int i = (c * 32 + lane) * 4;
+      if (i < dim) {
+        if constexpr (sizeof(TI) == 4) {
+          const float4 t = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(buf) + i);
+          v[c][0] = t.x; v[c][1] = t.y; v[c][2] = t.z; v[c][3] = t.w;
+        } else {
+          const uint2 t = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(buf) + i);
+          const float2 a = Elem16<TO>::unpack2(t.x);   // a 16-bit input has the output's type
+          const float2 b = Elem16<TO>::unpack2(t.y);
+          v[c][0] = a.x; v[c][1] = a.y; v[c][2] = b.x; v[c][3] = b.y;
+        }
+        s += (v[c][0] + v[c][1]) + (v[c][2] + v[c][3]);
       } else {
-        const uint2 tg = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(sg) + i);
-        const uint2 tb = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(sb) + i);
-        const float2 g0 = Elem16<TO>::unpack2(tg.x);
-        const float2 g1 = Elem16<TO>::unpack2(tg.y);
-        const float2 b0 = Elem16<TO>::unpack2(tb.x);
-        const float2 b1 = Elem16<TO>::unpack2(tb.y);
-        g[0] = g0.x; g[1] = g0.y; g[2] = g1.x; g[3] = g1.y;
-        b[0] = b0.x; b[1] = b0.y; b[2] = b1.x; b[3] = b1.y;
+        v[c][0] = v[c][1] = v[c][2] = v[c][3] = 0.f;
       }
+    }
+    const float mean = warp_sum(s) / static_cast<float>(dim);
+    // every lane's reads of the buffer fed `mean`: the buffer is free, the next row goes into it now
+    const long long next = row + stride;
+    if (next < rows && lane == 0) {
+      mbar_expect_tx(bar, row_bytes);
+      ln_bulk_load(const_cast<TI*>(buf), x + next * dim, row_bytes, bar, mean);
+    }
+    float q = 0.f;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) o[k] = (v[c][k] - mean) * rstd * g[k] + b[k];
-      if constexpr (sizeof(TO) == 4) {
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(yr) + i) = make_float4(o[0], o[1], o[2], o[3]);
-      } else {
-        uint2 t;
-        t.x = Elem16<TO>::pack2(o[0], o[1]);
-        t.y = Elem16<TO>::pack2(o[2], o[3]);
-        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(yr) + i) = t;
+    for (int c = 0; c < CACHE; ++c) {
+      const int i = (c * 32 + lane) * 4;
+      if (i < dim) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float d = v[c][k] - mean;
+          q += d * d;
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(dim) + eps);
+    TO* yr = y + row * dim;
+#pragma unroll
+    for (int c = 0; c < CACHE; ++c) {
+      const int i = (c * 32 + lane) * 4;
+      if (i < dim) {
+        float g[4], b[4], o[4];
+        if constexpr (sizeof(TO) == 4) {
+          const float4 tg = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sg) + i);
+          const float4 tb = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sb) + i);
+          g[0] = tg.x; g[1] = tg.y; g[2] = tg.z; g[3] = tg.w;
+          b[0] = tb.x; b[1] = tb.y; b[2] = tb.z; b[3] = tb.w;
+        } else {
+          const uint2 tg = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(sg) + i);
+          const uint2 tb = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(sb) + i);
+          const float2 g0 = Elem16<TO>::unpack2(tg.x);
+          const float2 g1 = Elem16<TO>::unpack2(tg.y);
+          const float2 b0 = Elem16<TO>::unpack2(tb.x);
+          const float2 b1 = Elem16<TO>::unpack2(tb.y);
+          g[0] = g0.x; g[1] = g0.y; g[2] = g1.x; g[3] = g1.y;
+          b[0] = b0.x; b[1] = b0.y; b[2] = b1.x; b[3] = b1.y;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = (v[c][k] - mean) * rstd * g[k] + b[k];
+        if constexpr (sizeof(TO) == 4) {
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(yr) + i) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+          uint2 t;
+          t.x = Elem16<TO>::pack2(o[0], o[1]);
+          t.y = Elem16<TO>::pack2(o[2], o[3]);
+          *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(yr) + i) = t;
+        }
       }
     }
   }
@@ -372,11 +403,22 @@ int layernorm_launch(const void* x, const void* gamma, const void* beta, void* y
   MAVLM_REQUIRE(dtype == MAVLM_F32 || dim % 8 == 0, MAVLM_E_INVALID, "layernorm: 16-bit dim %d must be a multiple of 8", dim);
   MAVLM_REQUIRE((reinterpret_cast<uintptr_t>(gamma) & 15) == 0 && (reinterpret_cast<uintptr_t>(beta) & 15) == 0,
                 MAVLM_E_INVALID, "layernorm: gamma / beta must be 16-byte aligned");
+  MAVLM_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, MAVLM_E_INVALID, "layernorm: x must be 16-byte aligned");
   if (rows == 0) return MAVLM_OK;
   LaunchCfg lc;
 #define MAVLM_LN(TI, TO, CA)                                                                                       \
   do {                                                                                                             \
-    make_launch(lc, dim3(ceil_div(rows, LN_WARPS)), dim3(32 * LN_WARPS), 2 * dim * sizeof(TO), st, 1, 4);          \
+    const size_t smem = 2 * static_cast<size_t>(dim) * sizeof(TO) + LN_WARPS * static_cast<size_t>(dim) * sizeof(TI) + \
+                        LN_WARPS * sizeof(uint64_t);                                                              \
+    static bool configured_dev[64] = {}; /* per instantiation and device */                                       \
+    int dev_id = 0;                                                                                                \
+    MAVLM_CUDA_OK(cudaGetDevice(&dev_id));                                                                         \
+    if (!configured_dev[dev_id & 63]) {                                                                            \
+      MAVLM_CUDA_OK(cudaFuncSetAttribute(layernorm_kernel<TI, TO, CA>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         232448));                                                                 \
+      configured_dev[dev_id & 63] = true;                                                                          \
+    }                                                                                                              \
+    make_launch(lc, dim3(rows < sm_count() ? rows : sm_count()), dim3(32 * LN_WARPS), smem, st, 1, 4);             \
     MAVLM_CUDA_OK(cudaLaunchKernelEx(&lc.cfg, layernorm_kernel<TI, TO, CA>, static_cast<const TI*>(x),             \
                                      static_cast<const TO*>(gamma), static_cast<const TO*>(beta),                 \
                                      static_cast<TO*>(y), rows, dim, eps));                                       \

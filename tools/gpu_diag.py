@@ -460,16 +460,83 @@ def fam_ab():
         lib.mavlm_debug_set_flags(flags)
         variants[name] = GraphedPipeline(pipe, 1, 64)       # the launch attributes are baked in at capture time
     lib.mavlm_debug_set_flags(0)
-    for rnd in range(5):
-        print(f"round {rnd}:  " + "   ".join(f"{name}: {graph_ms(gp, 20):.3f} ms" for name, gp in variants.items()), flush=True)
-        time.sleep(0.5)
+    names = list(variants)
+    for rnd in range(6):                                    # rotate the order and idle before every measurement: the
+        order = names[rnd % len(names):] + names[:rnd % len(names)]   # power cap bites ~0.1 s into a burst
+        res = {}
+        for name in order:
+            time.sleep(0.5)
+            res[name] = graph_ms(variants[name], 20)
+        print(f"round {rnd} (order {order}):  " + "   ".join(f"{name}: {res[name]:.3f} ms" for name in names), flush=True)
     ref = variants["no-pdl"](x, idx)["sequence"].float().clone()
     out = variants["pdl"](x, idx)["sequence"].float()
     torch.cuda.synchronize()
     print("pdl vs no-pdl max abs diff:", float((out - ref).abs().max()))
 
 
-FAMS = {"micro": fam_micro, "ab": fam_ab, "elem": fam_elem, "simt": fam_simt, "gemm": fam_gemm, "attn": fam_attn, "pipe": fam_pipe, "perf": fam_perf}
+def fam_lnperf():
+    """LayerNorm / assembly throughput, timed as CUDA-graph replays (no Python between launches), with a parity check
+    against torch at rows that make a warp loop (rows > 148 * 12)."""
+    import torch
+    import torch.nn.functional as F
+    from mavlm_b200 import ops
+    dev = "cuda"
+    torch.manual_seed(0)
+
+    def graph_us(fn, reps=20, n=5):
+        fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(reps):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(n):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) * 1e3 / reps)
+        return best
+
+    for d, idt, odt in ((3584, torch.float32, torch.bfloat16), (3584, torch.bfloat16, torch.bfloat16),
+                        (896, torch.float32, torch.bfloat16), (4096, torch.float32, torch.float32), (64, torch.float32, torch.float32)):
+        for rows in (1, 77, 1568, 1777, 5000, 12544, 50176):
+            x = (torch.randn(rows, d, device=dev) * 3 + 1).to(idt)
+            g = torch.randn(d, device=dev).to(odt)
+            b = torch.randn(d, device=dev).to(odt)
+            out = torch.empty(rows, d, device=dev, dtype=odt)
+            ops.layernorm(x, g, b, 1e-12, out_dtype=odt, out=out)
+            ref = F.layer_norm(x.double(), (d,), g.double(), b.double(), 1e-12)
+            err = nerr(out.float(), ref)
+            us = graph_us(lambda: ops.layernorm(x, g, b, 1e-12, out_dtype=odt, out=out))
+            by = rows * d * (x.element_size() + out.element_size())
+            print(f"layernorm {idt}->{odt} d={d} rows={rows}: err {err:.2e}  {us:.1f} us  {by / us / 1e3:.0f} GB/s", flush=True)
+    # assembly at the bench shape: 2 states in place, 32 fine frames
+    d, p = 3584, 196
+    dt = torch.bfloat16
+    frames = torch.randn(64, p, d, device=dev).to(dt)
+    fine = torch.arange(0, 64, 2, device=dev)
+    emb = torch.randn(2, d, device=dev).to(dt)
+    nl = torch.randn(d, device=dev).to(dt)
+    tab = torch.randn(50000, d, device=dev).to(dt)
+    pm = torch.tensor([1986, 374, 264, 1550, 11591, 12126, 315, 279, 2766, 25], device=dev)
+    pf = torch.tensor([9485, 525, 48876, 9124, 14087, 504, 279, 2766, 25], device=dev)
+    n_mem = 2 * 1568
+    n = 10 + n_mem + 1 + 9 + 32 * p + 1
+    seq = torch.zeros(n, d, device=dev, dtype=dt)
+    us = graph_us(lambda: ops.assemble(seq, None, n_mem, frames, fine, p, emb, nl, tab, pm, pf))
+    rows = n - n_mem
+    print(f"assemble (mem in place) {rows} rows: {us:.1f} us  {2 * rows * d * 2 / us / 1e3:.0f} GB/s")
+    ref = torch.cat([tab[pm].float(), torch.zeros(n_mem, d, device=dev), nl[None].float(), tab[pf].float(),
+                     (frames[fine].float() + emb[1].float()).reshape(-1, d), nl[None].float()]).to(dt)
+    print("assemble equal:", bool((seq == ref).all()))
+
+
+FAMS = {"micro": fam_micro, "ab": fam_ab, "elem": fam_elem, "simt": fam_simt, "gemm": fam_gemm, "attn": fam_attn, "pipe": fam_pipe, "perf": fam_perf, "lnperf": fam_lnperf}
 
 if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[1] == "--child":
