@@ -458,6 +458,15 @@ def run_ours(args):
     breakdown = {fam: {"ms_per_step": f["ms"], "share": f["ms"] / step_ms_prof} for fam, f in fams.items()}
     gemm_shapes = km.shapes("gemm")
     attn_shapes = km.shapes("xattn")
+    # ---- the bandwidth-bound kernels once more, ISOLATED: 20 back-to-back launches of the kernel alone in a plain CUDA
+    # graph (no event nodes, launches overlap as in the un-instrumented step), at the step's shapes.  A 6 us kernel cannot
+    # be timed between two event nodes (the launch floor above is as long as the kernel).
+    if not args.no_extras:
+        iso = isolated_hbm_kernels(torch, ops, dev, peaks["hbm_gbs"])
+        for ent in roofline_kernels:
+            for fam, rec in iso.items():
+                if ent["kernel"] == kernel_names.get(fam):
+                    ent["isolated"] = rec
     for _ in range(3):
         step_e2e()
     streamer.synchronize()
@@ -508,6 +517,13 @@ def run_ours(args):
                 "achieved_scaled_note": "achieved x instrumented_step_ms / timed_step_ms: the GEMM rate inside the timed "
                                         "region if every kernel family sped up alike (an estimate, not a measurement)",
                 "instrumented_step_ms": step_ms_prof, "timed_step_ms": ms_total / steps,
+                "instrumentation_launch_floor_us": 1e3 * km.launch_floor_ms,
+                "instrumentation_launch_floor_note": "event -> 8-element cast kernel -> event inside the same instrumented "
+                                                     "graph: what the event nodes and the un-overlapped launch add to every "
+                                                     "metered launch; `achieved` / `frac` are RAW (floor included), "
+                                                     "roofline_kernels[*].frac_net_of_launch_floor takes it out",
+                "achieved_net_of_launch_floor": (g["flops"] / ((g["ms"] - g["launches"] * km.launch_floor_ms) * 1e-3) / 1e12
+                                                 if g["ms"] > g["launches"] * km.launch_floor_ms else None),
                 "clocks_during_instrumented_pass": clocks_prof}
 
     # ---- sustained: >= 5 s of back-to-back replays with their own clock record (what the path holds under the power cap)
@@ -588,6 +604,66 @@ def run_ours(args):
     emit_line(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def isolated_hbm_kernels(torch, ops, dev, hbm_gbs, reps=20, replays=9):
+    """LayerNorm / pool + PE / assembly at the shapes of one bench step, each as `reps` back-to-back launches in its own
+    CUDA graph; median over `replays` of (graph time / reps).  LayerNorm reads what the GEMM ahead of it has just written
+    (L2-resident in the step as in this loop); pool and assembly stream tensors larger than half the L2."""
+    lq, d, p = 1568, HIDDEN, 196
+    out = {}
+
+    def graph_us(fn):
+        fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(reps):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(replays):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3 / reps)
+            time.sleep(0.05)
+        return _median(ts)
+
+    def rec(us, nbytes, what):
+        gbs = nbytes / us / 1e3
+        return {"us_per_launch": us, "achieved": gbs, "unit": "GB/s", "peak": hbm_gbs, "frac": gbs / hbm_gbs,
+                "bytes_per_launch": nbytes, "what": what,
+                "method": f"{reps} back-to-back launches in a plain CUDA graph, median of {replays} replays (CUDA events)"}
+
+    bf = torch.bfloat16
+    x = torch.randn(lq, d, device=dev)
+    g_ = torch.randn(d, device=dev).to(bf)
+    b_ = torch.randn(d, device=dev).to(bf)
+    y = torch.empty(lq, d, device=dev, dtype=bf)
+    out["layernorm"] = rec(graph_us(lambda: ops.layernorm(x, g_, b_, 1e-12, out_dtype=bf, out=y)), lq * d * 6,
+                           f"{lq} x {d} fp32 pre-LN sum -> bf16")
+    xt = torch.randn(FRAMES, 729, d, device=dev).to(bf)
+    table = torch.randn(600, d, device=dev)
+    fidx = torch.arange(FRAMES, device=dev)
+    yp = ops.pool_pe(xt, side=27, pe_table=table, frame_idx=fidx)
+    out["pool_pe"] = rec(graph_us(lambda: ops.pool_pe(xt, side=27, pe_table=table, frame_idx=fidx)),
+                         xt.numel() * 2 + yp.numel() * 2, f"{FRAMES} frames 27x27 -> 14x14 + PE")
+    fine = torch.arange(0, FRAMES, max(1, FRAMES // 32), device=dev)[:32]
+    emb = torch.randn(2, d, device=dev).to(bf)
+    nl = torch.randn(d, device=dev).to(bf)
+    tab = torch.randn(1000, d, device=dev).to(bf)
+    pm = torch.arange(10, device=dev)
+    pf = torch.arange(9, device=dev)
+    n_mem = 2 * lq
+    rows = 10 + 1 + 9 + len(fine) * p + 1
+    seq = torch.zeros(rows + n_mem, d, device=dev, dtype=bf)
+    out["assemble"] = rec(graph_us(lambda: ops.assemble(seq, None, n_mem, yp, fine, p, emb, nl, tab, pm, pf)),
+                          2 * rows * d * 2, f"{rows} rows (memory tokens already in place)")
+    return out
 
 
 def bench_config3(torch, dist, M, synthetic, dev, rank, world, barrier, videos=8, frames=256, chunk=16, n_timed=5):
