@@ -78,11 +78,7 @@ MAVLM_API int mavlm_add_pe_fwd(const void* x, void* y, const float* pe_table, co
  *   C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]) (+ resid[M,N]) (+ addvec[N])
  * A, W, resid in `dtype`; bias/addvec in `dtype`; C in out_dtype (MAVLM_F32 allowed with bf16 inputs:
  * used for the pre-LayerNorm sum).  ld* are row strides in elements.  bias/resid/addvec may be NULL.
- * W is a module PARAMETER (an nn.Linear weight): the bf16 / fp16 kernel requests the first W slabs of each worker's
- * first tile before it waits for the kernel ahead of it on the stream (programmatic dependent launch), so W must not be
- * the output of one of this library's own launches still in flight on `stream` (a tensor torch or a memcpy produced is
- * fine: those complete before a dependent launch starts).  mavlm_gemm_ex is the entry for computed operands.  The
- * same holds for gamma / beta of mavlm_layernorm_fwd. */
+ */
 MAVLM_API int mavlm_gemm_bias_act_fwd(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* resid,
                             int64_t ldr, const void* addvec, void* C, int64_t ldc, int M, int N, int K, int act,
                             int dtype, int out_dtype, void* stream);
@@ -116,7 +112,10 @@ MAVLM_API int mavlm_gemm_fill_fwd(const mavlm_gemm_desc* primary, const mavlm_ge
 MAVLM_API int mavlm_cast_fwd(const void* x, void* y, int64_t n, int src_dtype, int dst_dtype, void* stream);
 
 /* ---- nn.LayerNorm over the last dim (MemoryController.py:24,28): y = (x-mean)/sqrt(var+eps)*g+b.
- * x in x_dtype (MAVLM_F32 pre-LN sums or `dtype`), gamma/beta and y in dtype. */
+ * x in x_dtype (MAVLM_F32 pre-LN sums or `dtype`), gamma/beta and y in dtype.  x 16-byte aligned (rows are fetched with
+ * cp.async.bulk).  gamma / beta are module PARAMETERS: the kernel stages them before it waits for the launch ahead of
+ * it on the stream (programmatic dependent launch), so they must not be the output of one of this library's own
+ * launches still in flight on `stream` (tensors written by torch kernels or copies are fine: those complete first). */
 MAVLM_API int mavlm_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, int rows, int dim, float eps,
                         int x_dtype, int dtype, void* stream);
 

@@ -10,7 +10,6 @@ int gemm_bf16_tc(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, 
                  void* C, long long ldc, int M, int N, int K, int act, int out_f32, cudaStream_t st, int half = 0,
                  const float* pe_table = nullptr, const long long* pe_idx = nullptr, int pe_tokens = 0);
 void gemm_tc_force_bn(int bn);
-void gemm_tc_early_weights(bool on);
 int gemm_fill_num_tiles(const mavlm_gemm_desc* d);
 int gemm_fill_range(const mavlm_gemm_desc* d, int t0, int t1, int half, cudaStream_t st);
 int gemm_fill_fwd(const mavlm_gemm_desc* prim, const mavlm_gemm_desc* fill, int fill_begin, int fill_avail_end,
@@ -148,13 +147,11 @@ MAVLM_API int mavlm_debug_force_gemm_bn(int bn) {
   return MAVLM_OK;
 }
 
-/* development knob: bit 4 (16) turns programmatic dependent launch off (A/B timing of the launch overlap); bit 5 (32)
-   turns the early weight loads of the forward GEMMs off (W slabs requested before griddepcontrol.wait); bit 6 (64)
+/* development knob: bit 4 (16) turns programmatic dependent launch off (A/B timing of the launch overlap); bit 6 (64)
    runs head_dim 448 attention on the CTA-pair kernel (attn_pair.cu: correct, measured slower, kept for A/B).  No flag
    changes what a kernel computes or stores. */
 MAVLM_API int mavlm_debug_set_flags(int flags) {
   pdl_force_off((flags & 16) != 0);
-  gemm_tc_early_weights((flags & 32) == 0);
   attn_use_pair_kernel((flags & 64) != 0);
   return MAVLM_OK;
 }

@@ -50,9 +50,6 @@ struct GemmTcParams {
   int fill_first_idle, fill_n_idle;
   // EPI = 1 (probability column sums, MemoryController.py:135): rows = keys, columns = queries of one (batch, head)
   // problem; the epilogue adds sum_q exp2(c * cs_scale_log2 - lse[q] * log2 e) of its columns to cs_out[b][key]
-  // B is a constant of the step (nn.Linear weights): the producer loads the first tile's first W slabs BEFORE
-  // griddepcontrol.wait, i.e. under the previous kernel's tail (only A depends on that kernel)
-  int early_b;
   const float* cs_lse;   // [batches][N] natural-log LSE of the attention forward
   float* cs_out;         // [outer][cs_out_stride] (summed over the inner = head problems and all query tiles)
   float cs_scale_log2;
@@ -178,30 +175,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      // ---- weights first: W does not depend on the previous kernel, so the first tile's first W slabs (up to a full
-      // ring) are requested before the wait -- their HBM latency hides under the previous kernel's tail.  The barrier
-      // of such a stage already expects the whole stage; the main loop below adds only the A box.
-      int early = 0;
-      if constexpr (!B_MN) {
-        const int t0 = p.tile_begin + worker;
-        if (p.early_b && t0 < p.tile_end) {
-          int m_blk, n_blk;
-          const int kblocks0 = (p.K + GEMM_BK - 1) / GEMM_BK;
-          gemm_tile_coords(t0, p.m_tiles, p.n_tiles, p.group_m, m_blk, n_blk);  // early_b implies one batch
-          const int n0 = n_blk * BN + static_cast<int>(rank) * Cfg::B_ROWS;
-          early = kblocks0 < STAGES ? kblocks0 : STAGES;
-          for (int kb = 0; kb < early; ++kb) {
-            uint8_t* b_dst = sB + kb * Cfg::B_BYTES;
-            if (CG == 2) {
-              if (rank == 0) mbar_expect_tx(&full[kb], 2 * Cfg::STAGE_BYTES);
-              tma_load_4d_pair(b_dst, &tmB, mapa_u32(smem_u32(&full[kb]), 0), kb * GEMM_BK, n0, 0, 0);
-            } else {
-              mbar_expect_tx(&full[kb], Cfg::STAGE_BYTES);
-              tma_load_4d(b_dst, &tmB, &full[kb], kb * GEMM_BK, n0, 0, 0);
-            }
-          }
-        }
-      }
       pdl_wait();
       for (int pi = 0; pi <= has2; ++pi) {
       MAVLM_GEMM_PROBLEM(pi);
@@ -216,13 +189,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* a_dst = sA + stage * Cfg::A_BYTES;
           uint8_t* b_dst = sB + stage * Cfg::B_BYTES;
-          if (early > 0) {  // first tile's first stages: W is already on its way and the barrier armed (see above)
-            --early;
-            if (CG == 2) tma_load_4d_pair(a_dst, ta, mapa_u32(smem_u32(&full[stage]), 0), kb * GEMM_BK, m0, bi, bo);
-            else tma_load_4d(a_dst, ta, &full[stage], kb * GEMM_BK, m0, bi, bo);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-            continue;
-          }
           if (CG == 2) {
             // both CTAs' boxes are credited to the leader's barrier, which expects the pair's bytes
             if (rank == 0) mbar_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
@@ -691,8 +657,6 @@ static int dispatch_bn(int bn, int cg, const CUtensorMap& tmA, const CUtensorMap
 // halve the W bytes each SM stages, narrow tiles quantise better.
 // Encoding of the choice (also the debug override): BN + 1000 * (CG - 1).
 static int g_force_bn = 0;
-static bool g_early_b = true;
-void gemm_tc_early_weights(bool on) { g_early_b = on; }
 int gemm_tc_pick_tile(int M, int N, int batches, bool pair_ok) {
   if (g_force_bn == -1) pair_ok = false;  // debug: heuristic restricted to single-CTA tiles
   else if (g_force_bn) return (g_force_bn >= 1000 && !pair_ok) ? g_force_bn - 1000 : g_force_bn;
@@ -809,7 +773,6 @@ int gemm_bf16_tc(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, 
   p.M = M; p.N = N; p.K = K;
   p.bias = bias; p.resid = resid; p.ldr = ldr; p.addvec = addvec;
   p.C = C; p.ldc = ldc; p.act = act; p.out_f32 = out_f32;
-  p.early_b = g_early_b ? 1 : 0;  // W is an nn.Linear weight: nothing on the stream ahead of this launch writes it
   return gemm_tc_general(A, lda, false, W, ldw, false, p, 1, 1, nullptr, st);
 }
 

@@ -456,7 +456,7 @@ def fam_ab():
         return e0.elapsed_time(e1) / n
 
     variants = {}
-    for name, flags in (("pdl", 0), ("no-early-w", 32), ("no-pdl", 16)):
+    for name, flags in (("pdl", 0), ("no-pdl", 16)):
         lib.mavlm_debug_set_flags(flags)
         variants[name] = GraphedPipeline(pipe, 1, 64)       # the launch attributes are baked in at capture time
     lib.mavlm_debug_set_flags(0)
