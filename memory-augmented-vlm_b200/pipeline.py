@@ -146,8 +146,12 @@ class VisualMemoryPipeline(nn.Module):
     @torch.no_grad()
     def memory_forward(self, z: torch.Tensor, *, seq_out: Optional[torch.Tensor] = None, drop_frames: bool = False,
                        return_states: bool = True, boundaries: Optional[Sequence[int]] = None,
-                       piece_frames: Optional[int] = None, before_piece=None) -> Dict[str, torch.Tensor]:
+                       piece_frames: Optional[int] = None, before_piece=None,
+                       frames_assembled: bool = False) -> Dict[str, torch.Tensor]:
         """z: pooled + PE'd frames [B, F, P, D].  Runs the recurrence, the fuser and the assembly.
+        `frames_assembled`: the caller has already run `assemble_frames(seq_out, z)` (every row of the sequence that
+        does not hold a memory token: they depend on z only, so a host-streaming front end can send them back while the
+        recurrence runs); only the memory-token rows are written here.
         `boundaries`: chunk boundaries [0, ..., F] replacing the uniform scheduler of llava_arch.py:528-534, e.g. the
         scene-based ones of `legacy.adjusted_segment(legacy.frame_means(z[0]))` (segment.py:52-128).
         `piece_frames` / `before_piece`: the frames arrive in pieces of `piece_frames` frames (a multiple of the chunk
@@ -290,8 +294,9 @@ class VisualMemoryPipeline(nn.Module):
             # whatever the tails did not absorb: the remaining fuser tiles (each launch takes a ready filler along)
             for w_ in fuse_work:
                 w_.run(fillers=[o_ for o_ in fuse_work if not o_.done])
-            ops.assemble(seq_out[0], None, n_keep * lq, z[0], fine_idx, p, emb, self.image_newline.detach(),
-                         self.embed_tokens.weight.detach(), pm_ids, pf_ids, drop_frames)
+            if not frames_assembled:
+                ops.assemble(seq_out[0], None, n_keep * lq, z[0], fine_idx, p, emb, self.image_newline.detach(),
+                             self.embed_tokens.weight.detach(), pm_ids, pf_ids, drop_frames)
             out = {"sequence": seq_out}
             if return_states:
                 if first == 0:
@@ -300,6 +305,8 @@ class VisualMemoryPipeline(nn.Module):
                     order = [(first + i) % cap for i in range(n_keep)]
                     out["states"] = torch.cat([ring_states[:, s_:s_ + 1] for s_ in order], dim=1)
             return out
+        if isinstance(fz, MemoryFuser) and frames_assembled:
+            raise ValueError("mavlm: frames_assembled needs the MLP fuser (the encoder variant's tokens go through the assembly kernel)")
         if isinstance(fz, MemoryFuser):
             # encoder-variant fuser (MemoryFuser.py; the mode llava_arch.py:137-143 keeps commented out): self-attention
             # inside each 196-token memory slot, over the cached states oldest first (llava_arch.py:545-546)
@@ -331,8 +338,9 @@ class VisualMemoryPipeline(nn.Module):
                 dst = seq_out[bi, npm + i0 * lq: npm + (i0 + ln) * lq]
                 ops.linear(hidden[bi, s0:s0 + ln].reshape(ln * lq, 4 * d), fz[2].weight, fz[2].bias, addvec=emb[0],
                            out=dst)
-            ops.assemble(seq_out[bi], None, n_keep * lq, z[bi], fine_idx, p, emb, self.image_newline.detach(),
-                         self.embed_tokens.weight.detach(), pm_ids, pf_ids, drop_frames)
+            if not frames_assembled:
+                ops.assemble(seq_out[bi], None, n_keep * lq, z[bi], fine_idx, p, emb, self.image_newline.detach(),
+                             self.embed_tokens.weight.detach(), pm_ids, pf_ids, drop_frames)
         out = {"sequence": seq_out}
         if return_states:
             if first == 0:
@@ -341,6 +349,25 @@ class VisualMemoryPipeline(nn.Module):
                 order = [(first + i) % cap for i in range(n_keep)]
                 out["states"] = torch.cat([ring_states[:, s_:s_ + 1] for s_ in order], dim=1)
         return out
+
+    @torch.no_grad()
+    def assemble_frames(self, seq_out: torch.Tensor, z: torch.Tensor, *, drop_frames: bool = False) -> int:
+        """Every row of the assembled sequence [B, L, D] that is NOT a memory token -- both prompts, the newlines and
+        the fine frames + token_type_embedding[1] (llava_arch.py:548-554, 613-629) -- from the pooled frames z
+        [B, F, P, D] alone (uniform scheduler).  Returns the number of memory-token rows, which
+        `memory_forward(..., seq_out=seq_out, frames_assembled=True)` fills in."""
+        rmt = self.recurrent_memory_transformer
+        b, f, p, d = z.shape
+        lq = rmt.num_memory_tokens * p
+        n_keep = min(len(uniform_segment_variant(f, self.chunk_size)) - 1, rmt.cache_size)
+        self.prepare_constants(f, z.device)
+        fine_idx = self._consts[("fine", f, str(z.device))]
+        pm_ids, pf_ids = self._const_ids(z.device)
+        emb = self.token_type_embedding.weight.detach()
+        for bi in range(b):
+            ops.assemble(seq_out[bi], None, n_keep * lq, z[bi], fine_idx, p, emb, self.image_newline.detach(),
+                         self.embed_tokens.weight.detach(), pm_ids, pf_ids, drop_frames)
+        return n_keep * lq
 
     @torch.no_grad()
     def forward(self, tower_tokens: torch.Tensor, frame_idx: torch.Tensor, *, validate: bool = True,
@@ -536,59 +563,156 @@ class GraphedPipeline:
         return self.out
 
 
+class _StreamSlot:
+    """One of the two buffer sets of HostStreamEncoder: static input / pooled-frame / sequence buffers and the CUDA
+    graphs that connect them -- one per input PIECE (projector + pool + PE of that piece's frames) and one for the
+    recurrence + fuser -- so that ordinary stream events can sit between them (piece j's graph waits only for piece j's
+    H2D copy; the frame rows of the sequence are assembled and on their way back before the recurrence starts)."""
+
+    def __init__(self, pipe: VisualMemoryPipeline, batch: int, frames: int, pieces: int):
+        p0 = pipe.mm_projector[0].weight
+        dev, dtype = p0.device, p0.dtype
+        rmt = pipe.recurrent_memory_transformer
+        self.pipe, self.dev, self.batch, self.frames = pipe, dev, batch, frames
+        n = batch * frames
+        self.x = torch.zeros((n, pipe.side * pipe.side, p0.shape[1]), dtype=dtype, device=dev)
+        self.idx = torch.zeros((n,), dtype=torch.int64, device=dev)
+        self.z = torch.zeros((n, rmt.patch_size, rmt.hidden_size), dtype=dtype, device=dev)
+        n_keep = min(len(uniform_segment_variant(frames, pipe.chunk_size)) - 1, rmt.cache_size)
+        self.n_mem_rows = n_keep * rmt.num_memory_tokens * rmt.patch_size
+        self.head_rows = len(MEMORY_PROMPT_IDS) + self.n_mem_rows       # memory prompt + memory tokens: known last
+        seq_len = pipe.sequence_length(n_keep, min(pipe.max_fine_frames, frames))
+        self.seq = torch.zeros((batch, seq_len, rmt.hidden_size), dtype=dtype, device=dev)
+        step = -(-n // pieces)
+        self.ranges = [(i, min(n, i + step)) for i in range(0, n, step)]
+        self.capture()
+
+    def weights_key(self):
+        pipe = self.pipe
+        ts = [*pipe.parameters(), *pipe.buffers(), pipe.image_newline]
+        return tuple((t.data_ptr(), t._version) for t in ts)
+
+    def _encode(self, r0: int, r1: int) -> None:
+        self.pipe.encode_frames(self.x[r0:r1], self.idx[r0:r1], validate=False, out=self.z[r0:r1])
+
+    def _z4(self) -> torch.Tensor:
+        return self.z.reshape(self.batch, self.frames, *self.z.shape[1:])
+
+    def assemble(self) -> None:                                         # one small kernel per video: launched eagerly
+        self.pipe.assemble_frames(self.seq, self._z4())
+
+    def _recur(self) -> None:
+        self.pipe.memory_forward(self._z4(), seq_out=self.seq, return_states=False, frames_assembled=True)
+
+    def capture(self) -> None:
+        dev = self.dev
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):                               # warm-up: packs weights, fills constant caches
+                for _ in range(2):
+                    for (r0, r1) in self.ranges:
+                        self._encode(r0, r1)
+                    self.assemble()
+                    self._recur()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.g_piece = []
+            for (r0, r1) in self.ranges:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._encode(r0, r1)
+                self.g_piece.append(g)
+            self.g_recur = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_recur):
+                self._recur()
+        self.key = self.weights_key()
+
+
 class HostStreamEncoder:
-    """Host-buffer front end: pinned host tower tokens in, pinned host sequence out, with the H2D copy of
-    video i+1 and the D2H copy of result i-1 overlapped with the graph replay of video i on three
-    streams (copy-in / compute / copy-out).  Two captured graphs take turns, so the copies go straight into / out of
-    a graph's static buffers (no staging copy on the compute stream): while graph A computes, video i+1 lands in
-    graph B's input and result i-1 leaves graph B's output.  This is the public end-to-end call bench.py's `e2e`
+    """Host-buffer front end: pinned host tower tokens in, pinned host sequence out, on three streams (copy-in /
+    compute / copy-out) and two buffer sets that take turns, so that the H2D copy of video i+1 and the D2H copy of
+    result i-1 overlap the compute of video i.  Inside one video the copies are pipelined as well (`pieces`, default
+    4): the input arrives in pieces of frames and each piece's projector graph waits only for its own piece (the first
+    kernel starts after a quarter of the 107 MB, not all of it), and the rows of the sequence that depend on the frames
+    alone -- prompts, newlines, fine frames: two thirds of it -- are assembled right after the projector and copied back
+    WHILE the recurrence runs; only the memory-token rows leave after the last kernel.  Same kernels, same results bit
+    for bit as `pipe(...)`; a single video's host-to-host latency drops from copy + compute + copy to about a quarter
+    of the input copy + compute + a third of the output copy.  This is the public end-to-end call bench.py's `e2e`
     times."""
 
-    def __init__(self, pipe: VisualMemoryPipeline, batch: int, frames: int):
-        self.gs = [pipe.graphed(batch, frames), GraphedPipeline(pipe, batch, frames)]
-        self.g = self.gs[0]
-        dev = self.g.x.device
+    def __init__(self, pipe: VisualMemoryPipeline, batch: int, frames: int, pieces: int = 4):
+        if isinstance(pipe.memory_fuser, MemoryFuser):
+            raise ValueError("mavlm: HostStreamEncoder needs the MLP fuser (llava_arch.py:132-136)")
+        n = batch * frames
+        pieces = max(1, min(int(pieces), n))
+        self.slots = [_StreamSlot(pipe, batch, frames, pieces) for _ in range(2)]
+        dev = self.slots[0].dev
         self.dev = dev
+        self.pipe = pipe
         self.s_in, self.s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-        self.ev_in = [torch.cuda.Event(), torch.cuda.Event()]
-        self.ev_done = [torch.cuda.Event(), torch.cuda.Event()]         # replay finished: input consumed, output ready
-        self.ev_out_free = [torch.cuda.Event(), torch.cuda.Event()]     # D2H of the output finished
+        self.ev_piece = [[torch.cuda.Event() for _ in sl.ranges] for sl in self.slots]
+        self.ev_x_free = [torch.cuda.Event(), torch.cuda.Event()]       # the projector graphs have read the slot's input
+        self.ev_frames = [torch.cuda.Event(), torch.cuda.Event()]       # frame rows of the sequence are assembled
+        self.ev_done = [torch.cuda.Event(), torch.cuda.Event()]         # memory-token rows written: sequence complete
+        self.ev_out_free = [torch.cuda.Event(), torch.cuda.Event()]     # both D2H copies of the slot's sequence finished
         self._used = [False, False]
         self._k = 0
-        self._idx_synced = False
+        self._idx_set = False
 
     @torch.no_grad()
-    def submit(self, host_tokens: torch.Tensor, frame_idx: torch.Tensor, host_out: torch.Tensor) -> None:
-        """Enqueue one batch: host_tokens (pinned) -> device -> path -> host_out (pinned).  Asynchronous;
-        call synchronize() before reading host_out."""
+    def submit(self, host_tokens: torch.Tensor, frame_idx: Optional[torch.Tensor], host_out: torch.Tensor) -> None:
+        """Enqueue one batch: host_tokens (pinned) -> device -> path -> host_out (pinned, [B, L, D]).  Asynchronous;
+        call synchronize() before reading host_out.  frame_idx None = keep the indices of the previous call
+        (initially 0 .. F-1 per video)."""
         with torch.cuda.device(self.dev):
             self._submit(host_tokens, frame_idx, host_out)
 
-    def _submit(self, host_tokens: torch.Tensor, frame_idx: torch.Tensor, host_out: torch.Tensor) -> None:
+    def _submit(self, host_tokens: torch.Tensor, frame_idx: Optional[torch.Tensor], host_out: torch.Tensor) -> None:
         k = self._k
-        g = self.gs[k]
+        sl = self.slots[k]
         cur = torch.cuda.current_stream(self.dev)
+        if sl.weights_key() != sl.key:                                  # a weight changed since the capture
+            torch.cuda.synchronize(self.dev)
+            for s_ in self.slots:
+                s_.capture()
+        if frame_idx is not None:                                       # new indices go to both slots (stream-ordered
+            self.pipe.positional_encoding.validate(frame_idx)           # on the compute stream, like every replay)
+            for s_ in self.slots:
+                s_.idx.copy_(frame_idx.reshape(s_.idx.shape), non_blocking=True)
+            self._idx_set = True
+        elif not self._idx_set:
+            per_video = torch.arange(sl.frames, dtype=torch.int64).repeat(sl.batch)
+            for s_ in self.slots:
+                s_.idx.copy_(per_video, non_blocking=True)
+            self._idx_set = True
+        src = host_tokens.reshape(sl.x.shape)
         with torch.cuda.stream(self.s_in):
             if self._used[k]:
-                self.s_in.wait_event(self.ev_done[k])                   # this graph's previous replay has read its input
-            g.x.copy_(host_tokens.reshape(g.x.shape), non_blocking=True)
-            self.ev_in[k].record(self.s_in)
-        cur.wait_event(self.ev_in[k])
+                self.s_in.wait_event(self.ev_x_free[k])                 # the slot's previous projector pass has read its input
+            for j, (r0, r1) in enumerate(sl.ranges):
+                sl.x[r0:r1].copy_(src[r0:r1], non_blocking=True)
+                self.ev_piece[k][j].record(self.s_in)
         if self._used[k]:
-            cur.wait_event(self.ev_out_free[k])                         # ... and its previous output has left
-        if frame_idx is not None:                                       # new indices go to both graphs
-            self.gs[0].pipe.positional_encoding.validate(frame_idx)
-            for gg in self.gs:
-                gg.idx.copy_(frame_idx.reshape(gg.idx.shape), non_blocking=True)
-            self._idx_synced = True
-        elif not self._idx_synced:                                      # None = keep the indices of pipe.graphed(...)
-            self.gs[1].idx.copy_(self.gs[0].idx, non_blocking=True)
-            self._idx_synced = True
-        out = g(None, None)
+            cur.wait_event(self.ev_out_free[k])                         # ... and its previous sequence has left
+        for j, g in enumerate(sl.g_piece):
+            cur.wait_event(self.ev_piece[k][j])
+            g.replay()
+        self.ev_x_free[k].record(cur)
+        sl.assemble()
+        self.ev_frames[k].record(cur)
+        sl.g_recur.replay()
         self.ev_done[k].record(cur)
+        dst = host_out.reshape(sl.seq.shape)
         with torch.cuda.stream(self.s_out):
-            self.s_out.wait_event(self.ev_done[k])
-            host_out.copy_(out["sequence"], non_blocking=True)
+            self.s_out.wait_event(self.ev_frames[k])
+            if sl.batch == 1:                                           # contiguous row ranges: two plain copies
+                dst[0, sl.head_rows:].copy_(sl.seq[0, sl.head_rows:], non_blocking=True)
+                self.s_out.wait_event(self.ev_done[k])
+                dst[0, :sl.head_rows].copy_(sl.seq[0, :sl.head_rows], non_blocking=True)
+            else:
+                self.s_out.wait_event(self.ev_done[k])
+                dst.copy_(sl.seq, non_blocking=True)
             self.ev_out_free[k].record(self.s_out)
         self._used[k] = True
         self._k = k ^ 1

@@ -741,3 +741,78 @@ def test_frame_sharded_encoder_single_process_equals_the_plain_path():
     assert torch.equal(again["sequence"], plain["sequence"])
     with pytest.raises(ValueError):
         enc(x, torch.full((18,), 600))                                           # PE index check survives
+
+
+# ------------------------------------------------------------------------------------------------
+# bandwidth-bound kernels at shapes that exercise their persistent loops
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d", [8, 64, 896, 3584, 4096])
+def test_layernorm_op_row_counts_dims_and_dtypes(d):
+    """nn.LayerNorm (MemoryController.py:24,28; eps = 1e-12) against a float64 evaluation of the same formula:
+    one CTA per SM and 12 warps per CTA, so 1 / 77 rows leave warps idle, 1777 gives some warps a second row and 5000
+    makes every warp loop (its row buffer is refilled by the bulk copy engine while the previous row is normalised).
+    A constant row (variance exactly 0) must come out as beta: the two-pass variance keeps eps = 1e-12 meaningful."""
+    g32 = torch.randn(d, device=DEV)
+    b32 = torch.randn(d, device=DEV)
+    for rows in (1, 77, 1777, 5000):
+        x = torch.randn(rows, d, device=DEV) * 3 + 1
+        x[rows // 2] = 2.5                                               # constant row
+        for idt, odt, tol in ((torch.float32, torch.float32, FP32_TOL), (torch.float32, torch.bfloat16, 8e-3),
+                              (torch.bfloat16, torch.bfloat16, 8e-3), (torch.float32, torch.float16, 1e-3),
+                              (torch.float16, torch.float16, 1e-3)):
+            if odt != torch.float32 and d % 8:
+                continue
+            xin, g, b = x.to(idt), g32.to(odt), b32.to(odt)
+            ref = torch.nn.functional.layer_norm(xin.double(), (d,), g.double(), b.double(), 1e-12)
+            ref[rows // 2] = b.double()                                  # (x - mean) = 0 exactly in either precision
+            y = ops.layernorm(xin, g, b, 1e-12, out_dtype=odt)
+            assert y.dtype == odt and y.shape == xin.shape
+            assert err(y, ref.cpu().numpy()) < tol, (rows, d, idt, odt)
+            out = torch.empty_like(y)
+            assert ops.layernorm(xin, g, b, 1e-12, out_dtype=odt, out=out) is out and torch.equal(out, y)
+
+
+def test_assemble_with_memory_rows_already_in_place():
+    """Token assembly (llava_arch.py:613-629, 705-731) when the fuser GEMM's epilogue has already written the memory
+    tokens: the launch covers only the other rows and must leave the memory rows untouched; bit-exact (one bf16
+    rounding of frame + type embedding, as `x + emb` in the reference)."""
+    d, p = 256, 196
+    dt = torch.bfloat16
+    frames = torch.randn(40, p, d, device=DEV).to(dt)
+    fine = torch.tensor([0, 3, 9, 39], device=DEV)
+    emb = torch.randn(2, d, device=DEV).to(dt)
+    nl = torch.randn(d, device=DEV).to(dt)
+    tab = torch.randn(5000, d, device=DEV).to(dt)
+    pm = torch.tensor([198, 374, 264, 1550, 1159, 1212, 315, 279, 2766, 25], device=DEV)
+    pf = torch.tensor([948, 525, 4887, 912, 1408, 504, 279, 2766, 25], device=DEV)
+    n_mem = 3 * 8 * p
+    mem_rows = torch.randn(n_mem, d, device=DEV).to(dt)
+    n = 10 + n_mem + 1 + 9 + 4 * p + 1
+    seq = torch.zeros(n, d, device=DEV, dtype=dt)
+    seq[10:10 + n_mem] = mem_rows
+    ops.assemble(seq, None, n_mem, frames, fine, p, emb, nl, tab, pm, pf)
+    ref = torch.cat([tab[pm], mem_rows, nl[None], tab[pf], (frames[fine] + emb[1]).reshape(-1, d), nl[None]])
+    assert torch.equal(seq, ref)
+    seq2 = torch.zeros_like(seq)                                         # and with the memory rows passed in
+    ops.assemble(seq2, mem_rows, n_mem, frames, fine, p, emb, nl, tab, pm, pf)
+    ref2 = torch.cat([tab[pm], mem_rows + emb[0], nl[None], tab[pf], (frames[fine] + emb[1]).reshape(-1, d), nl[None]])
+    assert torch.equal(seq2, ref2)
+
+
+@pytest.mark.parametrize("batch,frames,pieces", [(1, 32, 1), (1, 32, 3), (2, 16, 4), (1, 40, 4)])
+def test_host_streaming_pieces_and_batches_match_eager(batch, frames, pieces):
+    """HostStreamEncoder: input copied in `pieces` pieces (ragged last piece, pieces that straddle videos), frame rows
+    of the sequence sent back ahead of the memory rows -- bit-identical to the eager path, on both buffer sets, and
+    with a ragged last chunk (40 frames, chunk 16)."""
+    pipe, _ = synthetic.build_pipeline(896, 1152, dtype=torch.bfloat16, chunk_size=16, device=DEV)
+    xs = [synthetic.synthetic_tower_tokens(batch, frames, 1152, seed=s, pin=True) for s in (1, 2, 3)]
+    idx = (torch.arange(frames) * 2)[None].repeat(batch, 1)
+    want = [pipe(x.to(DEV), idx)["sequence"].cpu() for x in xs]
+    enc = M.HostStreamEncoder(pipe, batch, frames, pieces=pieces)
+    outs = [torch.empty(want[0].shape, dtype=want[0].dtype, pin_memory=True) for _ in xs]
+    enc.submit(xs[0], idx, outs[0])
+    enc.submit(xs[1], None, outs[1])
+    enc.submit(xs[2], None, outs[2])
+    enc.synchronize()
+    for o, w in zip(outs, want):
+        assert torch.equal(o, w)

@@ -28,10 +28,11 @@ for line in sass.split("\n"):
         total[m.group(1)] += 1
 n_fn = len(re.findall(r"Function : ", sass))
 print(f"cuobjdump -sass memory-augmented-vlm_b200/libmavlm.so   ({n_fn} sm_100a functions)")
-cols = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAPF", "SYNCS", "MUFU.EX2", "HMMA", "HGMMA"]
+cols = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "MUFU.EX2", "HMMA", "HGMMA"]
 print(f"{'kernel family':<20}" + "".join(f"{c:>10}" for c in cols))
 for f in ("gemm_tc_kernel", "attn_tc_kernel", "attn_pair_kernel", "other kernels"):
     print(f"{f:<20}" + "".join(f"{per[f][c]:>10}" for c in cols))
 print(f"{'TOTAL':<20}" + "".join(f"{total[c]:>10}" for c in cols))
 print("\nUTCHMMA = tcgen05.mma kind::f16 (tmem[...] operand form = TS mode), UTCBAR = tcgen05.commit, LDTM / STTM = tcgen05.ld / st,")
-print("UTMALDG / UTMASTG = cp.async.bulk.tensor load / store (TMA), SYNCS = mbarrier ops.  HMMA / HGMMA (mma.sync / wgmma): none.")
+print("UTMALDG / UTMASTG = cp.async.bulk.tensor load / store (TMA), UBLKCP = cp.async.bulk (1-D bulk copy: LayerNorm row staging),")
+print("SYNCS = mbarrier ops.  HMMA / HGMMA (mma.sync / wgmma): none.")
