@@ -632,16 +632,17 @@ class _StreamSlot:
 class HostStreamEncoder:
     """Host-buffer front end: pinned host tower tokens in, pinned host sequence out, on three streams (copy-in /
     compute / copy-out) and two buffer sets that take turns, so that the H2D copy of video i+1 and the D2H copy of
-    result i-1 overlap the compute of video i.  Inside one video the copies are pipelined as well (`pieces`, default
-    4): the input arrives in pieces of frames and each piece's projector graph waits only for its own piece (the first
-    kernel starts after a quarter of the 107 MB, not all of it), and the rows of the sequence that depend on the frames
-    alone -- prompts, newlines, fine frames: two thirds of it -- are assembled right after the projector and copied back
-    WHILE the recurrence runs; only the memory-token rows leave after the last kernel.  Same kernels, same results bit
-    for bit as `pipe(...)`; a single video's host-to-host latency drops from copy + compute + copy to about a quarter
-    of the input copy + compute + a third of the output copy.  This is the public end-to-end call bench.py's `e2e`
-    times."""
+    result i-1 overlap the compute of video i.  Inside one video the copies are pipelined as well: the input arrives in
+    `pieces` pieces of frames and each piece's projector graph waits only for its own piece (the first kernel starts
+    after half of the 107 MB, not all of it), and the rows of the sequence that depend on the frames alone -- prompts,
+    newlines, fine frames: two thirds of it -- are assembled right after the projector and copied back WHILE the
+    recurrence runs; only the memory-token rows leave after the last kernel.  Same kernels, same results bit for bit as
+    `pipe(...)`.  Measured on B200 (tools/e2e_gap.py, OV-7B, 64 frames): one video host to host 7.4 ms serial -> 6.1 ms
+    with 4 pieces; in a stream of videos 4 pieces cost the projector 0.14 ms per video (its second GEMM runs on 3136
+    rows: 2.5 waves) and save 1.4 ms once per stream, 2 pieces cost 0.01 ms and save 0.95 ms: hence the default of 2.
+    This is the public end-to-end call bench.py's `e2e` times."""
 
-    def __init__(self, pipe: VisualMemoryPipeline, batch: int, frames: int, pieces: int = 4):
+    def __init__(self, pipe: VisualMemoryPipeline, batch: int, frames: int, pieces: int = 2):
         if isinstance(pipe.memory_fuser, MemoryFuser):
             raise ValueError("mavlm: HostStreamEncoder needs the MLP fuser (llava_arch.py:132-136)")
         n = batch * frames
