@@ -64,9 +64,10 @@ def run_point(batch, frames, chunk, slots, iters=3, peaks=None):
     kernels = km.roofline_kernels(peaks["tflops_sustained"], peaks) if peaks else []
     res = {"batch": batch, "frames": frames, "chunk": chunk, "slots": slots, "lq": 196 * slots, "ms": ms,
            "frames_per_s": batch * frames / ms * 1e3, "algorithmic_tflops": gf / ms, "gflop": gf,
-           "launches": len(km.recs),
+           "launches": len(km.recs), "instrumentation_launch_floor_us": 1e3 * km.launch_floor_ms,
            "kernels": [{"kernel": k["kernel"].split(" ")[0], "bound": k["bound"], "share": k["share_of_step"],
-                        "achieved": k["achieved"], "unit": k["unit"], "frac": k["frac"]} for k in kernels]}
+                        "achieved": k["achieved"], "unit": k["unit"], "frac": k["frac"],
+                        "frac_net_of_launch_floor": k.get("frac_net_of_launch_floor")} for k in kernels]}
     del pipe, z, graph, out, km
     torch.cuda.empty_cache()
     return res
@@ -99,7 +100,8 @@ def main():
         json.dump({"peaks": peaks, "points": out}, fh, indent=1)
     print(f"{'cfg':>3} {'B':>2} {'F':>5} {'C':>3} {'M':>4} {'ms':>9} {'frames/s':>10} {'TFLOP/s':>8} {'frac':>5}")
     for r in out:
-        per = "  ".join(f"{k['kernel'].replace('_kernel', '')}:{k['frac']:.2f}({k['share']:.0%})" for k in r["kernels"])
+        per = "  ".join(f"{k['kernel'].replace('_kernel', '')}:{k['frac']:.2f}/{(k['frac_net_of_launch_floor'] or 0):.2f}({k['share']:.0%})"
+                        for k in r["kernels"])   # raw / net of the instrumentation's per-launch floor (share of the step)
         print(f"{r['config']:>3} {r['batch']:>2} {r['frames']:>5} {r['chunk']:>3} {r['slots']:>4} {r['ms']:>9.2f} "
               f"{r['frames_per_s']:>10.0f} {r['algorithmic_tflops']:>8.0f} {r['frac_of_peak']:>5.2f}   {per}")
 
