@@ -53,7 +53,7 @@ def drain():
     enc.s_in.synchronize()
 
 
-def timed(fn, n=20):
+def timed(fn, n=40):
     for _ in range(3):
         fn()
     drain()
@@ -70,8 +70,23 @@ def timed(fn, n=20):
     return (time.perf_counter() - t0) * 1e3 / n
 
 
-variants = [("one graph", dev_step), ("slot graphs, no copies", slot_step), ("copies only", copy_step), ("e2e", e2e_step)]
-for rnd in range(4):
-    order = variants[rnd % 4:] + variants[:rnd % 4]
+def slot_h2d_step():                                                 # compute + a concurrent H2D into a SPARE buffer
+    with torch.cuda.stream(enc.s_in):
+        spare_x.copy_(x_host.reshape(spare_x.shape), non_blocking=True)
+    slot_step()
+
+
+def slot_d2h_step():                                                 # compute + a concurrent D2H from a SPARE buffer
+    with torch.cuda.stream(enc.s_out):
+        out_host.copy_(spare_seq, non_blocking=True)
+    slot_step()
+
+
+spare_x = torch.zeros_like(sl.x)
+spare_seq = torch.zeros_like(sl.seq)
+variants = [("one graph", dev_step), ("slot graphs, no copies", slot_step), ("copies only", copy_step), ("e2e", e2e_step),
+            ("compute + H2D", slot_h2d_step), ("compute + D2H", slot_d2h_step)]
+for rnd in range(6):
+    order = variants[rnd % 6:] + variants[:rnd % 6]
     res = {name: timed(fn) for name, fn in order}
     print(f"round {rnd}: " + "   ".join(f"{name}: {res[name]:.3f} ms" for name, _ in variants), flush=True)
