@@ -15,7 +15,10 @@ Prints ONE JSON line on rank 0.  `value` is device-resident throughput, `e2e` is
 through the public API with pinned HOST buffers (H2D of the tower tokens and D2H of the assembled
 sequence inside the timed region; `e2e.copy_only` times the same copies without the compute),
 `roofline` is the dominant kernel (tcgen05 GEMM) and `roofline_kernels` every kernel family of the
-step (medians over >= 100 instrumented graph replays, CUDA events between the kernels), `sustained`
+step (medians over >= 100 instrumented graph replays, CUDA events between the kernels: RAW numbers,
+with `instrumentation_launch_floor_us` -- what the event nodes add to every launch -- reported beside
+them, `frac_net_of_launch_floor` per kernel, and the bandwidth-bound kernels also timed `isolated`),
+`e2e.single_video_host_to_host_ms` one submit + synchronize on an idle GPU, `sustained`
 is a >= 5 s replay loop with its own clock record, `config3` is BASELINE config[2] (8 videos x 256
 frames, 16-frame chunks, sharded 8/N per rank, NCCL all-gather of the assembled sequences inside the
 timed region), `frame_sharded` (N > 1) one 1024-frame video with the frame-sharded pre-pass and the
