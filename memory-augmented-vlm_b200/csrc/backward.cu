@@ -377,6 +377,61 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const T* __restrict__ dy, 
   }
 }
 
+// bf16, n % 8 == 0, 16-byte aligned: 8 elements per thread and iteration (the scalar kernels above move 64 bytes per
+// warp load: 0.59 of the copy bandwidth on the 12 544 x 14 336 MLP activations of a training step).  Same arithmetic
+// per element as the scalar kernels.
+__device__ __forceinline__ float act_fwd_one(float v, int act) {
+  return act == MAVLM_ACT_GELU_ERF ? gelu_erf_f(v) : (act == MAVLM_ACT_RELU ? fmaxf(v, 0.f) : v);
+}
+__device__ __forceinline__ float act_bwd_one(float g, float r, int act) {
+  if (act == MAVLM_ACT_RELU) return r > 0.f ? g : 0.f;
+  if (act == MAVLM_ACT_GELU_ERF) {
+    const float cdf = 0.5f * (1.f + erff(r * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * __expf(-0.5f * r * r);
+    return g * (cdf + r * pdf);
+  }
+  return g;
+}
+__device__ __forceinline__ void unpack8_bf16(const uint4& t, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8_bf16(const float (&v)[8]) {
+  uint4 t;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  return t;
+}
+__global__ void __launch_bounds__(256) act_fwd_bf16_vec_kernel(const uint4* __restrict__ x, uint4* __restrict__ y,
+                                                               long long nvec, int act) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float v[8];
+    unpack8_bf16(x[i], v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = act_fwd_one(v[k], act);
+    y[i] = pack8_bf16(v);
+  }
+}
+__global__ void __launch_bounds__(256) act_bwd_bf16_vec_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ ref,
+                                                               uint4* __restrict__ dx, long long nvec, int act) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float g[8], r[8];
+    unpack8_bf16(dy[i], g);
+    unpack8_bf16(ref[i], r);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g[k] = act_bwd_one(g[k], r[k], act);
+    dx[i] = pack8_bf16(g);
+  }
+}
+
 // ---- attention backward, fp32 tier: elementwise steps over the materialised [B*H*Lq, Lk] score workspace ----
 // s[row, :] = exp(s[row, :] - lse[row])
 __global__ void __launch_bounds__(256) probs_from_lse_kernel(float* __restrict__ s, const float* __restrict__ lse, int n) {
@@ -548,7 +603,9 @@ int mavlm_act_fwd(const void* x, void* y, int64_t n, int act, int dtype, void* s
   MAVLM_REQUIRE(dtype == MAVLM_F32 || dtype == MAVLM_BF16, MAVLM_E_INVALID, "act_fwd: bad dtype");
   if (n == 0) return MAVLM_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == MAVLM_F32)
+  if (dtype == MAVLM_BF16 && n % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0)
+    act_fwd_bf16_vec_kernel<<<ew_grid(n / 8), 256, 0, st>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y), n / 8, act);
+  else if (dtype == MAVLM_F32)
     act_fwd_kernel<float><<<ew_grid(n), 256, 0, st>>>(static_cast<const float*>(x), static_cast<float*>(y), n, act);
   else
     act_fwd_kernel<__nv_bfloat16><<<ew_grid(n), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x),
@@ -561,7 +618,11 @@ int mavlm_act_bwd(const void* dy, const void* ref, void* dx, int64_t n, int act,
   MAVLM_REQUIRE(dtype == MAVLM_F32 || dtype == MAVLM_BF16, MAVLM_E_INVALID, "act_bwd: bad dtype");
   if (n == 0) return MAVLM_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == MAVLM_F32)
+  if (dtype == MAVLM_BF16 && n % 8 == 0 &&
+      ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(ref) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0)
+    act_bwd_bf16_vec_kernel<<<ew_grid(n / 8), 256, 0, st>>>(static_cast<const uint4*>(dy), static_cast<const uint4*>(ref),
+                                                            static_cast<uint4*>(dx), n / 8, act);
+  else if (dtype == MAVLM_F32)
     act_bwd_kernel<float><<<ew_grid(n), 256, 0, st>>>(static_cast<const float*>(dy), static_cast<const float*>(ref),
                                                       static_cast<float*>(dx), n, act);
   else
